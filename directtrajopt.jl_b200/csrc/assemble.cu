@@ -1,0 +1,465 @@
+// K2/K3/K4/K5/K6: the HBM-bound kernels around the interval kernels.
+//   analytic_kernel      DerivativeIntegrator residual + dense Jacobian block          (derivative_integrator.jl:45-86)
+//   constraint_kernel    NonlinearKnotPointConstraint values + Jacobian (hyper-duals)   (knot_point_constraint.jl:235-268)
+//   hessian_assemble     per-knot upper-triangle Hessian of the Lagrangian in COO order (evaluator.jl:560-647)
+//   objective_kernel     objective value + dense gradient, warp-shuffle reductions       (_objectives.jl:111-128)
+//   violation_kernel     max-norm constraint violation
+//   jac_product_kernel   y = J w / J' w from the COO values                              (evaluator.jl:406-456)
+#include "dto_internal.h"
+#include "knotfun.cuh"
+
+namespace {
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// block-wide sum, result valid in thread 0 (and broadcast through smem slot)
+__device__ double block_sum(double v, double* red) {
+    v = warp_sum(v);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+    __syncthreads();
+    if (l == 0) red[w] = v;
+    __syncthreads();
+    if (w == 0) {
+        double t = (l < nw) ? red[l] : 0.0;
+        t = warp_sum(t);
+        if (l == 0) red[0] = t;
+    }
+    __syncthreads();
+    return red[0];
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: DerivativeIntegrator  f = x+ - x - dt*xdot : residual and full d x 2z block (zeros included)
+// ------------------------------------------------------------------------------------------------
+__global__ void analytic_kernel(DProb P, const double* __restrict__ Z, double* __restrict__ g, double* __restrict__ jac) {
+    const int b = blockIdx.x / P.nI, kl = blockIdx.x % P.nI, z = P.z;
+    const double* zk = Z + (long long)b * P.n_vars_local + (long long)kl * z;
+    const double* zk1 = zk + z;
+    if (P.halo != nullptr && kl + 1 == P.nK - 1) zk1 = P.halo;
+    const double dt = zk[P.dt_off];
+    for (int ii = 0; ii < P.n_int; ++ii) {
+        const DInt& I = P.in[ii];
+        if (I.kind != DTO_INT_DERIVATIVE) continue;
+        const int d = I.n;
+        if (g != nullptr) {
+            double* gp = g + (long long)b * P.n_cons_local + I.row_off + (long long)kl * d;
+            for (int a = threadIdx.x; a < d; a += blockDim.x) gp[a] = zk1[I.x_off + a] - zk[I.x_off + a] - dt * zk[I.u_off + a];
+        }
+        if (jac != nullptr) {
+            double* jp = jac + (long long)b * P.nnz_jac_local;
+            const long long own_off = jac_own_off(P, kl, I.doff, d);
+            const long long prev_off = jac_prev_off(P, kl + 1, I.doff);
+            for (int e = threadIdx.x; e < 2 * z * d; e += blockDim.x) {
+                const int l = e / d, a = e % d;
+                double v = 0.0;
+                long long pos;
+                if (l < z) {
+                    if (l == I.x_off + a) v += -1.0;
+                    if (l == I.u_off + a) v += -dt;
+                    if (l == P.dt_off) v += -zk[I.u_off + a];
+                    pos = P.jac_colptr[(long long)kl * z + l] + own_off + a;
+                } else {
+                    if (l - z == I.x_off + a) v = 1.0;
+                    pos = P.jac_colptr[(long long)(kl + 1) * z + (l - z)] + prev_off + a;
+                }
+                jp[pos] = v;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5: knot constraints, one thread per (problem, owned time entry)
+// ------------------------------------------------------------------------------------------------
+__global__ void constraint_kernel(DProb P, int ci, const double* __restrict__ Z, double* __restrict__ g, double* __restrict__ jac,
+                                  double* __restrict__ dense_probe) {
+    const DCon& C = P.co[ci];
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)P.batch * C.nt_own) return;
+    const int b = (int)(t / C.nt_own), j = (int)(t % C.nt_own);
+    const int kl = C.own_knot[j];
+    const double* zk = Z + (long long)b * P.n_vars_local + (long long)kl * P.z;
+    const double* p = C.params + (long long)C.own_ti[j] * C.np;
+    const int nv = C.nv, gd = C.gd;
+    if (g != nullptr) {
+        double v[DTO_MAX_KNOTFN_VARS], out[16];
+        for (int i = 0; i < nv; ++i) v[i] = zk[C.var_offs[i]];
+        knot_cfun<double>(C.fn, v, nv, p, out, gd);
+        double* gp = g + (long long)b * P.n_cons_local + C.row_off + (long long)j * gd;
+        for (int a = 0; a < gd; ++a) gp[a] = out[a];
+    }
+    if (jac != nullptr || dense_probe != nullptr) {
+        HDual v[DTO_MAX_KNOTFN_VARS], out[16];
+        for (int i = 0; i < nv; ++i) v[i] = HDual(zk[C.var_offs[i]]);
+        for (int i = 0; i < nv; ++i) {
+            v[i].d1 = 1.0;
+            knot_cfun<HDual>(C.fn, v, nv, p, out, gd);
+            v[i].d1 = 0.0;
+            for (int a = 0; a < gd; ++a) {
+                const long long e = ((long long)j * gd + a) * nv + i;
+                if (dense_probe != nullptr) {
+                    if (b == 0) dense_probe[e] = out[a].d1;
+                } else {
+                    const long long pos = C.jac_pos[e];
+                    if (pos >= 0) jac[(long long)b * P.nnz_jac_local + pos] = out[a].d1;
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: Hessian of the Lagrangian, one CTA per (problem, owned knot)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void sym_add(double* diag, int z, int i, int j, double v) {
+    if (i <= j) diag[i * z + j] += v;
+    else diag[j * z + i] += v;
+}
+
+// parameter p of integrator I -> (0: own knot, 1: next knot, component offset)
+__device__ __forceinline__ void int_param(const DInt& I, int dt_off, int p, int& next, int& comp) {
+    if (I.kind == DTO_INT_BILINEAR) {
+        next = 0;
+        comp = p < I.m ? I.u_off + p : dt_off;
+    } else {  // tdbilinear: [u0 (m), u1 (m, order 1), dt, t]
+        const int nu = I.order == 1 ? 2 * I.m : I.m;
+        if (p < I.m) { next = 0; comp = I.u_off + p; }
+        else if (p < nu) { next = 1; comp = I.u_off + (p - I.m); }
+        else if (p == nu) { next = 0; comp = dt_off; }
+        else { next = 0; comp = I.t_off; }
+    }
+}
+__device__ __forceinline__ int int_nparam(const DInt& I) {
+    return I.kind == DTO_INT_BILINEAR ? I.m + 1 : (I.order == 1 ? 2 * I.m : I.m) + 2;
+}
+
+__global__ void hessian_assemble_kernel(DProb P, const double* __restrict__ Z, double sigma, const double* __restrict__ mu,
+                                        double* __restrict__ hess) {
+    extern __shared__ double sm[];
+    const int z = P.z, tid = threadIdx.x, nt = blockDim.x;
+    const int b = blockIdx.x / P.nOwn, kl = blockIdx.x % P.nOwn;
+    double* diag = sm;                               // z*z, entries (i<=l) used
+    double* cross = sm + z * z;                      // z*z if any_cross: cross[i*z + l] = H[knot kl-1 comp i][knot kl comp l]
+    double* red = sm + (P.any_cross ? 2 : 1) * z * z;  // 32
+    const double* zk = Z + (long long)b * P.n_vars_local + (long long)kl * z;
+    const double* mub = mu + (long long)b * P.n_cons_local;
+    const bool has_cross = hess_knot_has_cross(P, kl);
+    for (int e = tid; e < z * z; e += nt) diag[e] = 0.0;
+    if (P.any_cross)
+        for (int e = tid; e < z * z; e += nt) cross[e] = 0.0;
+    __syncthreads();
+
+    for (int ii = 0; ii < P.n_int; ++ii) {
+        const DInt& I = P.in[ii];
+        if (I.kind == DTO_INT_DERIVATIVE) {
+            if (kl < P.nI) {
+                const double* mup = mub + I.row_off + (long long)kl * I.n;
+                for (int a = tid; a < I.n; a += nt) sym_add(diag, z, I.u_off + a, P.dt_off, -mup[a]);
+            }
+            __syncthreads();
+            continue;
+        }
+        const int np = int_nparam(I), n = I.n;
+        if (kl < P.nI) {  // own interval: entries among this knot's variables
+            const double* hs = I.hs + ((long long)b * P.nI + kl) * I.hs_stride;
+            const double* hpp = hs + (long long)np * n;
+            for (int e = tid; e < np * n; e += nt) {
+                const int p = e / n, a = e % n;
+                int nx, comp;
+                int_param(I, P.dt_off, p, nx, comp);
+                if (!nx) sym_add(diag, z, I.x_off + a, comp, hs[e]);
+            }
+            __syncthreads();
+            for (int e = tid; e < np * np; e += nt) {
+                const int p = e / np, q = e % np;
+                if (p > q) continue;
+                int nxp, cp, nxq, cq;
+                int_param(I, P.dt_off, p, nxp, cp);
+                int_param(I, P.dt_off, q, nxq, cq);
+                if (!nxp && !nxq) sym_add(diag, z, cp, cq, hpp[e]);
+            }
+            __syncthreads();
+        }
+        if (I.kind == DTO_INT_TDBILINEAR && I.order == 1 && kl >= 1) {
+            // previous interval: (next,next) -> this knot's diagonal block; (own,next) -> cross block
+            const double* hs = I.hs + ((long long)b * P.nI + (kl - 1)) * I.hs_stride;
+            const double* hpp = hs + (long long)np * n;
+            for (int e = tid; e < np * n; e += nt) {
+                const int p = e / n, a = e % n;
+                int nx, comp;
+                int_param(I, P.dt_off, p, nx, comp);
+                if (nx) cross[(I.x_off + a) * z + comp] += hs[e];
+            }
+            __syncthreads();
+            for (int e = tid; e < np * np; e += nt) {
+                const int p = e / np, q = e % np;
+                int nxp, cp, nxq, cq;
+                int_param(I, P.dt_off, p, nxp, cp);
+                int_param(I, P.dt_off, q, nxq, cq);
+                if (nxp && nxq) {
+                    if (p <= q) sym_add(diag, z, cp, cq, hpp[e]);
+                } else if (!nxp && nxq) {
+                    cross[cp * z + cq] += hpp[e];
+                }
+            }
+            __syncthreads();
+        }
+    }
+
+    // knot constraints at this knot: sum_a mu_a * Hess g_a  (hyper-dual pairs)
+    for (int ci = 0; ci < P.n_con; ++ci) {
+        const DCon& C = P.co[ci];
+        const int j = C.knot_to_own[kl];
+        if (j >= 0) {
+            const int nv = C.nv, gd = C.gd;
+            const double* p = C.params + (long long)C.own_ti[j] * C.np;
+            const double* mup = mub + C.row_off + (long long)j * gd;
+            for (int e = tid; e < nv * nv; e += nt) {
+                const int a = e / nv, c = e % nv;
+                if (a > c) continue;
+                HDual v[DTO_MAX_KNOTFN_VARS], out[16];
+                for (int i = 0; i < nv; ++i) v[i] = HDual(zk[C.var_offs[i]]);
+                v[a].d1 = 1.0;
+                v[c].d2 = 1.0;
+                knot_cfun<HDual>(C.fn, v, nv, p, out, gd);
+                double s = 0.0;
+                for (int q = 0; q < gd; ++q) s = fma(mup[q], out[q].d12, s);
+                sym_add(diag, z, C.var_offs[a], C.var_offs[c], s);
+            }
+        }
+        __syncthreads();
+    }
+
+    // objective: sigma * sum_i w_i Hess J_i   (skipped entirely when sigma == 0, evaluator.jl:626)
+    if (sigma != 0.0) {
+        for (int oi = 0; oi < P.n_obj; ++oi) {
+            const DObj& O = P.ob[oi];
+            if (O.kind == DTO_OBJ_QUADREG) {
+                if (O.knot_to_own[kl] >= 0) {
+                    const double dt = zk[P.dt_off], sw = sigma * O.weight;
+                    const long long kg = (long long)P.kb - 1 + kl;  // global 0-based knot
+                    double part = 0.0;
+                    for (int a = tid; a < O.nv; a += nt) {
+                        const int va = O.var_offs[a];
+                        const double dv = zk[va] - (O.baseline ? O.baseline[kg * O.nv + a] : 0.0);
+                        diag[va * z + va] += sw * dt * dt * O.R[a];
+                        // written only at (row v, col dt): survives the upper-triangle filter iff v <= dt
+                        // (regularizers.jl:160, evaluator.jl:637)
+                        if (va <= P.dt_off && va != P.dt_off) diag[va * z + P.dt_off] += sw * 2.0 * dt * O.R[a] * dv;
+                        part += O.R[a] * dv * dv;
+                    }
+                    const double q = block_sum(part, red);
+                    if (tid == 0) diag[P.dt_off * z + P.dt_off] += sw * q;
+                }
+                __syncthreads();
+            } else if (O.kind == DTO_OBJ_KNOT) {
+                const int j = O.knot_to_own[kl];
+                if (j >= 0) {
+                    const int nv = O.nv;
+                    const double* p = O.params + (long long)O.own_ti[j] * O.np;
+                    const double sw = sigma * O.weight * O.Qs[O.own_ti[j]];
+                    for (int e = tid; e < nv * nv; e += nt) {
+                        const int a = e / nv, c = e % nv;
+                        if (a > c) continue;
+                        HDual v[DTO_MAX_KNOTFN_VARS];
+                        for (int i = 0; i < nv; ++i) v[i] = HDual(zk[O.var_offs[i]]);
+                        v[a].d1 = 1.0;
+                        v[c].d2 = 1.0;
+                        const HDual r = knot_lfun<HDual>(O.fn, v, nv, p);
+                        sym_add(diag, z, O.var_offs[a], O.var_offs[c], sw * r.d12);
+                    }
+                }
+                __syncthreads();
+            }
+        }
+    }
+
+    // stream the knot's region out in COO order: per column l: [z cross rows][l+1 diagonal rows]
+    double* hp = hess + (long long)b * P.nnz_hess_local + hess_knot_base(P, kl);
+    const int warp = tid >> 5, lane = tid & 31, nwarp = nt >> 5;
+    for (int l = warp; l < z; l += nwarp) {
+        const long long cs = has_cross ? (long long)l * z + (long long)l * (l + 1) / 2 : (long long)l * (l + 1) / 2;
+        const int ncross = has_cross ? z : 0;
+        for (int i = lane; i < ncross + l + 1; i += 32) {
+            double v;
+            if (i < ncross) v = P.any_cross ? cross[i * z + l] : 0.0;
+            else v = diag[(i - ncross) * z + l];
+            hp[cs + i] = v;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K6: objective value + gradient, one CTA per (problem, owned knot); partial sums reduced in a
+// second, deterministic pass.
+// ------------------------------------------------------------------------------------------------
+__global__ void objective_kernel(DProb P, const double* __restrict__ Z, double* __restrict__ grad, double* __restrict__ partials) {
+    extern __shared__ double sm[];
+    const int z = P.z, tid = threadIdx.x, nt = blockDim.x;
+    const int b = blockIdx.x / P.nOwn, kl = blockIdx.x % P.nOwn;
+    double* gz = sm;        // z
+    double* red = sm + z;   // 32
+    const double* zk = Z + (long long)b * P.n_vars_local + (long long)kl * z;
+    const long long kg = (long long)P.kb - 1 + kl;  // global 0-based knot
+    for (int e = tid; e < z; e += nt) gz[e] = 0.0;
+    __syncthreads();
+    double Jk = 0.0;  // meaningful in thread 0 only
+    for (int oi = 0; oi < P.n_obj; ++oi) {
+        const DObj& O = P.ob[oi];
+        if (O.kind == DTO_OBJ_QUADREG) {
+            if (O.knot_to_own[kl] >= 0) {
+                const double dt = zk[P.dt_off];
+                double part = 0.0;
+                for (int a = tid; a < O.nv; a += nt) {
+                    const double dv = zk[O.var_offs[a]] - (O.baseline ? O.baseline[kg * O.nv + a] : 0.0);
+                    gz[O.var_offs[a]] += O.weight * dt * dt * O.R[a] * dv;
+                    part += O.R[a] * dv * dv;
+                }
+                const double q = block_sum(part, red);
+                if (tid == 0) {
+                    Jk += O.weight * 0.5 * dt * dt * q;
+                    gz[P.dt_off] += O.weight * q * dt;
+                }
+            }
+            __syncthreads();
+        } else if (O.kind == DTO_OBJ_MINTIME) {
+            if (tid == 0 && kg < P.N - 1) {
+                Jk += O.weight * O.D * zk[P.dt_off];
+                gz[P.dt_off] += O.weight * O.D;
+            }
+            __syncthreads();
+        } else if (O.kind == DTO_OBJ_KNOT) {
+            const int j = O.knot_to_own[kl];
+            if (j >= 0) {
+                const int nv = O.nv;
+                const double* p = O.params + (long long)O.own_ti[j] * O.np;
+                const double w = O.weight * O.Qs[O.own_ti[j]];
+                for (int a = tid; a < nv; a += nt) {
+                    HDual v[DTO_MAX_KNOTFN_VARS];
+                    for (int i = 0; i < nv; ++i) v[i] = HDual(zk[O.var_offs[i]]);
+                    v[a].d1 = 1.0;
+                    const HDual r = knot_lfun<HDual>(O.fn, v, nv, p);
+                    gz[O.var_offs[a]] += w * r.d1;
+                    if (a == 0) Jk += w * r.v;  // a == 0 is handled by thread 0
+                }
+            }
+            __syncthreads();
+        }
+    }
+    if (grad != nullptr)
+        for (int e = tid; e < z; e += nt) grad[((long long)b * P.nOwn + kl) * z + e] = gz[e];
+    if (tid == 0 && partials != nullptr) partials[(long long)b * P.nOwn + kl] = Jk;
+}
+
+__global__ void objective_reduce_kernel(int nOwn, const double* __restrict__ partials, double* __restrict__ J) {
+    const int b = blockIdx.x;
+    double s = 0.0;
+    for (int k = threadIdx.x; k < nOwn; k += blockDim.x) s += partials[(long long)b * nOwn + k];
+    __shared__ double red[32];
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) J[b] = s;
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void violation_kernel(long long n_cons, const double* __restrict__ g, const int* __restrict__ row_is_eq,
+                                 double* __restrict__ viol) {
+    const int b = blockIdx.y;
+    double m = 0.0;
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n_cons; r += (long long)gridDim.x * blockDim.x) {
+        const double v = g[(long long)b * n_cons + r];
+        m = fmax(m, row_is_eq[r] ? fabs(v) : fmax(v, 0.0));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    // non-negative doubles order like their bit patterns
+    if ((threadIdx.x & 31) == 0 && m > 0.0) atomicMax((unsigned long long*)(viol + b), (unsigned long long)__double_as_longlong(m));
+}
+
+__global__ void jac_product_kernel(long long nnz, long long n_rows, long long n_cols, const double* __restrict__ jac,
+                                   const long long* __restrict__ rows0, const long long* __restrict__ cols0,
+                                   const double* __restrict__ w, double* __restrict__ y, int transpose) {
+    const int b = blockIdx.y;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += (long long)gridDim.x * blockDim.x) {
+        const double v = jac[(long long)b * nnz + e];
+        if (!transpose) atomicAdd(y + (long long)b * n_rows + rows0[e], v * w[(long long)b * n_cols + cols0[e]]);
+        else atomicAdd(y + (long long)b * n_cols + cols0[e], v * w[(long long)b * n_rows + rows0[e]]);
+    }
+}
+
+}  // namespace
+
+void launch_analytic(const DProb& P, const double* Z, double* g, double* jac, EvalFlags f, cudaStream_t st, long long* launches) {
+    bool any_deriv = false;
+    for (int i = 0; i < P.n_int; ++i) any_deriv |= P.in[i].kind == DTO_INT_DERIVATIVE;
+    if (any_deriv && P.nI > 0) {
+        analytic_kernel<<<P.nI * P.batch, 128, 0, st>>>(P, Z, f.want_g ? g : nullptr, f.want_jac ? jac : nullptr);
+        ++*launches;
+    }
+    for (int ci = 0; ci < P.n_con; ++ci) {
+        const long long tot = (long long)P.batch * P.co[ci].nt_own;
+        if (tot == 0) continue;
+        constraint_kernel<<<(unsigned)((tot + 63) / 64), 64, 0, st>>>(P, ci, Z, f.want_g ? g : nullptr, f.want_jac ? jac : nullptr,
+                                                                       nullptr);
+        ++*launches;
+    }
+}
+
+void launch_constraint_pattern_probe(const DProb& P, const double* Z, double* dense, cudaStream_t st, long long* launches) {
+    long long off = 0;
+    for (int ci = 0; ci < P.n_con; ++ci) {
+        const DCon& C = P.co[ci];
+        const long long tot = (long long)P.batch * C.nt_own;
+        if (tot) {
+            constraint_kernel<<<(unsigned)((tot + 63) / 64), 64, 0, st>>>(P, ci, Z, nullptr, nullptr, dense + off);
+            ++*launches;
+        }
+        off += (long long)C.nt_own * C.gd * C.nv;
+    }
+}
+
+void launch_hessian_assemble(const DProb& P, const double* Z, double sigma, const double* mu, double* hess, cudaStream_t st,
+                             long long* launches) {
+    if (P.nOwn <= 0) return;
+    const size_t smem = sizeof(double) * ((size_t)P.z * P.z * (P.any_cross ? 2 : 1) + 32);
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        cudaFuncSetAttribute(hessian_assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        configured = 227 * 1024;
+    }
+    hessian_assemble_kernel<<<P.nOwn * P.batch, 128, smem, st>>>(P, Z, sigma, mu, hess);
+    ++*launches;
+}
+
+void launch_objective(const DProb& P, const double* Z, double* J, double* grad, double* partials, cudaStream_t st,
+                      long long* launches) {
+    if (P.nOwn <= 0) return;
+    const size_t smem = sizeof(double) * (P.z + 32);
+    objective_kernel<<<P.nOwn * P.batch, 64, smem, st>>>(P, Z, grad, J ? partials : nullptr);
+    ++*launches;
+    if (J) {
+        objective_reduce_kernel<<<P.batch, 256, 0, st>>>(P.nOwn, partials, J);
+        ++*launches;
+    }
+}
+
+void launch_violation(const DProb& P, const double* g, const int* row_is_eq, double* viol, cudaStream_t st, long long* launches) {
+    cudaMemsetAsync(viol, 0, sizeof(double) * P.batch, st);
+    if (P.n_cons_local == 0) return;
+    dim3 grid((unsigned)((P.n_cons_local + 255) / 256 > 1184 ? 1184 : (P.n_cons_local + 255) / 256), P.batch);
+    violation_kernel<<<grid, 256, 0, st>>>(P.n_cons_local, g, row_is_eq, viol);
+    ++*launches;
+}
+
+void launch_jac_product(const DProb& P, const double* jac, const long long* rows0, const long long* cols0, const double* w,
+                        double* y, bool transpose, cudaStream_t st, long long* launches) {
+    const long long n_rows = P.n_cons_local, n_cols = P.n_vars_local;
+    cudaMemsetAsync(y, 0, sizeof(double) * (transpose ? n_cols : n_rows) * P.batch, st);
+    if (P.nnz_jac_local == 0) return;
+    dim3 grid((unsigned)((P.nnz_jac_local + 255) / 256 > 2368 ? 2368 : (P.nnz_jac_local + 255) / 256), P.batch);
+    jac_product_kernel<<<grid, 256, 0, st>>>(P.nnz_jac_local, n_rows, n_cols, jac, rows0, cols0, w, y, transpose ? 1 : 0);
+    ++*launches;
+}

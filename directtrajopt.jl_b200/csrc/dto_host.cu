@@ -1,0 +1,812 @@
+// Host side of libdto_b200.so: descriptor validation, the closed-form structure builder that
+// replaces Evaluator(prob)'s sparse-matrix construction and O(n_vars^2) index maps
+// (/root/reference/src/solvers/evaluator.jl:99-288), device residency, and the C ABI of
+// include/dto_b200.h.  No torch types, no CPU compute fallback: every value comes from a kernel.
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <limits>
+#include <new>
+
+#include "dto_internal.h"
+#include "knotfun.cuh"
+
+static thread_local std::string g_create_error;
+
+struct ConEntry {
+    long long col_local;  // local column
+    long long grow;       // global 0-based row
+    long long lrow;       // local 0-based row
+    long long e;          // index into the constraint's dense [j][a][i] table
+    int ci;
+};
+
+struct dto_handle {
+    std::string err;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    DProb P;
+    dto_size_info sizes_global{};  // of the WHOLE problem (one batch member)
+    dto_size_info sizes_local{};
+    int eval_hessian = 1;
+    int sharded = 0;
+    int k0 = 1, k1 = 1;
+    std::vector<void*> allocs;
+    // host copies of the descriptor
+    std::vector<dto_integrator_desc> ints;
+    std::vector<dto_objective_desc> objs;
+    std::vector<dto_constraint_desc> cons;
+    std::vector<std::vector<int>> obj_var_offs, obj_times, con_var_offs, con_times;
+    std::vector<std::vector<int>> con_own_ti;  // owned entries per constraint
+    std::vector<long long> int_goff;           // global row offset of each integrator
+    std::vector<long long> con_goff;           // global row offset of each constraint (after dynamics)
+    std::vector<long long> jac_colptr;         // local
+    std::vector<ConEntry> con_entries;         // stored constraint Jacobian entries (owned), sorted by (col, row)
+    std::vector<std::vector<unsigned char>> con_stored_all;  // per constraint: stored mask over ALL times [ti][a][i]
+    std::vector<int> row_is_eq;
+    // device buffers
+    double *dZ = nullptr, *dmu = nullptr, *dg = nullptr, *djac = nullptr, *dhess = nullptr, *dgrad = nullptr, *dJ = nullptr,
+           *dpartials = nullptr, *dviol = nullptr, *dw = nullptr, *dy = nullptr;
+    int* d_row_is_eq = nullptr;
+    long long *d_rows0 = nullptr, *d_cols0 = nullptr;
+    void* ipc_peer = nullptr;
+    long long launches = 0;
+    std::vector<std::string> variants;
+};
+
+#define CUDA_TRY(h, call)                                                                       \
+    do {                                                                                         \
+        cudaError_t _e = (call);                                                                 \
+        if (_e != cudaSuccess) {                                                                 \
+            (h)->err = std::string(#call) + ": " + cudaGetErrorString(_e);                       \
+            return DTO_ERR_CUDA;                                                                 \
+        }                                                                                        \
+    } while (0)
+
+template <class T>
+static T* dev_upload(dto_handle* h, const T* src, size_t count) {
+    if (count == 0) return nullptr;
+    void* p = nullptr;
+    if (cudaMalloc(&p, count * sizeof(T)) != cudaSuccess) return nullptr;
+    h->allocs.push_back(p);
+    if (src) cudaMemcpy(p, src, count * sizeof(T), cudaMemcpyHostToDevice);
+    else cudaMemset(p, 0, count * sizeof(T));
+    return (T*)p;
+}
+
+static int fail_create(dto_handle* h, int code, const std::string& msg) {
+    g_create_error = msg;
+    if (h) dto_destroy(h);
+    return code;
+}
+
+extern "C" int dto_abi_version(void) { return DTO_B200_ABI_VERSION; }
+
+extern "C" const char* dto_last_error(const dto_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+extern "C" void dto_destroy(dto_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->ipc_peer) cudaIpcCloseMemHandle(h->ipc_peer);
+    for (void* p : h->allocs) cudaFree(p);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+
+extern "C" int dto_create(const dto_problem_desc* d, dto_handle** out) {
+    if (!d || !out) return fail_create(nullptr, DTO_ERR_INVALID, "null descriptor");
+    *out = nullptr;
+    if (d->abi_version != DTO_B200_ABI_VERSION) return fail_create(nullptr, DTO_ERR_INVALID, "ABI version mismatch");
+    if (d->N < 2 || d->z < 1 || d->batch < 1) return fail_create(nullptr, DTO_ERR_INVALID, "need N >= 2, z >= 1, batch >= 1");
+    if (d->dt_off < 0 || d->dt_off >= d->z) return fail_create(nullptr, DTO_ERR_INVALID, "timestep component outside the knot");
+    if (d->n_integrators < 1)
+        return fail_create(nullptr, DTO_ERR_UNSUPPORTED, "at least one integrator is required (dense block Hessian structure)");
+    if (d->n_integrators > DTO_MAX_INT || d->n_objectives > DTO_MAX_OBJ || d->n_constraints > DTO_MAX_CON)
+        return fail_create(nullptr, DTO_ERR_UNSUPPORTED, "too many integrators / objective terms / constraints");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail_create(nullptr, DTO_ERR_CUDA, "no CUDA device: libdto_b200 has no CPU fallback");
+    dto_handle* h = new (std::nothrow) dto_handle();
+    if (!h) return fail_create(nullptr, DTO_ERR_ALLOC, "out of host memory");
+    if (d->device >= 0) {
+        if (cudaSetDevice(d->device) != cudaSuccess) return fail_create(h, DTO_ERR_CUDA, "cudaSetDevice failed");
+        h->device = d->device;
+    } else {
+        cudaGetDevice(&h->device);
+    }
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess)
+        return fail_create(h, DTO_ERR_CUDA, "cudaStreamCreate failed");
+
+    const int N = d->N, z = d->z;
+    h->eval_hessian = d->eval_hessian;
+    h->sharded = d->shard_k0 > 0;
+    h->k0 = h->sharded ? d->shard_k0 : 1;
+    h->k1 = h->sharded ? d->shard_k1 : N;
+    if (h->k0 < 1 || h->k1 > N || h->k0 > h->k1) return fail_create(h, DTO_ERR_INVALID, "bad shard range");
+    if (h->sharded && d->batch != 1) return fail_create(h, DTO_ERR_UNSUPPORTED, "knot-range shards require batch == 1");
+
+    DProb& P = h->P;
+    memset(&P, 0, sizeof(P));
+    P.N = N;
+    P.z = z;
+    P.dt_off = d->dt_off;
+    P.batch = d->batch;
+    P.kb = h->k0;
+    P.nOwn = h->k1 - h->k0 + 1;
+    P.nK = P.nOwn + (h->k1 < N ? 1 : 0);
+    P.nI = P.nK - 1;
+    P.first_has_cross = h->k0 > 1;
+    P.n_int = d->n_integrators;
+    P.n_obj = d->n_objectives;
+    P.n_con = d->n_constraints;
+    P.n_vars_local = (long long)P.nK * z;
+
+    // ---- integrators -------------------------------------------------------------------------
+    long long goff = 0, loff = 0;
+    int doff = 0;
+    for (int i = 0; i < d->n_integrators; ++i) {
+        const dto_integrator_desc& s = d->integrators[i];
+        h->ints.push_back(s);
+        DInt& I = P.in[i];
+        I.kind = s.kind;
+        I.x_off = s.x_off;
+        I.n = s.x_dim;
+        I.u_off = s.u_off;
+        I.m = s.u_dim;
+        I.t_off = s.t_off;
+        I.order = s.spline_order;
+        I.n_carrier = s.n_carrier;
+        I.doff = doff;
+        I.row_off = loff;
+        I.steps = s.tdb_steps > 0 ? s.tdb_steps : 8;
+        if (s.x_dim < 1 || s.x_off < 0 || s.x_off + s.x_dim > z) return fail_create(h, DTO_ERR_INVALID, "integrator state component outside the knot");
+        const size_t nn = (size_t)s.x_dim * s.x_dim;
+        if (s.kind == DTO_INT_BILINEAR) {
+            if (s.u_dim < 0 || s.u_off < 0 || s.u_off + s.u_dim > z || !s.G) return fail_create(h, DTO_ERR_INVALID, "bilinear integrator: bad drive component or missing generators");
+            const size_t per = (size_t)(s.u_dim + 1) * nn;
+            const size_t cnt = s.G_batch_stride ? (size_t)s.G_batch_stride * (d->batch - 1) + per : per;
+            I.G = dev_upload(h, s.G, cnt);
+            I.G_stride = s.G_batch_stride;
+            I.hs_stride = (s.u_dim + 1) * s.x_dim + (s.u_dim + 1) * (s.u_dim + 1);
+            I.variant = bilinear_dmma_supported(s.x_dim, s.u_dim) ? DTO_VAR_DMMA : DTO_VAR_GENERIC;
+            if (s.x_dim > 96) return fail_create(h, DTO_ERR_UNSUPPORTED, "bilinear integrator: state dimension > 96 not supported");
+        } else if (s.kind == DTO_INT_DERIVATIVE) {
+            if (s.u_dim != s.x_dim || s.u_off < 0 || s.u_off + s.u_dim > z) return fail_create(h, DTO_ERR_INVALID, "derivative integrator: derivative component must match the variable's dimension");
+        } else if (s.kind == DTO_INT_TDBILINEAR) {
+            if (s.u_dim < 0 || s.u_off < 0 || s.u_off + s.u_dim > z || s.t_off < 0 || s.t_off >= z || !s.G)
+                return fail_create(h, DTO_ERR_INVALID, "tdbilinear integrator: bad components");
+            if (!tdb_available()) return fail_create(h, DTO_ERR_UNSUPPORTED, "tdbilinear integrator kernel is not built into this library");
+            if (s.spline_order != 0 && s.spline_order != 1) return fail_create(h, DTO_ERR_UNSUPPORTED, "Unsupported spline order");
+            if (s.spline_order == 1 && h->sharded && h->k0 > 1)
+                return fail_create(h, DTO_ERR_UNSUPPORTED, "tdbilinear with spline_order 1 cannot be knot-range sharded (needs a left halo)");
+            I.G = dev_upload(h, s.G, nn);
+            I.A = dev_upload(h, s.A, nn * s.u_dim);
+            I.B = dev_upload(h, s.B, nn * s.u_dim);
+            I.omega = dev_upload(h, s.omega, s.u_dim);
+            I.phi = dev_upload(h, s.phi, s.u_dim);
+            I.D = dev_upload(h, s.D, nn * s.n_carrier);
+            I.omega_d = dev_upload(h, s.omega_d, s.n_carrier);
+            I.phi_d = dev_upload(h, s.phi_d, s.n_carrier);
+            const int np = (s.spline_order == 1 ? 2 * s.u_dim : s.u_dim) + 2;
+            I.hs_stride = np * s.x_dim + np * np;
+            if (s.spline_order == 1) P.any_cross = 1;
+            if (s.x_dim > 96) return fail_create(h, DTO_ERR_UNSUPPORTED, "tdbilinear integrator: state dimension > 96 not supported");
+        } else {
+            return fail_create(h, DTO_ERR_UNSUPPORTED, "unknown integrator kind");
+        }
+        if (I.hs_stride > 0 && d->eval_hessian) {
+            I.hs = dev_upload<double>(h, nullptr, (size_t)P.batch * std::max(P.nI, 1) * I.hs_stride);
+            if (!I.hs) return fail_create(h, DTO_ERR_ALLOC, "device allocation failed (Hessian scratch)");
+        }
+        h->int_goff.push_back(goff);
+        goff += (long long)s.x_dim * (N - 1);
+        loff += (long long)s.x_dim * P.nI;
+        doff += s.x_dim;
+        h->variants.push_back(s.kind == DTO_INT_BILINEAR ? (I.variant == DTO_VAR_DMMA ? "dmma" : "generic")
+                                                         : (s.kind == DTO_INT_DERIVATIVE ? "analytic" : "rk"));
+    }
+    P.Dsum = doff;
+    const long long n_dyn_global = goff, n_dyn_local = loff;
+
+    // ---- objectives --------------------------------------------------------------------------
+    h->obj_var_offs.resize(d->n_objectives);
+    h->obj_times.resize(d->n_objectives);
+    for (int i = 0; i < d->n_objectives; ++i) {
+        const dto_objective_desc& s = d->objectives[i];
+        h->objs.push_back(s);
+        DObj& O = P.ob[i];
+        O.kind = s.kind;
+        O.fn = s.fn;
+        O.weight = s.weight;
+        O.nv = s.n_vars;
+        O.nt = s.n_times;
+        O.np = s.n_params;
+        O.D = s.D;
+        if (s.kind == DTO_OBJ_MINTIME || s.kind == DTO_OBJ_NULL) continue;
+        if (s.kind != DTO_OBJ_QUADREG && s.kind != DTO_OBJ_KNOT) return fail_create(h, DTO_ERR_UNSUPPORTED, "unknown objective kind");
+        if (s.kind == DTO_OBJ_KNOT && !knot_lfun_known(s.fn)) return fail_create(h, DTO_ERR_UNSUPPORTED, "knot objective function is not in the device catalogue");
+        if (s.n_vars < 1 || s.n_vars > DTO_MAX_KNOTFN_VARS || !s.var_offs) return fail_create(h, DTO_ERR_INVALID, "objective: bad variable list");
+        for (int v = 0; v < s.n_vars; ++v) {
+            if (s.var_offs[v] < 0 || s.var_offs[v] >= z) return fail_create(h, DTO_ERR_INVALID, "objective: variable outside the knot");
+            for (int v2 = 0; v2 < v; ++v2)
+                if (s.var_offs[v2] == s.var_offs[v]) return fail_create(h, DTO_ERR_UNSUPPORTED, "objective: repeated variable");
+        }
+        std::vector<int> k2o(P.nK, -1), own;
+        for (int t = 0; t < s.n_times; ++t) {
+            const int k = s.times[t];
+            if (k < 1 || k > N) return fail_create(h, DTO_ERR_INVALID, "objective: time index outside 1..N");
+            if (k >= h->k0 && k <= h->k1) {
+                if (k2o[k - h->k0] >= 0) return fail_create(h, DTO_ERR_UNSUPPORTED, "objective: repeated time index");
+                k2o[k - h->k0] = (int)own.size();
+                own.push_back(t);
+            }
+        }
+        O.var_offs = dev_upload(h, s.var_offs, s.n_vars);
+        O.own_ti = dev_upload(h, own.data(), own.size());
+        O.knot_to_own = dev_upload(h, k2o.data(), k2o.size());
+        if (s.kind == DTO_OBJ_QUADREG) {
+            if (!s.R) return fail_create(h, DTO_ERR_INVALID, "quadratic regularizer: missing R");
+            O.R = dev_upload(h, s.R, s.n_vars);
+            O.baseline = s.baseline ? dev_upload(h, s.baseline, (size_t)s.n_vars * N) : nullptr;
+        } else {
+            if (!s.Qs || (s.n_params > 0 && !s.params)) return fail_create(h, DTO_ERR_INVALID, "knot objective: missing Qs/params");
+            O.params = dev_upload(h, s.params, (size_t)std::max(1, s.n_params) * s.n_times);
+            O.Qs = dev_upload(h, s.Qs, s.n_times);
+        }
+    }
+
+    // ---- knot constraints ----------------------------------------------------------------------
+    h->con_own_ti.resize(d->n_constraints);
+    long long cgoff = 0, cloff = n_dyn_local;
+    std::vector<std::vector<int>> con_own_knot(d->n_constraints);
+    for (int i = 0; i < d->n_constraints; ++i) {
+        const dto_constraint_desc& s = d->constraints[i];
+        h->cons.push_back(s);
+        if (!knot_cfun_known(s.fn)) return fail_create(h, DTO_ERR_UNSUPPORTED, "knot constraint function is not in the device catalogue");
+        if (s.n_vars < 1 || s.n_vars > DTO_MAX_KNOTFN_VARS || s.g_dim < 1 || s.g_dim > 16 || !s.var_offs)
+            return fail_create(h, DTO_ERR_INVALID, "constraint: bad variable list or g_dim");
+        if (s.fn != DTO_G_LINEAR && s.g_dim != 1) return fail_create(h, DTO_ERR_INVALID, "constraint: g_dim must be 1 for this function");
+        if (!d->Z0) return fail_create(h, DTO_ERR_INVALID, "knot constraints need the initial trajectory Z0 (stored Jacobian pattern)");
+        for (int v = 0; v < s.n_vars; ++v) {
+            if (s.var_offs[v] < 0 || s.var_offs[v] >= z) return fail_create(h, DTO_ERR_INVALID, "constraint: variable outside the knot");
+            for (int v2 = 0; v2 < v; ++v2)
+                if (s.var_offs[v2] == s.var_offs[v]) return fail_create(h, DTO_ERR_UNSUPPORTED, "constraint: repeated variable");
+        }
+        DCon& C = P.co[i];
+        C.fn = s.fn;
+        C.nv = s.n_vars;
+        C.gd = s.g_dim;
+        C.np = s.n_params;
+        std::vector<int> k2o(P.nK, -1);
+        for (int t = 0; t < s.n_times; ++t) {
+            const int k = s.times[t];
+            if (k < 1 || k > N) return fail_create(h, DTO_ERR_INVALID, "constraint: time index outside 1..N");
+            if (k >= h->k0 && k <= h->k1) {
+                if (k2o[k - h->k0] >= 0) return fail_create(h, DTO_ERR_UNSUPPORTED, "constraint: repeated time index");
+                k2o[k - h->k0] = (int)h->con_own_ti[i].size();
+                h->con_own_ti[i].push_back(t);
+                con_own_knot[i].push_back(k - h->k0);
+            }
+        }
+        C.nt_own = (int)h->con_own_ti[i].size();
+        C.row_off = cloff;
+        C.var_offs = dev_upload(h, s.var_offs, s.n_vars);
+        C.own_ti = dev_upload(h, h->con_own_ti[i].data(), h->con_own_ti[i].size());
+        C.own_knot = dev_upload(h, con_own_knot[i].data(), con_own_knot[i].size());
+        C.knot_to_own = dev_upload(h, k2o.data(), k2o.size());
+        C.params = dev_upload(h, s.params, (size_t)std::max(1, s.n_params) * s.n_times);
+        h->con_goff.push_back(cgoff);
+        cgoff += (long long)s.g_dim * s.n_times;
+        cloff += (long long)s.g_dim * C.nt_own;
+    }
+    const long long n_nl_global = cgoff;
+    P.n_cons_local = cloff;
+
+    // ---- stored pattern of the knot-constraint Jacobians at Z0 (problem 0) ---------------------
+    // Evaluated over ALL times (a shard needs the whole pattern to know global positions) with the
+    // same device templates that later produce the values.
+    h->con_stored_all.resize(d->n_constraints);
+    if (d->n_constraints > 0) {
+        DProb Q = P;  // whole-trajectory view for the probe
+        Q.batch = 1;
+        Q.kb = 1;
+        Q.nK = N;
+        Q.nOwn = N;
+        Q.nI = N - 1;
+        Q.n_vars_local = (long long)N * z;
+        Q.halo = nullptr;
+        double* dZ0 = dev_upload(h, d->Z0, (size_t)N * z);
+        long long total = 0;
+        std::vector<void*> tmp;
+        for (int i = 0; i < d->n_constraints; ++i) {
+            const dto_constraint_desc& s = d->constraints[i];
+            std::vector<int> all_ti(s.n_times), all_k(s.n_times);
+            for (int t = 0; t < s.n_times; ++t) {
+                all_ti[t] = t;
+                all_k[t] = s.times[t] - 1;
+            }
+            DCon& C = Q.co[i];
+            C.nt_own = s.n_times;
+            C.own_ti = dev_upload(h, all_ti.data(), all_ti.size());
+            C.own_knot = dev_upload(h, all_k.data(), all_k.size());
+            total += (long long)s.n_times * s.g_dim * s.n_vars;
+        }
+        double* dprobe = dev_upload<double>(h, nullptr, (size_t)std::max<long long>(total, 1));
+        launch_constraint_pattern_probe(Q, dZ0, dprobe, h->stream, &h->launches);
+        std::vector<double> probe((size_t)total);
+        if (cudaMemcpyAsync(probe.data(), dprobe, sizeof(double) * total, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
+            cudaStreamSynchronize(h->stream) != cudaSuccess)
+            return fail_create(h, DTO_ERR_CUDA, std::string("constraint pattern probe failed: ") + cudaGetErrorString(cudaGetLastError()));
+        long long off = 0;
+        for (int i = 0; i < d->n_constraints; ++i) {
+            const dto_constraint_desc& s = d->constraints[i];
+            const long long cnt = (long long)s.n_times * s.g_dim * s.n_vars;
+            h->con_stored_all[i].resize((size_t)cnt);
+            // SparseArrays' scalar setindex! does not store a zero value (either sign)
+            for (long long e = 0; e < cnt; ++e) h->con_stored_all[i][(size_t)e] = probe[(size_t)(off + e)] != 0.0 ? 1 : 0;
+            off += cnt;
+        }
+    }
+
+    // ---- local Jacobian column pointers and constraint scatter maps ----------------------------
+    std::vector<long long> ccount((size_t)P.nK * z, 0);
+    for (int i = 0; i < d->n_constraints; ++i) {
+        const dto_constraint_desc& s = d->constraints[i];
+        for (size_t j = 0; j < h->con_own_ti[i].size(); ++j) {
+            const int ti = h->con_own_ti[i][j], kl = con_own_knot[i][j];
+            for (int v = 0; v < s.n_vars; ++v)
+                for (int a = 0; a < s.g_dim; ++a)
+                    if (h->con_stored_all[i][((size_t)ti * s.g_dim + a) * s.n_vars + v]) ccount[(size_t)kl * z + s.var_offs[v]]++;
+        }
+    }
+    h->jac_colptr.assign((size_t)P.nK * z + 1, 0);
+    for (int kl = 0; kl < P.nK; ++kl) {
+        const long long per_col_int = (long long)P.Dsum * ((kl >= 1 ? 1 : 0) + (kl < P.nI ? 1 : 0));
+        for (int l = 0; l < z; ++l) {
+            const size_t c = (size_t)kl * z + l;
+            h->jac_colptr[c + 1] = h->jac_colptr[c] + per_col_int + ccount[c];
+        }
+    }
+    P.nnz_jac_local = h->jac_colptr.back();
+    P.jac_colptr = dev_upload(h, h->jac_colptr.data(), h->jac_colptr.size());
+    {
+        std::vector<long long> fill((size_t)P.nK * z, 0);
+        for (int i = 0; i < d->n_constraints; ++i) {
+            const dto_constraint_desc& s = d->constraints[i];
+            DCon& C = P.co[i];
+            std::vector<long long> pos((size_t)C.nt_own * s.g_dim * s.n_vars, -1);
+            for (size_t j = 0; j < h->con_own_ti[i].size(); ++j) {
+                const int ti = h->con_own_ti[i][j], kl = con_own_knot[i][j];
+                for (int v = 0; v < s.n_vars; ++v)
+                    for (int a = 0; a < s.g_dim; ++a) {
+                        if (!h->con_stored_all[i][((size_t)ti * s.g_dim + a) * s.n_vars + v]) continue;
+                        const size_t c = (size_t)kl * z + s.var_offs[v];
+                        const long long per_col_int = (long long)P.Dsum * ((kl >= 1 ? 1 : 0) + (kl < P.nI ? 1 : 0));
+                        const long long e = ((long long)j * s.g_dim + a) * s.n_vars + v;
+                        const long long p = h->jac_colptr[c] + per_col_int + fill[c]++;
+                        pos[(size_t)e] = p;
+                        ConEntry ce;
+                        ce.col_local = (long long)c;
+                        ce.grow = n_dyn_global + h->con_goff[i] + (long long)ti * s.g_dim + a;
+                        ce.lrow = C.row_off + (long long)j * s.g_dim + a;
+                        ce.e = p;  // local position
+                        ce.ci = i;
+                        h->con_entries.push_back(ce);
+                    }
+            }
+            C.jac_pos = dev_upload(h, pos.data(), pos.size());
+        }
+        std::stable_sort(h->con_entries.begin(), h->con_entries.end(),
+                         [](const ConEntry& a, const ConEntry& b) { return a.e < b.e; });
+    }
+
+    // ---- sizes -----------------------------------------------------------------------------------
+    const long long tri = (long long)z * (z + 1) / 2;
+    P.nnz_hess_local = hess_knot_base(P, P.nOwn);  // base of the knot after the last owned one
+    h->sizes_local.n_vars = (long long)P.nOwn * z;
+    h->sizes_local.n_dynamics_cons = n_dyn_local;
+    h->sizes_local.n_nonlinear_cons = P.n_cons_local - n_dyn_local;
+    h->sizes_local.n_cons = P.n_cons_local;
+    h->sizes_local.nnz_jac = P.nnz_jac_local;
+    h->sizes_local.nnz_hess = P.nnz_hess_local;
+    h->sizes_global.n_vars = (long long)N * z;
+    h->sizes_global.n_dynamics_cons = n_dyn_global;
+    h->sizes_global.n_nonlinear_cons = n_nl_global;
+    h->sizes_global.n_cons = n_dyn_global + n_nl_global;
+    {
+        long long stored = 0;
+        for (auto& m : h->con_stored_all)
+            for (unsigned char c : m) stored += c;
+        h->sizes_global.nnz_jac = (long long)(N - 1) * P.Dsum * 2 * z + stored;
+        h->sizes_global.nnz_hess = (long long)N * tri + (long long)(N - 1) * z * z;
+    }
+
+    // equality flags of the local rows
+    h->row_is_eq.assign((size_t)P.n_cons_local, 1);
+    for (int i = 0; i < d->n_constraints; ++i)
+        if (!d->constraints[i].equality)
+            for (long long r = 0; r < (long long)P.co[i].nt_own * P.co[i].gd; ++r) h->row_is_eq[(size_t)(P.co[i].row_off + r)] = 0;
+    h->d_row_is_eq = dev_upload(h, h->row_is_eq.data(), h->row_is_eq.size());
+
+    // keep host copies of small arrays the structure queries need
+    h->con_var_offs.resize(d->n_constraints);
+    h->con_times.resize(d->n_constraints);
+    for (int i = 0; i < d->n_constraints; ++i) {
+        h->con_var_offs[i].assign(d->constraints[i].var_offs, d->constraints[i].var_offs + d->constraints[i].n_vars);
+        h->con_times[i].assign(d->constraints[i].times, d->constraints[i].times + d->constraints[i].n_times);
+    }
+
+    // ---- work buffers --------------------------------------------------------------------------
+    const size_t B = (size_t)P.batch;
+    h->dZ = dev_upload<double>(h, nullptr, B * (size_t)P.n_vars_local);
+    h->dmu = dev_upload<double>(h, nullptr, B * (size_t)std::max<long long>(P.n_cons_local, 1));
+    h->dg = dev_upload<double>(h, nullptr, B * (size_t)std::max<long long>(P.n_cons_local, 1));
+    h->djac = dev_upload<double>(h, nullptr, B * (size_t)std::max<long long>(P.nnz_jac_local, 1));
+    h->dgrad = dev_upload<double>(h, nullptr, B * (size_t)P.nOwn * z);
+    h->dJ = dev_upload<double>(h, nullptr, B);
+    h->dviol = dev_upload<double>(h, nullptr, B);
+    h->dpartials = dev_upload<double>(h, nullptr, B * (size_t)P.nOwn);
+    if (d->eval_hessian) h->dhess = dev_upload<double>(h, nullptr, B * (size_t)std::max<long long>(P.nnz_hess_local, 1));
+    if (!h->dZ || !h->dmu || !h->dg || !h->djac || !h->dgrad || !h->dJ || !h->dpartials || (d->eval_hessian && !h->dhess))
+        return fail_create(h, DTO_ERR_ALLOC, "device allocation failed (work buffers)");
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess)
+        return fail_create(h, DTO_ERR_CUDA, "CUDA failure during construction");
+    *out = h;
+    return DTO_OK;
+}
+
+extern "C" int dto_sizes(const dto_handle* h, dto_size_info* out) {
+    if (!h || !out) return DTO_ERR_INVALID;
+    *out = h->sharded ? h->sizes_local : h->sizes_global;
+    return DTO_OK;
+}
+
+extern "C" void* dto_stream(const dto_handle* h) { return h ? (void*)h->stream : nullptr; }
+extern "C" int64_t dto_launch_count(const dto_handle* h) { return h ? h->launches : 0; }
+extern "C" const char* dto_kernel_variant(const dto_handle* h, int i) {
+    if (!h || i < 0 || i >= (int)h->variants.size()) return "";
+    return h->variants[i].c_str();
+}
+
+// ---- structures -----------------------------------------------------------------------------------
+// Jacobian: column-major over the local columns; inside a column [I1 prev | I1 own | I2 prev | ...]
+// then the stored knot-constraint rows (evaluator.jl:119-144; SURVEY.md section 8a structure contract).
+extern "C" int dto_jac_structure(const dto_handle* h, int64_t* rows, int64_t* cols) {
+    if (!h || !rows || !cols) return DTO_ERR_INVALID;
+    const DProb& P = h->P;
+    const int z = P.z;
+    long long w = 0;
+    size_t ce = 0;
+    for (int kl = 0; kl < P.nK; ++kl) {
+        const long long kg = (long long)P.kb - 1 + kl;  // global 0-based knot
+        for (int l = 0; l < z; ++l) {
+            const long long gcol = kg * z + l + 1;
+            for (int i = 0; i < P.n_int; ++i) {
+                const int dd = P.in[i].n;
+                if (kl >= 1)
+                    for (int a = 0; a < dd; ++a, ++w) {
+                        rows[w] = h->int_goff[i] + (kg - 1) * dd + a + 1;
+                        cols[w] = gcol;
+                    }
+                if (kl < P.nI)
+                    for (int a = 0; a < dd; ++a, ++w) {
+                        rows[w] = h->int_goff[i] + kg * dd + a + 1;
+                        cols[w] = gcol;
+                    }
+            }
+            while (ce < h->con_entries.size() && h->con_entries[ce].col_local == (long long)kl * z + l) {
+                rows[w] = h->con_entries[ce].grow + 1;
+                cols[w] = gcol;
+                ++w;
+                ++ce;
+            }
+        }
+    }
+    return w == P.nnz_jac_local ? DTO_OK : DTO_ERR_INVALID;
+}
+
+// Hessian: upper triangle, column-major: column (k,l) holds the z rows of knot k-1 (k >= 2) and rows
+// 1..l of knot k (evaluator.jl:151-203, _integrators.jl:68-77).
+extern "C" int dto_hess_structure(const dto_handle* h, int64_t* rows, int64_t* cols) {
+    if (!h || !rows || !cols) return DTO_ERR_INVALID;
+    const DProb& P = h->P;
+    const int z = P.z;
+    long long w = 0;
+    for (int kl = 0; kl < P.nOwn; ++kl) {
+        const long long kg = (long long)P.kb - 1 + kl;
+        for (int l = 0; l < z; ++l) {
+            const long long gcol = kg * z + l + 1;
+            if (kg >= 1)
+                for (int i = 0; i < z; ++i, ++w) {
+                    rows[w] = (kg - 1) * z + i + 1;
+                    cols[w] = gcol;
+                }
+            for (int i = 0; i <= l; ++i, ++w) {
+                rows[w] = kg * z + i + 1;
+                cols[w] = gcol;
+            }
+        }
+    }
+    return w == P.nnz_hess_local ? DTO_OK : DTO_ERR_INVALID;
+}
+
+extern "C" int dto_shard_info(const dto_handle* h, dto_shard_layout* out) {
+    if (!h || !out) return DTO_ERR_INVALID;
+    const DProb& P = h->P;
+    out->z_begin = (long long)(P.kb - 1) * P.z;
+    out->z_end = out->z_begin + (long long)P.nOwn * P.z;
+    out->z_halo_end = out->z_begin + (long long)P.nK * P.z;
+    out->n_local_cons = P.n_cons_local;
+    out->n_local_jac = P.nnz_jac_local;
+    out->n_local_hess = P.nnz_hess_local;
+    return DTO_OK;
+}
+
+extern "C" int dto_shard_maps(const dto_handle* h, int64_t* con_rows, int64_t* jac_pos, int64_t* hess_pos) {
+    if (!h) return DTO_ERR_INVALID;
+    const DProb& P = h->P;
+    const int z = P.z, N = P.N;
+    if (con_rows) {
+        long long w = 0;
+        for (int i = 0; i < P.n_int; ++i)
+            for (int kl = 0; kl < P.nI; ++kl)
+                for (int a = 0; a < P.in[i].n; ++a) con_rows[w++] = h->int_goff[i] + ((long long)P.kb - 1 + kl) * P.in[i].n + a;
+        for (size_t i = 0; i < h->cons.size(); ++i)
+            for (int ti : h->con_own_ti[i])
+                for (int a = 0; a < h->cons[i].g_dim; ++a)
+                    con_rows[w++] = h->sizes_global.n_dynamics_cons + h->con_goff[i] + (long long)ti * h->cons[i].g_dim + a;
+    }
+    if (jac_pos) {
+        // global column pointers from the all-times stored pattern
+        std::vector<long long> gcount((size_t)N * z, 0);
+        for (size_t i = 0; i < h->cons.size(); ++i) {
+            const dto_constraint_desc& s = h->cons[i];
+            for (int t = 0; t < s.n_times; ++t)
+                for (int v = 0; v < s.n_vars; ++v)
+                    for (int a = 0; a < s.g_dim; ++a)
+                        if (h->con_stored_all[i][((size_t)t * s.g_dim + a) * s.n_vars + v])
+                            gcount[(size_t)(h->con_times[i][t] - 1) * z + h->con_var_offs[i][v]]++;
+        }
+        std::vector<long long> gptr((size_t)N * z + 1, 0);
+        for (int k = 0; k < N; ++k) {
+            const long long per = (long long)P.Dsum * ((k >= 1 ? 1 : 0) + (k < N - 1 ? 1 : 0));
+            for (int l = 0; l < z; ++l) gptr[(size_t)k * z + l + 1] = gptr[(size_t)k * z + l] + per + gcount[(size_t)k * z + l];
+        }
+        long long w = 0;
+        size_t ce = 0;
+        for (int kl = 0; kl < P.nK; ++kl) {
+            const long long kg = (long long)P.kb - 1 + kl;
+            for (int l = 0; l < z; ++l) {
+                const long long base = gptr[(size_t)kg * z + l];
+                const bool gprev = kg >= 1, gown = kg < N - 1;
+                for (int i = 0; i < P.n_int; ++i) {
+                    const int dd = P.in[i].n, doff = P.in[i].doff;
+                    const long long prev_start = base + ((gprev && gown) ? 2LL * doff : doff);
+                    const long long own_start = base + ((gprev && gown) ? 2LL * doff + dd : doff);
+                    if (kl >= 1)
+                        for (int a = 0; a < dd; ++a) jac_pos[w++] = prev_start + a;
+                    if (kl < P.nI)
+                        for (int a = 0; a < dd; ++a) jac_pos[w++] = own_start + a;
+                }
+                const long long per = (long long)P.Dsum * ((gprev ? 1 : 0) + (gown ? 1 : 0));
+                long long r = 0;
+                while (ce < h->con_entries.size() && h->con_entries[ce].col_local == (long long)kl * z + l) {
+                    jac_pos[w++] = base + per + r++;
+                    ++ce;
+                }
+            }
+        }
+    }
+    if (hess_pos) {
+        const long long tri = (long long)z * (z + 1) / 2;
+        long long w = 0;
+        for (int kl = 0; kl < P.nOwn; ++kl) {
+            const long long kg = (long long)P.kb - 1 + kl;
+            const long long base = kg == 0 ? 0 : tri + (kg - 1) * ((long long)z * z + tri);
+            const long long cnt = kg == 0 ? tri : (long long)z * z + tri;
+            for (long long e = 0; e < cnt; ++e) hess_pos[w++] = base + e;
+        }
+    }
+    return DTO_OK;
+}
+
+extern "C" int dto_constraint_bounds(const dto_handle* h, double* lower, double* upper) {
+    if (!h || !lower || !upper) return DTO_ERR_INVALID;
+    for (long long r = 0; r < h->P.n_cons_local; ++r) {
+        upper[r] = 0.0;
+        lower[r] = h->row_is_eq[(size_t)r] ? 0.0 : -std::numeric_limits<double>::infinity();
+    }
+    return DTO_OK;
+}
+
+// ---- evaluation ------------------------------------------------------------------------------------
+static int run_eval(dto_handle* h, const double* dZ, double sigma, const double* dmu, double* dJ, double* dgrad, double* dg,
+                    double* djac, double* dhess) {
+    const DProb& P = h->P;
+    if (dhess && !h->eval_hessian) {
+        h->err = "evaluator was created with eval_hessian = false";
+        return DTO_ERR_INVALID;
+    }
+    if (dhess && !dmu) {
+        h->err = "Hessian evaluation needs mu";
+        return DTO_ERR_INVALID;
+    }
+    EvalFlags f{dg != nullptr, djac != nullptr, dhess != nullptr};
+    if (f.want_g || f.want_jac || f.want_hess) {
+        for (int i = 0; i < P.n_int; ++i) {
+            if (P.in[i].kind == DTO_INT_BILINEAR) {
+                bool done = false;
+                if (P.in[i].variant == DTO_VAR_DMMA) done = launch_bilinear_dmma(P, i, dZ, dmu, dg, djac, f, h->stream, &h->launches);
+                if (!done) launch_bilinear_generic(P, i, dZ, dmu, dg, djac, f, h->stream, &h->launches);
+            } else if (P.in[i].kind == DTO_INT_TDBILINEAR) {
+                launch_tdb(P, i, dZ, dmu, dg, djac, f, h->stream, &h->launches);
+            }
+        }
+        if (f.want_g || f.want_jac) launch_analytic(P, dZ, dg, djac, f, h->stream, &h->launches);
+        if (f.want_hess) launch_hessian_assemble(P, dZ, sigma, dmu, dhess, h->stream, &h->launches);
+    }
+    if (dJ || dgrad) launch_objective(P, dZ, dJ, dgrad, h->dpartials, h->stream, &h->launches);
+    CUDA_TRY(h, cudaGetLastError());
+    return DTO_OK;
+}
+
+extern "C" int dto_eval_all_dev(dto_handle* h, const double* dZ, double sigma, const double* dmu, double* dJ, double* dgrad,
+                                double* dg, double* djac, double* dhess) {
+    if (!h || !dZ) return DTO_ERR_INVALID;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    return run_eval(h, dZ, sigma, dmu, dJ, dgrad, dg, djac, dhess);
+}
+
+extern "C" int dto_synchronize(dto_handle* h) {
+    if (!h) return DTO_ERR_INVALID;
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return DTO_OK;
+}
+
+extern "C" int dto_eval_all(dto_handle* h, const double* Z, double sigma, const double* mu, double* J, double* grad, double* g,
+                            double* jac, double* hess) {
+    if (!h || !Z) return DTO_ERR_INVALID;
+    const DProb& P = h->P;
+    const size_t B = (size_t)P.batch;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaMemcpyAsync(h->dZ, Z, sizeof(double) * B * P.n_vars_local, cudaMemcpyHostToDevice, h->stream));
+    if (hess) {
+        if (!mu) {
+            h->err = "Hessian evaluation needs mu";
+            return DTO_ERR_INVALID;
+        }
+        CUDA_TRY(h, cudaMemcpyAsync(h->dmu, mu, sizeof(double) * B * P.n_cons_local, cudaMemcpyHostToDevice, h->stream));
+    }
+    int rc = run_eval(h, h->dZ, sigma, h->dmu, J ? h->dJ : nullptr, grad ? h->dgrad : nullptr, g ? h->dg : nullptr,
+                      jac ? h->djac : nullptr, hess ? h->dhess : nullptr);
+    if (rc != DTO_OK) return rc;
+    if (J) CUDA_TRY(h, cudaMemcpyAsync(J, h->dJ, sizeof(double) * B, cudaMemcpyDeviceToHost, h->stream));
+    if (grad) CUDA_TRY(h, cudaMemcpyAsync(grad, h->dgrad, sizeof(double) * B * P.nOwn * P.z, cudaMemcpyDeviceToHost, h->stream));
+    if (g) CUDA_TRY(h, cudaMemcpyAsync(g, h->dg, sizeof(double) * B * P.n_cons_local, cudaMemcpyDeviceToHost, h->stream));
+    if (jac) CUDA_TRY(h, cudaMemcpyAsync(jac, h->djac, sizeof(double) * B * P.nnz_jac_local, cudaMemcpyDeviceToHost, h->stream));
+    if (hess) CUDA_TRY(h, cudaMemcpyAsync(hess, h->dhess, sizeof(double) * B * P.nnz_hess_local, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return DTO_OK;
+}
+
+extern "C" int dto_eval_objective(dto_handle* h, const double* Z, double* J) {
+    if (!J) return DTO_ERR_INVALID;
+    return dto_eval_all(h, Z, 0.0, nullptr, J, nullptr, nullptr, nullptr, nullptr);
+}
+extern "C" int dto_eval_gradient(dto_handle* h, const double* Z, double* grad) {
+    if (!grad) return DTO_ERR_INVALID;
+    return dto_eval_all(h, Z, 0.0, nullptr, nullptr, grad, nullptr, nullptr, nullptr);
+}
+extern "C" int dto_eval_constraint(dto_handle* h, const double* Z, double* g) {
+    if (!g) return DTO_ERR_INVALID;
+    return dto_eval_all(h, Z, 0.0, nullptr, nullptr, nullptr, g, nullptr, nullptr);
+}
+extern "C" int dto_eval_jacobian(dto_handle* h, const double* Z, double* vals) {
+    if (!vals) return DTO_ERR_INVALID;
+    return dto_eval_all(h, Z, 0.0, nullptr, nullptr, nullptr, nullptr, vals, nullptr);
+}
+extern "C" int dto_eval_hessian(dto_handle* h, const double* Z, double sigma, const double* mu, double* vals) {
+    if (!vals) return DTO_ERR_INVALID;
+    return dto_eval_all(h, Z, sigma, mu, nullptr, nullptr, nullptr, nullptr, vals);
+}
+
+static int jac_product(dto_handle* h, const double* Z, const double* w, double* y, bool transpose) {
+    if (!h || !Z || !w || !y) return DTO_ERR_INVALID;
+    const DProb& P = h->P;
+    const size_t B = (size_t)P.batch;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    if (!h->d_rows0) {
+        std::vector<int64_t> r((size_t)P.nnz_jac_local), c((size_t)P.nnz_jac_local);
+        int rc = dto_jac_structure(h, r.data(), c.data());
+        if (rc != DTO_OK) return rc;
+        // local 0-based rows/cols: a whole-problem handle has local == global numbering
+        if (h->sharded) {
+            h->err = "Jacobian products are not available on knot-range shards";
+            return DTO_ERR_UNSUPPORTED;
+        }
+        for (auto& v : r) v -= 1;
+        for (auto& v : c) v -= 1;
+        h->d_rows0 = (long long*)dev_upload(h, (const long long*)r.data(), r.size());
+        h->d_cols0 = (long long*)dev_upload(h, (const long long*)c.data(), c.size());
+        h->dw = dev_upload<double>(h, nullptr, B * (size_t)std::max(P.n_vars_local, P.n_cons_local));
+        h->dy = dev_upload<double>(h, nullptr, B * (size_t)std::max(P.n_vars_local, P.n_cons_local));
+        if (!h->d_rows0 || !h->d_cols0 || !h->dw || !h->dy) {
+            h->err = "device allocation failed (Jacobian product)";
+            return DTO_ERR_ALLOC;
+        }
+    }
+    const size_t nw = transpose ? (size_t)P.n_cons_local : (size_t)P.n_vars_local;
+    const size_t ny = transpose ? (size_t)P.n_vars_local : (size_t)P.n_cons_local;
+    CUDA_TRY(h, cudaMemcpyAsync(h->dZ, Z, sizeof(double) * B * P.n_vars_local, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(h->dw, w, sizeof(double) * B * nw, cudaMemcpyHostToDevice, h->stream));
+    int rc = run_eval(h, h->dZ, 0.0, nullptr, nullptr, nullptr, nullptr, h->djac, nullptr);
+    if (rc != DTO_OK) return rc;
+    launch_jac_product(P, h->djac, h->d_rows0, h->d_cols0, h->dw, h->dy, transpose, h->stream, &h->launches);
+    CUDA_TRY(h, cudaMemcpyAsync(y, h->dy, sizeof(double) * B * ny, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return DTO_OK;
+}
+extern "C" int dto_eval_jacobian_product(dto_handle* h, const double* Z, const double* w, double* y) {
+    return jac_product(h, Z, w, y, false);
+}
+extern "C" int dto_eval_jacobian_transpose_product(dto_handle* h, const double* Z, const double* w, double* y) {
+    return jac_product(h, Z, w, y, true);
+}
+
+extern "C" int dto_violation_dev(dto_handle* h, const double* dg, double* dviol) {
+    if (!h || !dg || !dviol) return DTO_ERR_INVALID;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    launch_violation(h->P, dg, h->d_row_is_eq, dviol, h->stream, &h->launches);
+    CUDA_TRY(h, cudaGetLastError());
+    return DTO_OK;
+}
+
+// ---- halo over peer memory ---------------------------------------------------------------------------
+extern "C" double* dto_local_Z(dto_handle* h) { return h ? h->dZ : nullptr; }
+
+extern "C" int dto_halo_export(dto_handle* h, void* out64) {
+    if (!h || !out64) return DTO_ERR_INVALID;
+    cudaIpcMemHandle_t mh;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaIpcGetMemHandle(&mh, h->dZ));
+    static_assert(sizeof(mh) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(out64, &mh, 64);
+    return DTO_OK;
+}
+
+extern "C" int dto_halo_import(dto_handle* h, const void* in64) {
+    if (!h || !in64) return DTO_ERR_INVALID;
+    if (h->P.nK == h->P.nOwn) {
+        h->err = "the last shard has no right halo";
+        return DTO_ERR_INVALID;
+    }
+    cudaIpcMemHandle_t mh;
+    memcpy(&mh, in64, 64);
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    void* p = nullptr;
+    CUDA_TRY(h, cudaIpcOpenMemHandle(&p, mh, cudaIpcMemLazyEnablePeerAccess));
+    h->ipc_peer = p;
+    h->P.halo = (const double*)p;  // the neighbour's first owned knot
+    return DTO_OK;
+}
+
+extern "C" int dto_halo_attach(dto_handle* h, dto_handle* right) {
+    if (!h || !right) return DTO_ERR_INVALID;
+    if (h->P.nK == h->P.nOwn) {
+        h->err = "the last shard has no right halo";
+        return DTO_ERR_INVALID;
+    }
+    if (right->device != h->device) {
+        CUDA_TRY(h, cudaSetDevice(h->device));
+        cudaError_t e = cudaDeviceEnablePeerAccess(right->device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+            h->err = std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e);
+            return DTO_ERR_CUDA;
+        }
+        cudaGetLastError();
+    }
+    h->P.halo = right->dZ;
+    return DTO_OK;
+}

@@ -1,0 +1,117 @@
+// Internal device/host structures of libdto_b200.so.  Not part of the ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/dto_b200.h"
+
+#define DTO_MAX_INT 8
+#define DTO_MAX_OBJ 16
+#define DTO_MAX_CON 8
+#define DTO_MAX_KNOTFN_VARS 128
+
+// ---- device views (passed by value to kernels) ------------------------------------------------
+struct DInt {
+    int kind, x_off, n, u_off, m, t_off, order, n_carrier;
+    int doff;           // sum of x_dim of the integrators before this one
+    int hs_stride;      // doubles of compact Hessian scratch per interval
+    int steps;          // tdbilinear RK steps
+    int variant;        // kernel variant chosen on the host
+    long long row_off;  // local row of this integrator's first residual
+    long long G_stride;
+    const double* G;
+    const double *A, *B, *omega, *phi, *D, *omega_d, *phi_d;
+    double* hs;         // [batch][n_intervals][hs_stride]
+};
+
+struct DObj {
+    int kind, fn;
+    double weight;
+    int nv, nt, np;
+    double D;
+    const int* var_offs;
+    const int* own_ti;        // owned entries -> index into params/Qs (original position in `times`)
+    const int* knot_to_own;   // [local knots] -> owned entry index or -1
+    const double* R;
+    const double* baseline;   // nv x N (global knots), may be null
+    const double* params;
+    const double* Qs;
+};
+
+struct DCon {
+    int fn, nv, nt_own, gd, np;
+    long long row_off;            // local row of the first owned row
+    const int* var_offs;
+    const int* own_ti;
+    const int* own_knot;          // local knot (0-based) of each owned entry
+    const int* knot_to_own;
+    const double* params;
+    const long long* jac_pos;     // [nt_own][gd][nv] local Jacobian position or -1
+};
+
+struct DProb {
+    int N;          // global knots
+    int z, dt_off, batch;
+    int kb;         // global 1-based knot of local knot 0
+    int nK;         // local knots including the right halo knot (if any)
+    int nOwn;       // owned knots
+    int nI;         // local intervals (owned knots that have a successor)
+    int first_has_cross;  // shard does not start at knot 1: its first knot still owns a cross block
+    int any_cross;        // some integrator produces cross-knot Hessian entries (tdbilinear order 1)
+    int n_int, n_obj, n_con;
+    int Dsum;       // sum of x_dim over integrators
+    long long n_vars_local;   // nK * z  (stride of one problem in the local Z buffer)
+    long long n_cons_local, nnz_jac_local, nnz_hess_local;
+    const long long* jac_colptr;  // [nK*z + 1] local
+    const double* halo;           // if non-null: knot nK-1 is read from here (peer memory) instead of local Z
+    DInt in[DTO_MAX_INT];
+    DObj ob[DTO_MAX_OBJ];
+    DCon co[DTO_MAX_CON];
+};
+
+// Jacobian position helpers (local numbering) --------------------------------------------------
+// column of local knot kl (0-based), component l: [I1 prev | I1 own | I2 prev | I2 own | ... | constraints]
+__host__ __device__ inline long long jac_own_off(const DProb& P, int kl, int doff, int d) {
+    return (kl >= 1) ? 2LL * doff + d : doff;
+}
+__host__ __device__ inline long long jac_prev_off(const DProb& P, int kl, int doff) {
+    return (kl < P.nI) ? 2LL * doff : doff;
+}
+// Hessian: start of local knot kl's region and of column l inside it
+__host__ __device__ inline long long hess_knot_base(const DProb& P, int kl) {
+    long long z = P.z, tri = z * (z + 1) / 2;
+    if (P.first_has_cross) return (long long)kl * (z * z + tri);
+    return kl == 0 ? 0 : tri + (long long)(kl - 1) * (z * z + tri);
+}
+__host__ __device__ inline bool hess_knot_has_cross(const DProb& P, int kl) { return kl > 0 || P.first_has_cross; }
+
+// variants of the bilinear kernel
+enum { DTO_VAR_GENERIC = 0, DTO_VAR_DMMA = 1 };
+
+// ---- kernel launchers (defined in the .cu files) ------------------------------------------------
+struct EvalFlags {
+    bool want_g, want_jac, want_hess;
+};
+void launch_bilinear_generic(const DProb& P, int ii, const double* Z, const double* mu, double* g, double* jac, EvalFlags f,
+                             cudaStream_t st, long long* launches);
+bool launch_bilinear_dmma(const DProb& P, int ii, const double* Z, const double* mu, double* g, double* jac, EvalFlags f,
+                          cudaStream_t st, long long* launches);
+bool bilinear_dmma_supported(int n, int m);
+bool tdb_available();
+void launch_tdb(const DProb& P, int ii, const double* Z, const double* mu, double* g, double* jac, EvalFlags f, cudaStream_t st,
+                long long* launches);
+void launch_analytic(const DProb& P, const double* Z, double* g, double* jac, EvalFlags f, cudaStream_t st, long long* launches);
+void launch_hessian_assemble(const DProb& P, const double* Z, double sigma, const double* mu, double* hess, cudaStream_t st,
+                             long long* launches);
+void launch_objective(const DProb& P, const double* Z, double* J, double* grad, double* partials, cudaStream_t st,
+                      long long* launches);
+void launch_violation(const DProb& P, const double* g, const int* row_is_eq, double* viol, cudaStream_t st, long long* launches);
+void launch_jac_product(const DProb& P, const double* jac, const long long* rows0, const long long* cols0, const double* w,
+                        double* y, bool transpose, cudaStream_t st, long long* launches);
+// knot-constraint Jacobian at a host point (used at construction for the stored pattern): runs the
+// same device templates so that pattern and values come from one implementation.
+void launch_constraint_pattern_probe(const DProb& P, const double* Z, double* dense_jac /*[sum nt_own*gd*nv]*/, cudaStream_t st,
+                                     long long* launches);

@@ -1,0 +1,163 @@
+"""Problem recipes: the reference's test/benchmark fixtures and the BASELINE.json configurations,
+built through this package's mirror of the reference API with synthetic (seeded NumPy PCG64) data.
+
+  readme_problem            README.md:68-95 (BASELINE config c1)
+  standard_problem          test/test_snippets.jl:27-54 + test/test_utils.jl:113-178 (evaluator test problem)
+  evaluator_test_problem    src/solvers/evaluator.jl:656-684
+  bilinear_benchmark        benchmark/problem_utils.jl:10-42  (published micro-benchmark shape, N=51)
+  scaled_problem            benchmark/problem_utils.jl:49-77  (BASELINE config c5 shape, c4 shape)
+  quantum_gate_problem      BASELINE config c2: isomorphic state dim 32, 4 drives, free dt + MinimumTime
+  carrier_problem           BASELINE config c3: TimeDependentBilinear + Derivative chain + knot constraints
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .components import (BilinearIntegrator, CarrierGenerator, DerivativeIntegrator, MinimumTimeObjective,
+                         NonlinearKnotPointConstraint, NormMinus, QuadraticRegularizer, SqDist, TerminalObjective,
+                         TimeDependentBilinearIntegrator)
+from .evaluator import DirectTrajOptProblem
+from .trajectory import NamedTrajectory
+
+GX = np.array([[0, 0, 0, 1], [0, 0, 1, 0], [0, -1, 0, 0], [-1, 0, 0, 0]], float)
+GY = np.array([[0, -1, 0, 0], [1, 0, 0, 0], [0, 0, 0, -1], [0, 0, 1, 0]], float)
+GZ = np.array([[0, 0, 1, 0], [0, 0, 0, -1], [-1, 0, 0, 0], [0, 1, 0, 0]], float)
+
+
+def readme_problem(N=50, seed=42):
+    rng = np.random.default_rng(seed)
+    traj = NamedTrajectory({"x": rng.standard_normal((2, N)), "u": rng.standard_normal((1, N)), "dt": np.full(N, 0.1)},
+                           timestep="dt", controls=("u",), initial={"x": [0.0, 0.0]}, final={"x": [1.0, 0.0]})
+    G_drift = np.array([[-0.1, 1.0], [-1.0, -0.1]])
+    G_drives = [np.array([[0.0, 1.0], [1.0, 0.0]])]
+    G = lambda u: G_drift + sum(ui * Gi for ui, Gi in zip(u, G_drives))
+    integrator = BilinearIntegrator(G, "x", "u", traj)
+    obj = QuadraticRegularizer("u", traj, 1.0)
+    return DirectTrajOptProblem(traj, obj, integrator)
+
+
+def bilinear_dynamics_and_trajectory(N=10, dt=0.1, u_bound=0.1, omega=0.1, add_time=False, seed=0):
+    rng = np.random.default_rng(seed)
+    G = lambda u: omega * GZ + u[0] * GX + u[1] * GY
+    comps = {
+        "x": 2 * rng.random((4, N)) - 1,
+        "u": u_bound * (2 * rng.random((2, N)) - 1),
+        "du": rng.standard_normal((2, N)),
+        "ddu": rng.standard_normal((2, N)),
+        "dt": np.full(N, dt),
+    }
+    if add_time:
+        comps["t"] = np.arange(N) * dt
+    traj = NamedTrajectory(comps, controls=("ddu", "dt"), timestep="dt", bounds={"u": u_bound, "dt": (0.01, 0.5)},
+                           initial={"x": [1.0, 0, 0, 0], "u": [0, 0]}, final={"u": [0, 0]}, goal={"x": [0.0, 1.0, 0, 0]})
+    return G, traj
+
+
+def standard_problem(N=10, seed=0):
+    G, traj = bilinear_dynamics_and_trajectory(N=N, seed=seed)
+    integrators = [BilinearIntegrator(G, "x", "u", traj), DerivativeIntegrator("u", "du", traj), DerivativeIntegrator("du", "ddu", traj)]
+    J = TerminalObjective(SqDist(traj.goal["x"]), "x", traj)
+    J = J + QuadraticRegularizer("u", traj, 1.0)
+    J = J + QuadraticRegularizer("du", traj, 1.0)
+    J = J + MinimumTimeObjective(traj)
+    g_u_norm = NonlinearKnotPointConstraint(NormMinus(1.0), "u", traj, times=range(2, traj.N), equality=False)
+    return DirectTrajOptProblem(traj, J, integrators, constraints=[g_u_norm])
+
+
+def evaluator_test_problem(N=10, seed=0):
+    G, traj = bilinear_dynamics_and_trajectory(N=N, seed=seed)
+    integrators = [BilinearIntegrator(G, "x", "u", traj), DerivativeIntegrator("u", "du", traj), DerivativeIntegrator("du", "ddu", traj)]
+    J = TerminalObjective(SqDist(traj.goal["x"]), "x", traj)
+    J = J + QuadraticRegularizer("u", traj, 2.0e-1)
+    J = J + QuadraticRegularizer("du", traj, 3.0e-1)
+    J = J + QuadraticRegularizer("ddu", traj, 4.0e-1)
+    J = J + MinimumTimeObjective(traj)
+    g_u_norm = NonlinearKnotPointConstraint(NormMinus(1.0), "u", traj, times=range(2, traj.N), equality=False)
+    return DirectTrajOptProblem(traj, J, integrators, constraints=[g_u_norm])
+
+
+def bilinear_benchmark(N=51, seed=42):
+    G, traj = bilinear_dynamics_and_trajectory(N=N, seed=seed)
+    integrators = [BilinearIntegrator(G, "x", "u", traj), DerivativeIntegrator("u", "du", traj), DerivativeIntegrator("du", "ddu", traj)]
+    J = QuadraticRegularizer("u", traj, 1.0) + QuadraticRegularizer("du", traj, 1.0)
+    return DirectTrajOptProblem(traj, J, integrators)
+
+
+def scaled_problem(N, state_dim, n_controls=2, seed=42, generator_scale=1.0):
+    """make_scaled_problem: random dense generators, x, u, du, dt; Bilinear + Derivative(u, du); QuadReg(u)."""
+    rng = np.random.default_rng(seed)
+    G_drift = generator_scale * rng.standard_normal((state_dim, state_dim))
+    G_drives = [generator_scale * rng.standard_normal((state_dim, state_dim)) for _ in range(n_controls)]
+    x_init = np.zeros(state_dim)
+    x_init[0] = 1.0
+    x_goal = np.zeros(state_dim)
+    x_goal[min(1, state_dim - 1)] = 1.0
+    traj = NamedTrajectory(
+        {"x": rng.standard_normal((state_dim, N)), "u": 0.1 * rng.standard_normal((n_controls, N)),
+         "du": rng.standard_normal((n_controls, N)), "dt": np.full(N, 0.1)},
+        controls=("du", "dt"), timestep="dt", bounds={"u": 1.0, "dt": (0.01, 0.5)},
+        initial={"x": x_init, "u": np.zeros(n_controls)}, final={"u": np.zeros(n_controls)}, goal={"x": x_goal})
+    integrators = [BilinearIntegrator((G_drift, G_drives), "x", "u", traj), DerivativeIntegrator("u", "du", traj)]
+    J = QuadraticRegularizer("u", traj, 1.0)
+    return DirectTrajOptProblem(traj, J, integrators)
+
+
+def iso_generator(H):
+    """Real isomorphism of -iH acting on [re; im]: G = [[Im H, Re H], [-Re H, Im H]]."""
+    return np.block([[H.imag, H.real], [-H.real, H.imag]])
+
+
+def quantum_gate_problem(N=2000, levels=16, n_drives=4, seed=42, dt=0.1):
+    """BASELINE config c2: a `levels`-level complex system in the real isomorphism
+    (state dim 2*levels), `n_drives` drives + drift, Hermitian random Hamiltonians scaled so that
+    ||dt*G(u)||_1 ~ 1; x ~ U(-1,1), u ~ 0.1 U(-1,1), free dt; QuadReg(u) + MinimumTime + terminal
+    ||x - x_goal||^2."""
+    rng = np.random.default_rng(seed)
+    n = 2 * levels
+
+    def herm():
+        M = rng.standard_normal((levels, levels)) + 1j * rng.standard_normal((levels, levels))
+        return (M + M.conj().T) / 2
+
+    G0 = iso_generator(herm())
+    Gd = [iso_generator(herm()) for _ in range(n_drives)]
+    scale = 1.0 / (dt * np.abs(G0).sum(axis=0).max())
+    G0 = G0 * scale
+    Gd = [g * scale for g in Gd]
+    x_goal = np.zeros(n)
+    x_goal[1] = 1.0
+    traj = NamedTrajectory(
+        {"x": 2 * rng.random((n, N)) - 1, "u": 0.1 * (2 * rng.random((n_drives, N)) - 1), "dt": np.full(N, dt)},
+        controls=("u", "dt"), timestep="dt", bounds={"u": 1.0, "dt": (0.01, 0.5)}, goal={"x": x_goal})
+    integ = BilinearIntegrator((G0, Gd), "x", "u", traj)
+    J = QuadraticRegularizer("u", traj, 1.0) + MinimumTimeObjective(traj, D=1.0) + TerminalObjective(SqDist(x_goal), "x", traj)
+    return DirectTrajOptProblem(traj, J, [integ])
+
+
+def carrier_problem(N=1000, state_dim=64, n_drives=2, seed=42, dt=0.05, spline_order=1, steps=0):
+    """BASELINE config c3: TimeDependentBilinearIntegrator with carrier-modulated drives,
+    DerivativeIntegrator chain (u, du, ddu), knot constraint ||u|| - 1 <= 0 at knots 2..N-1."""
+    rng = np.random.default_rng(seed)
+    n = state_dim
+
+    def skew():
+        M = rng.standard_normal((n, n))
+        return (M - M.T) / 2
+
+    G0 = skew()
+    G0 /= np.abs(G0).sum(axis=0).max()
+    A = np.stack([skew() for _ in range(n_drives)])
+    B = np.stack([skew() for _ in range(n_drives)])
+    A /= np.abs(A).sum(axis=1).max()
+    B /= np.abs(B).sum(axis=1).max()
+    omega = 1.0 + rng.random(n_drives)
+    gen = CarrierGenerator(G0, A, B, omega, np.zeros(n_drives))
+    comps = {"x": 2 * rng.random((n, N)) - 1, "u": 0.3 * (2 * rng.random((n_drives, N)) - 1),
+             "du": rng.standard_normal((n_drives, N)), "ddu": rng.standard_normal((n_drives, N)),
+             "t": np.arange(N) * dt, "dt": np.full(N, dt)}
+    traj = NamedTrajectory(comps, controls=("ddu", "dt"), timestep="dt")
+    integrators = [TimeDependentBilinearIntegrator(gen, "x", "u", "t", traj, spline_order=spline_order, steps=steps),
+                   DerivativeIntegrator("u", "du", traj), DerivativeIntegrator("du", "ddu", traj)]
+    J = QuadraticRegularizer("u", traj, 1.0) + QuadraticRegularizer("du", traj, 1.0) + MinimumTimeObjective(traj)
+    con = NonlinearKnotPointConstraint(NormMinus(1.0), "u", traj, times=range(2, N), equality=False)
+    return DirectTrajOptProblem(traj, J, integrators, constraints=[con])

@@ -1,0 +1,141 @@
+"""Parity of the CUDA evaluator (through the C ABI) against the CPU oracle on identical seeded
+trajectories: structures bit-exact, values within 1e-10 relative to the array's max-norm
+(BASELINE.json north_star tolerance; SURVEY.md section 7 explains why the norm is per block)."""
+import numpy as np
+import pytest
+
+import dto_b200 as dto
+import dto_oracle as orc
+from dto_b200 import problem_templates as pt
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-10
+
+
+def relerr(got, ref):
+    scale = max(np.abs(ref).max() if ref.size else 0.0, 1e-300)
+    return np.abs(got - ref).max() / scale if ref.size else 0.0
+
+
+PROBLEMS = {
+    "readme_c1": lambda: pt.readme_problem(N=50),
+    "standard": lambda: pt.standard_problem(N=10),
+    "evaluator_test": lambda: pt.evaluator_test_problem(N=10),
+    "benchmark_N51": lambda: pt.bilinear_benchmark(N=51),
+    "scaled_n5": lambda: pt.scaled_problem(N=6, state_dim=5, n_controls=2, generator_scale=0.7),
+    "scaled_n8": lambda: pt.scaled_problem(N=12, state_dim=8, n_controls=2),
+    "scaled_n16_bignorm": lambda: pt.scaled_problem(N=8, state_dim=16, n_controls=2),
+    "gate_n32": lambda: pt.quantum_gate_problem(N=12, levels=16, n_drives=4),
+    "gate_n6": lambda: pt.quantum_gate_problem(N=7, levels=3, n_drives=2),
+    "gate_n64": lambda: pt.quantum_gate_problem(N=5, levels=32, n_drives=2),
+}
+
+
+@pytest.fixture(scope="module", params=list(PROBLEMS))
+def case(request):
+    prob = PROBLEMS[request.param]()
+    ev = dto.Evaluator(prob)
+    yield request.param, prob, ev
+    ev.close()
+
+
+def test_structures_bit_exact(case):
+    name, prob, ev = case
+    spec, Z = prob.to_spec(), prob.trajectory.datavec.copy()
+    jr, jc = ev.jacobian_structure()
+    orow, ocol = orc.jacobian_structure(spec, Z)
+    assert jr.size == orow.size and np.array_equal(jr, orow) and np.array_equal(jc, ocol)
+    hr, hc = ev.hessian_lagrangian_structure()
+    orow, ocol = orc.hessian_structure(spec, Z)
+    assert hr.size == orow.size and np.array_equal(hr, orow) and np.array_equal(hc, ocol)
+    nd, nn = orc.n_constraints(spec)
+    assert (ev.n_dynamics_constraints, ev.n_nonlinear_constraints, ev.n_constraints) == (nd, nn, nd + nn)
+
+
+def test_values_match_oracle(case):
+    name, prob, ev = case
+    spec = prob.to_spec()
+    rng = np.random.default_rng(7)
+    Z0 = prob.trajectory.datavec.copy()
+    Z = Z0 + 0.05 * rng.standard_normal(Z0.size)  # an iterate away from the initial point
+    Z[spec["components"][spec["timestep"]][0] :: spec["z"]] = np.abs(Z[spec["components"][spec["timestep"]][0] :: spec["z"]])
+    jst, hst = orc.jacobian_structure(spec, Z0), orc.hessian_structure(spec, Z0)
+    mu = rng.random(ev.n_constraints)
+    sigma = 2.0
+
+    assert abs(ev.eval_objective(Z) - orc.eval_objective(spec, Z)) <= TOL * max(1.0, abs(orc.eval_objective(spec, Z)))
+    grad = np.full(ev.n_vars, np.nan)
+    ev.eval_objective_gradient(grad, Z)
+    assert relerr(grad, orc.eval_objective_gradient(spec, Z)) <= TOL
+    g = np.full(ev.n_constraints, np.nan)
+    ev.eval_constraint(g, Z)
+    assert relerr(g, orc.eval_constraint(spec, Z)) <= TOL
+    J = np.full(ev.nnz_jacobian, np.nan)
+    ev.eval_constraint_jacobian(J, Z)
+    assert relerr(J, orc.eval_constraint_jacobian(spec, Z, jst)) <= TOL
+    H = np.full(ev.nnz_hessian, np.nan)
+    ev.eval_hessian_lagrangian(H, Z, sigma, mu)
+    Href = orc.eval_hessian_lagrangian(spec, Z, sigma, mu, hst)
+    assert relerr(H, Href) <= TOL
+    # sigma == 0 skips the objective (evaluator.jl:626)
+    ev.eval_hessian_lagrangian(H, Z, 0.0, mu)
+    assert relerr(H, orc.eval_hessian_lagrangian(spec, Z, 0.0, mu, hst)) <= TOL
+
+
+def test_fused_eval_all_equals_separate_callbacks(case):
+    name, prob, ev = case
+    rng = np.random.default_rng(11)
+    Z = prob.trajectory.datavec.copy()
+    mu = rng.random(ev.n_constraints)
+    Jv, grad = np.empty(1), np.empty(ev.n_vars)
+    g, jac, hess = np.empty(ev.n_constraints), np.empty(ev.nnz_jacobian), np.empty(ev.nnz_hessian)
+    ev.eval_all(Z, 1.5, mu, Jv, grad, g, jac, hess)
+    g2, jac2, hess2, grad2 = np.empty_like(g), np.empty_like(jac), np.empty_like(hess), np.empty_like(grad)
+    ev.eval_constraint(g2, Z)
+    ev.eval_constraint_jacobian(jac2, Z)
+    ev.eval_hessian_lagrangian(hess2, Z, 1.5, mu)
+    ev.eval_objective_gradient(grad2, Z)
+    assert np.array_equal(g, g2) and np.array_equal(jac, jac2) and np.array_equal(hess, hess2) and np.array_equal(grad, grad2)
+    assert Jv[0] == ev.eval_objective(Z)
+
+
+def test_jacobian_products(case):
+    """evaluator.jl:808-853: products vs the dense Jacobian, atol 1e-10."""
+    name, prob, ev = case
+    rng = np.random.default_rng(5)
+    Z = prob.trajectory.datavec.copy()
+    jr, jc = ev.jacobian_structure()
+    vals = np.empty(ev.nnz_jacobian)
+    ev.eval_constraint_jacobian(vals, Z)
+    Jd = np.zeros((ev.n_constraints, ev.n_vars))
+    np.add.at(Jd, (jr - 1, jc - 1), vals)
+    w = rng.standard_normal(ev.n_vars)
+    y = np.empty(ev.n_constraints)
+    ev.eval_constraint_jacobian_product(y, Z, w)
+    assert np.allclose(y, Jd @ w, atol=1e-10 * max(1, np.abs(Jd @ w).max()))
+    w = rng.standard_normal(ev.n_constraints)
+    y = np.empty(ev.n_vars)
+    ev.eval_constraint_jacobian_transpose_product(y, Z, w)
+    assert np.allclose(y, Jd.T @ w, atol=1e-10 * max(1, np.abs(Jd.T @ w).max()))
+
+
+def test_features_and_bounds():
+    prob = pt.standard_problem(N=6)
+    ev = dto.Evaluator(prob, eval_hessian=False)
+    assert ev.features_available() == ["Grad", "Jac"]
+    H = np.empty(ev.nnz_hessian)
+    with pytest.raises(dto.DtoError):
+        ev.eval_hessian_lagrangian(H, prob.trajectory.datavec, 1.0, np.ones(ev.n_constraints))
+    lo, hi = ev.constraint_bounds()
+    assert np.all(hi == 0) and np.all(lo[: ev.n_dynamics_constraints] == 0) and np.all(np.isneginf(lo[ev.n_dynamics_constraints :]))
+    ev.close()
+    assert dto.Evaluator(prob).features_available() == ["Grad", "Jac", "Hess"]
+
+
+def test_unsupported_components_raise_at_construction():
+    G, traj = pt.bilinear_dynamics_and_trajectory(N=5)
+    with pytest.raises(dto.UnsupportedComponent):
+        dto.BilinearIntegrator(lambda u: pt.GZ + u[0] ** 2 * pt.GX, "x", "u", traj)
+    with pytest.raises(dto.UnsupportedComponent):
+        dto.NonlinearKnotPointConstraint(lambda u: [u[0]], "u", traj)
