@@ -1,0 +1,295 @@
+#!/usr/bin/env python
+"""bench.py -- full NLP evaluations per second of the B200 evaluator (BASELINE.json metric).
+
+One *step* = one full evaluation of one iterate of the workload problem: constraint residual +
+sparse constraint Jacobian + sparse Hessian of the Lagrangian (objective and gradient are computed
+in the same pass and are part of the step).  Workload at N=1: BASELINE.json configs[1] ("c2"):
+bilinear isomorphic-state quantum gate problem, state dim 32, 4 drives, N=2000 knots, free dt +
+MinimumTimeObjective.  With --gpus N > 1 every rank evaluates its own independent problem of the
+same shape (problem-parallel, no data-path collective): weak scaling.
+
+  value      whole-job evaluations/s with Z, mu and all outputs resident in HBM (dto_eval_all_dev)
+  e2e        the same metric through the host-pointer C-ABI call (dto_eval_all) with pinned HOST
+             buffers: H2D of Z and mu and D2H of all five outputs inside the timed region
+  roofline   dominant kernel (K1, the bilinear interval kernel): algorithmic FP64 flops per launch
+             (SURVEY.md section 8d canonical count C1) / CUDA-event duration measured live
+  cpu_baseline   the CPU oracle port timed on the host cores on a bounded sample of the same workload
+
+`--impl reference` times the reference's CPU algorithm for the path (the oracle port; the reference
+is Julia and neither Julia nor its packages exist here or on the GPU box) on the same config.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (builder kwargs, description)
+    "c2": dict(N=2000, levels=16, n_drives=4),
+}
+FP64_PEAK_TFLOPS = 37.1  # measured on this pool's B200: DMMA m8n8k4 saturation (profiles/r01_fp64_peaks_and_box_probe.log)
+TAYLOR_T = 20            # canonical term count of SURVEY.md section 8d (C1)
+
+
+def canonical_flops_per_interval(n, m, T=TAYLOR_T, s=0):
+    """SURVEY.md section 8d, count C1: (i) full propagator by Pade-13 scaling and squaring,
+    (ii) forward second-order directional propagation, (iii) adjoint first-order propagation."""
+    p = m + 1
+    i = 2 * n**3 * (6 + s) + (8.0 / 3.0) * n**3
+    ii = (1 + 2 * p + 3 * p * (p + 1) / 2) * T * 2 * n * n
+    iii = (1 + 2 * p) * T * 2 * n * n
+    return i + ii + iii
+
+
+def build_problem(workload, seed):
+    import dto_b200 as dto
+
+    kw = WORKLOADS[workload]
+    return dto.problem_templates.quantum_gate_problem(seed=seed, **kw)
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi SM clocks and throttle reasons while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.rows = index, threading.Event(), []
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.1)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def cpu_port_rate(prob, sample_intervals, threads):
+    """Oracle port timed on the host: full constraint+Jacobian+Hessian work of `sample_intervals`
+    knot intervals (the reference's cost is linear in N: serial knot loop,
+    src/integrators/bilinear_integrator.jl:99,113,142), scaled to evaluations/s of the whole problem."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import dto_oracle_c as oc
+
+    return oc.time_port(prob, sample_intervals, threads)
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    prob = build_problem(args.workload, seed=42)
+    threads = os.cpu_count() or 1
+    vals = []
+    sample = args.ref_sample
+    for i in range(args.warmup + args.steps):
+        rate, info = cpu_port_rate(prob, sample, threads)
+        if i >= args.warmup:
+            vals.append(rate)
+    v = float(np.mean(vals))
+    t = prob.trajectory
+    line = {
+        "impl": "reference", "metric": "full NLP evals/sec (constraint+Jacobian+Hessian)", "value": v, "unit": "evals/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / v, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: bilinear quantum gate, state dim {t.dims['x']}, {t.dims['u']} drives, N={t.N}, free dt + MinimumTime"},
+        "cpu_baseline": {"value": v, "unit": "evals/s", "cores": info["threads"], "kind": "port", "sample": info["sample"]},
+        "e2e": {"value": v, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference is Julia (absent here and on the GPU box); this arm times oracle/dto_oracle.c, a C restatement of the reference's ForwardDiff-through-expv algorithm, OpenMP over knot intervals",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=list(WORKLOADS))
+    ap.add_argument("--cpu-sample", type=int, default=24, help="knot intervals timed for cpu_baseline")
+    ap.add_argument("--ref-sample", type=int, default=32, help="knot intervals per step of --impl reference")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import dto_b200 as dto
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the evaluator has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    prob = build_problem(args.workload, seed=42 + rank)  # an independent problem per rank
+    t = prob.trajectory
+    n, m = t.dims["x"], t.dims["u"]
+    ev = dto.Evaluator(prob, device=local_rank)
+    rng = np.random.default_rng(1234 + rank)
+    Z = t.datavec.copy()
+    mu = rng.random(ev.n_constraints)
+    sigma = 1.0
+
+    dev = torch.device("cuda", local_rank)
+    stream = torch.cuda.ExternalStream(ev.stream, device=dev)
+    dZ = torch.from_numpy(Z).to(dev)
+    dmu = torch.from_numpy(mu).to(dev)
+    dJ = torch.empty(1, dtype=torch.float64, device=dev)
+    dgrad = torch.empty(ev.n_vars, dtype=torch.float64, device=dev)
+    dg = torch.empty(ev.n_constraints, dtype=torch.float64, device=dev)
+    djac = torch.empty(ev.nnz_jacobian, dtype=torch.float64, device=dev)
+    dhess = torch.empty(ev.nnz_hessian, dtype=torch.float64, device=dev)
+    flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)  # > 126 MB L2
+    torch.cuda.synchronize()
+
+    def step_dev():
+        ev.eval_all_dev(dZ.data_ptr(), sigma, dmu.data_ptr(), dJ.data_ptr(), dgrad.data_ptr(), dg.data_ptr(), djac.data_ptr(),
+                        dhess.data_ptr())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing ------------------------------------------------------------------
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            flush.zero_()
+            step_dev()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = ev.launch_count
+    ev.kernel_timing(True)
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    t_wall0 = time.perf_counter()
+    with torch.cuda.stream(stream):
+        for e0, e1 in evs:
+            flush.zero_()  # L2 flush between timed iterations (outside the per-step events)
+            e0.record(stream)
+            step_dev()
+            e1.record(stream)
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    step_ms = [e0.elapsed_time(e1) for e0, e1 in evs]
+    k1_ms, k1_n = ev.kernel_time_ms()
+    ev.kernel_timing(False)
+    launches = ev.launch_count - l0
+    dev_ms = float(np.sum(step_ms))
+
+    # ---- end-to-end through the host-pointer C ABI (pinned host buffers) -------------------------
+    hZ = torch.from_numpy(Z).pin_memory()
+    hmu = torch.from_numpy(mu).pin_memory()
+    hJ = torch.empty(1, dtype=torch.float64).pin_memory()
+    hgrad = torch.empty(ev.n_vars, dtype=torch.float64).pin_memory()
+    hg = torch.empty(ev.n_constraints, dtype=torch.float64).pin_memory()
+    hjac = torch.empty(ev.nnz_jacobian, dtype=torch.float64).pin_memory()
+    hhess = torch.empty(ev.nnz_hessian, dtype=torch.float64).pin_memory()
+    nz, nmu = hZ.numpy(), hmu.numpy()
+    outs = [a.numpy() for a in (hJ, hgrad, hg, hjac, hhess)]
+    for _ in range(args.warmup):
+        ev.eval_all(nz, sigma, nmu, *outs)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ev.eval_all(nz, sigma, nmu, *outs)  # synchronises the stream before returning
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    sampler.stop_flag.set()
+    sampler.join()
+    h2d = 8 * (Z.size + mu.size)
+    d2h = 8 * (1 + ev.n_vars + ev.n_constraints + ev.nnz_jacobian + ev.nnz_hessian)
+
+    # parity guard on the timed outputs: the device-resident and host paths must agree bit for bit
+    same = bool(np.array_equal(outs[3], djac.cpu().numpy()) and np.array_equal(outs[4], dhess.cpu().numpy()))
+
+    # ---- max over ranks ---------------------------------------------------------------------------
+    agg = torch.tensor([dev_ms, e2e_s, k1_ms / max(k1_n, 1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(agg, op=dist.ReduceOp.MAX)
+    dev_ms_max, e2e_s_max, k1_avg_ms = agg.tolist()
+
+    if rank == 0:
+        evals = world * args.steps
+        value = evals / (dev_ms_max * 1e-3)
+        e2e_value = evals / e2e_s_max
+        flops_launch = canonical_flops_per_interval(n, m) * (t.N - 1)
+        achieved = flops_launch / (k1_avg_ms * 1e-3) * 1e-12
+        line = {
+            "metric": "full NLP evals/sec (constraint+Jacobian+Hessian)", "value": value, "unit": "evals/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {
+                "workload": f"{args.workload}: bilinear quantum gate, state dim {n}, {m} drives, N={t.N}, free dt + MinimumTime "
+                            f"(z={t.dim}, {ev.n_vars} vars, {ev.n_constraints} rows, {ev.nnz_jacobian} Jac nnz, {ev.nnz_hessian} Hess nnz)",
+                "per_rank": "one independent problem per GPU (problem-parallel, no collective)",
+                "l2": "256 MB memset between timed steps (outside the per-step CUDA events)",
+                "step": "objective+gradient+constraint+Jacobian+Hessian of one iterate, outputs left in HBM",
+                "kernel_variant": ev.kernel_variant(0),
+            },
+            "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_s_max / args.steps * 1e3, "matches_device_path": same},
+            "gpu_launches": int(launches),
+            "clocks": sampler.summary(),
+            "roofline": {
+                "bound": "tensor", "achieved": achieved, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": achieved / FP64_PEAK_TFLOPS,
+                "traffic": None, "kernel": "bilinear interval kernel (K1)", "kernel_ms": k1_avg_ms,
+                "kernel_share_of_step": k1_avg_ms / (dev_ms_max / args.steps),
+                "algorithmic_flops_per_launch": flops_launch,
+                "peak_source": "FP64 DMMA m8n8k4 saturation measured on this pool (profiles/r01_fp64_peaks_and_box_probe.log); "
+                               "MEASURED_PEAKS.json carries no FP64 figure; cuBLAS DGEMM 8192^3 measured 35.5 TFLOP/s",
+                "hbm_gbs_step": 8 * (2 * Z.size + 2 * mu.size + ev.n_constraints + ev.nnz_jacobian + ev.nnz_hessian) / (dev_ms_max / args.steps * 1e-3) * 1e-9,
+            },
+            "wall_s_timed_region": t_wall,
+        }
+        if not args.no_cpu_baseline:
+            try:
+                threads = os.cpu_count() or 1
+                rate, info = cpu_port_rate(prob, args.cpu_sample, threads)
+                line["cpu_baseline"] = {"value": rate, "unit": "evals/s", "cores": info["threads"], "kind": "port", "sample": info["sample"]}
+            except Exception as e:  # the baseline must never take the GPU number down with it
+                line["cpu_baseline"] = {"value": None, "unit": "evals/s", "cores": 0, "kind": "port", "sample": f"failed: {e}"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    ev.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -53,6 +53,12 @@ struct dto_handle {
     void* ipc_peer = nullptr;
     long long launches = 0;
     std::vector<std::string> variants;
+    // optional device timing of the interval kernels (bench.py's roofline numerator)
+    int timing = 0;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
+    size_t ev_used = 0;
+    double k1_ms = 0.0;
+    long long k1_count = 0;
 };
 
 #define CUDA_TRY(h, call)                                                                       \
@@ -89,6 +95,10 @@ extern "C" void dto_destroy(dto_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->ipc_peer) cudaIpcCloseMemHandle(h->ipc_peer);
+    for (auto& e : h->ev_pool) {
+        cudaEventDestroy(e.first);
+        cudaEventDestroy(e.second);
+    }
     for (void* p : h->allocs) cudaFree(p);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -108,6 +118,7 @@ extern "C" int dto_create(const dto_problem_desc* d, dto_handle** out) {
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return fail_create(nullptr, DTO_ERR_CUDA, "no CUDA device: libdto_b200 has no CPU fallback");
+    cudaGetLastError();  // do not inherit a stale error from an earlier, unrelated call
     dto_handle* h = new (std::nothrow) dto_handle();
     if (!h) return fail_create(nullptr, DTO_ERR_ALLOC, "out of host memory");
     if (d->device >= 0) {
@@ -636,6 +647,9 @@ static int run_eval(dto_handle* h, const double* dZ, double sigma, const double*
     EvalFlags f{dg != nullptr, djac != nullptr, dhess != nullptr};
     if (f.want_g || f.want_jac || f.want_hess) {
         for (int i = 0; i < P.n_int; ++i) {
+            if (P.in[i].kind == DTO_INT_DERIVATIVE) continue;
+            const bool timed = h->timing && h->ev_used < h->ev_pool.size();
+            if (timed) cudaEventRecord(h->ev_pool[h->ev_used].first, h->stream);
             if (P.in[i].kind == DTO_INT_BILINEAR) {
                 bool done = false;
                 if (P.in[i].variant == DTO_VAR_DMMA) done = launch_bilinear_dmma(P, i, dZ, dmu, dg, djac, f, h->stream, &h->launches);
@@ -643,6 +657,7 @@ static int run_eval(dto_handle* h, const double* dZ, double sigma, const double*
             } else if (P.in[i].kind == DTO_INT_TDBILINEAR) {
                 launch_tdb(P, i, dZ, dmu, dg, djac, f, h->stream, &h->launches);
             }
+            if (timed) cudaEventRecord(h->ev_pool[h->ev_used++].second, h->stream);
         }
         if (f.want_g || f.want_jac) launch_analytic(P, dZ, dg, djac, f, h->stream, &h->launches);
         if (f.want_hess) launch_hessian_assemble(P, dZ, sigma, dmu, dhess, h->stream, &h->launches);
@@ -670,6 +685,10 @@ extern "C" int dto_eval_all(dto_handle* h, const double* Z, double sigma, const 
     if (!h || !Z) return DTO_ERR_INVALID;
     const DProb& P = h->P;
     const size_t B = (size_t)P.batch;
+    if (hess && !h->eval_hessian) {
+        h->err = "evaluator was created with eval_hessian = false";
+        return DTO_ERR_INVALID;
+    }
     CUDA_TRY(h, cudaSetDevice(h->device));
     CUDA_TRY(h, cudaMemcpyAsync(h->dZ, Z, sizeof(double) * B * P.n_vars_local, cudaMemcpyHostToDevice, h->stream));
     if (hess) {
@@ -808,5 +827,38 @@ extern "C" int dto_halo_attach(dto_handle* h, dto_handle* right) {
         cudaGetLastError();
     }
     h->P.halo = right->dZ;
+    return DTO_OK;
+}
+
+// ---- instrumentation: device time of the interval kernels ------------------------------------------
+extern "C" int dto_kernel_timing(dto_handle* h, int enable) {
+    if (!h) return DTO_ERR_INVALID;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    if (enable && h->ev_pool.empty()) {
+        h->ev_pool.resize(4096);
+        for (auto& e : h->ev_pool) {
+            CUDA_TRY(h, cudaEventCreate(&e.first));
+            CUDA_TRY(h, cudaEventCreate(&e.second));
+        }
+    }
+    h->timing = enable;
+    h->ev_used = 0;
+    h->k1_ms = 0.0;
+    h->k1_count = 0;
+    return DTO_OK;
+}
+
+extern "C" int dto_kernel_time_ms(dto_handle* h, double* ms_sum, int64_t* launches) {
+    if (!h || !ms_sum || !launches) return DTO_ERR_INVALID;
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    for (size_t i = 0; i < h->ev_used; ++i) {
+        float ms = 0.f;
+        CUDA_TRY(h, cudaEventElapsedTime(&ms, h->ev_pool[i].first, h->ev_pool[i].second));
+        h->k1_ms += ms;
+        h->k1_count += 1;
+    }
+    h->ev_used = 0;
+    *ms_sum = h->k1_ms;
+    *launches = h->k1_count;
     return DTO_OK;
 }

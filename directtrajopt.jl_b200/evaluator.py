@@ -350,5 +350,13 @@ class Evaluator:
     def launch_count(self):
         return int(self._lib.dto_launch_count(self._h))
 
+    def kernel_timing(self, enable=True):
+        _lib.check(self._lib.dto_kernel_timing(self._h, int(enable)), self._h)
+
+    def kernel_time_ms(self):
+        ms, n = C.c_double(), C.c_int64()
+        _lib.check(self._lib.dto_kernel_time_ms(self._h, C.byref(ms), C.byref(n)), self._h)
+        return ms.value, n.value
+
     def kernel_variant(self, i=0):
         return self._lib.dto_kernel_variant(self._h, i).decode()

@@ -217,8 +217,12 @@ double* dto_local_Z(dto_handle* h);
 /* ---- instrumentation ---- */
 /* kernels launched by this handle since creation (bench.py's gpu_launches) */
 int64_t dto_launch_count(const dto_handle* h);
-/* name of the bilinear kernel variant chosen for integrator i ("dmma32", "generic", ...) */
+/* name of the bilinear kernel variant chosen for integrator i ("dmma", "generic", ...) */
 const char* dto_kernel_variant(const dto_handle* h, int integrator);
+/* CUDA-event timing of the interval kernels (K1/K7) on the handle's stream: enable, run evaluations,
+ * then read the summed device time and the number of timed launches (resets on enable). */
+int dto_kernel_timing(dto_handle* h, int enable);
+int dto_kernel_time_ms(dto_handle* h, double* ms_sum, int64_t* launches);
 
 #ifdef __cplusplus
 }

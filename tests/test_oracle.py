@@ -152,3 +152,26 @@ def test_quadreg_delta_t_squared_quirk():
     Z = prob.trajectory.datavec.copy()
     u = prob.trajectory.u[0]
     assert np.isclose(orc.eval_objective(spec, Z), 0.5 * np.sum((0.1 * u) ** 2))
+
+
+@pytest.mark.parametrize("name", ["standard", "scaled", "gate"])
+def test_c_port_of_reference_algorithm_agrees_with_analytic_oracle(name):
+    """Two independent restatements -- forward-mode jets through the truncated Taylor expv (the
+    reference's algorithm, oracle/dto_oracle.c) and exact Frechet derivatives from block-triangular
+    scipy expm (oracle/dto_oracle.py) -- must agree to 1e-12."""
+    import dto_oracle_c as oc
+
+    prob = PROBLEMS[name]()
+    spec = prob.to_spec()
+    Z = prob.trajectory.datavec
+    z = spec["z"]
+    it = spec["integrators"][0]
+    mu = np.random.default_rng(1).random(it["G"].shape[1])
+    for k in range(spec["N"] - 1):
+        zk, zk1 = Z[k * z : (k + 1) * z], Z[(k + 1) * z : (k + 2) * z]
+        r, J, H = orc._bilinear_interval(spec, it, zk, zk1, mu)
+        for all_dirs in (True, False):
+            r2, J2, H2 = oc.bilinear_interval(spec, it, zk, zk1, mu, all_dirs=all_dirs)
+            assert np.abs(r - r2).max() <= 1e-12 * max(1, np.abs(r).max())
+            assert np.abs(J - J2).max() <= 1e-12 * np.abs(J).max()
+            assert np.abs(H - H2).max() <= 1e-12 * np.abs(H).max()
