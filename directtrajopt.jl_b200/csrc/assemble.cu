@@ -86,19 +86,15 @@ __global__ void constraint_kernel(DProb P, int ci, const double* __restrict__ Z,
     const double* p = C.params + (long long)C.own_ti[j] * C.np;
     const int nv = C.nv, gd = C.gd;
     if (g != nullptr) {
-        double v[DTO_MAX_KNOTFN_VARS], out[16];
-        for (int i = 0; i < nv; ++i) v[i] = zk[C.var_offs[i]];
-        knot_cfun<double>(C.fn, v, nv, p, out, gd);
+        double out[16];
+        knot_cfun<double>(C.fn, ValueVars{zk, C.var_offs}, nv, p, out, gd);
         double* gp = g + (long long)b * P.n_cons_local + C.row_off + (long long)j * gd;
         for (int a = 0; a < gd; ++a) gp[a] = out[a];
     }
     if (jac != nullptr || dense_probe != nullptr) {
-        HDual v[DTO_MAX_KNOTFN_VARS], out[16];
-        for (int i = 0; i < nv; ++i) v[i] = HDual(zk[C.var_offs[i]]);
+        HDual out[16];
         for (int i = 0; i < nv; ++i) {
-            v[i].d1 = 1.0;
-            knot_cfun<HDual>(C.fn, v, nv, p, out, gd);
-            v[i].d1 = 0.0;
+            knot_cfun<HDual>(C.fn, SeededVars{zk, C.var_offs, i, -1}, nv, p, out, gd);
             for (int a = 0; a < gd; ++a) {
                 const long long e = ((long long)j * gd + a) * nv + i;
                 if (dense_probe != nullptr) {
@@ -221,11 +217,8 @@ __global__ void hessian_assemble_kernel(DProb P, const double* __restrict__ Z, d
             for (int e = tid; e < nv * nv; e += nt) {
                 const int a = e / nv, c = e % nv;
                 if (a > c) continue;
-                HDual v[DTO_MAX_KNOTFN_VARS], out[16];
-                for (int i = 0; i < nv; ++i) v[i] = HDual(zk[C.var_offs[i]]);
-                v[a].d1 = 1.0;
-                v[c].d2 = 1.0;
-                knot_cfun<HDual>(C.fn, v, nv, p, out, gd);
+                HDual out[16];
+                knot_cfun<HDual>(C.fn, SeededVars{zk, C.var_offs, a, c}, nv, p, out, gd);
                 double s = 0.0;
                 for (int q = 0; q < gd; ++q) s = fma(mup[q], out[q].d12, s);
                 sym_add(diag, z, C.var_offs[a], C.var_offs[c], s);
@@ -265,11 +258,7 @@ __global__ void hessian_assemble_kernel(DProb P, const double* __restrict__ Z, d
                     for (int e = tid; e < nv * nv; e += nt) {
                         const int a = e / nv, c = e % nv;
                         if (a > c) continue;
-                        HDual v[DTO_MAX_KNOTFN_VARS];
-                        for (int i = 0; i < nv; ++i) v[i] = HDual(zk[O.var_offs[i]]);
-                        v[a].d1 = 1.0;
-                        v[c].d2 = 1.0;
-                        const HDual r = knot_lfun<HDual>(O.fn, v, nv, p);
+                        const HDual r = knot_lfun<HDual>(O.fn, SeededVars{zk, O.var_offs, a, c}, nv, p);
                         sym_add(diag, z, O.var_offs[a], O.var_offs[c], sw * r.d12);
                     }
                 }
@@ -339,10 +328,7 @@ __global__ void objective_kernel(DProb P, const double* __restrict__ Z, double* 
                 const double* p = O.params + (long long)O.own_ti[j] * O.np;
                 const double w = O.weight * O.Qs[O.own_ti[j]];
                 for (int a = tid; a < nv; a += nt) {
-                    HDual v[DTO_MAX_KNOTFN_VARS];
-                    for (int i = 0; i < nv; ++i) v[i] = HDual(zk[O.var_offs[i]]);
-                    v[a].d1 = 1.0;
-                    const HDual r = knot_lfun<HDual>(O.fn, v, nv, p);
+                    const HDual r = knot_lfun<HDual>(O.fn, SeededVars{zk, O.var_offs, a, -1}, nv, p);
                     gz[O.var_offs[a]] += w * r.d1;
                     if (a == 0) Jk += w * r.v;  // a == 0 is handled by thread 0
                 }

@@ -76,7 +76,7 @@ struct Series {
 __device__ __forceinline__ Series choose_series(double theta) {
     Series s{1, 2};
     if (theta < 1e8) {
-        s.stages = theta > 1.0 ? (int)ceil(theta) : 1;
+        s.stages = theta > 4.0 ? (int)ceil(theta * 0.25) : 1;  // one stage up to ||dt G||_1 = 4 (e^4 round-off amplification)
         const double ths = theta / s.stages;
         double term = ths;
         int T = 1;
@@ -108,15 +108,16 @@ __global__ void __launch_bounds__(128) bilinear_dmma_kernel(DProb P, int ii, con
     int role = blockIdx.y;
     if (role == 1 && !want_jac) role = ROLE_ADJ;
     const bool active = kl < P.nI;
-    const double* Gg = I.G + (long long)b * I.G_stride;  // column-major matrices: Gg[i][k*n + s] = G_i(s,k)
+    const double* Gg = I.G + (long long)b * I.G_stride;    // column-major matrices: Gg[i][k*n + s] = G_i(s,k)
+    const double* Gr = I.Grm + (long long)b * I.G_stride;  // row-major copies:      Gr[i][s*n + k] = G_i(s,k)
 
     double* Gs = sm;                                  // m matrices, row-major G_i(s,k) at [s*ld + k]
     double* Gu = Gs + (size_t)m * n * ld + (size_t)warp * (n * ld + (1 + kMaxDrives) * n);  // per warp
     double* vbuf = Gu + n * ld;                       // per warp: n + kMaxDrives*n doubles of exchange space
 
     for (int e = threadIdx.x; e < m * n * n; e += blockDim.x) {
-        const int i = e / (n * n), r = e % (n * n), k = r / n, s = r % n;
-        Gs[(size_t)i * n * ld + s * ld + k] = Gg[(size_t)(1 + i) * n * n + r];
+        const int i = e / (n * n), r = e % (n * n), s = r / n, k = r % n;
+        Gs[(size_t)i * n * ld + s * ld + k] = Gr[(size_t)(1 + i) * n * n + r];  // coalesced read, conflict-free store
     }
     __syncthreads();
     if (!active) return;
@@ -131,14 +132,17 @@ __global__ void __launch_bounds__(128) bilinear_dmma_kernel(DProb P, int ii, con
     for (int i = 0; i < kMaxDrives; ++i) uu[i] = i < m ? zk[I.u_off + i] : 0.0;
 
     // per-warp generator G(u) (ADJ: its transpose), built from global (coalesced) into smem
-    for (int e = lane; e < n * n; e += 32) {
-        const int k = e / n, s = e % n;
-        double v = Gg[e];
+    {
+        // FWD/EXP want G(u) row-major, ADJ wants its transpose: read whichever global copy makes both the
+        // global read coalesced and the shared store conflict-free
+        const double* Gsrc = role == ROLE_ADJ ? Gg : Gr;
+        for (int e = lane; e < n * n; e += 32) {
+            double v = Gsrc[e];
 #pragma unroll
-        for (int i = 0; i < kMaxDrives; ++i)
-            if (i < m) v = fma(uu[i], Gg[(size_t)(1 + i) * n * n + e], v);
-        if (role == ROLE_ADJ) Gu[k * ld + s] = v;
-        else Gu[s * ld + k] = v;
+            for (int i = 0; i < kMaxDrives; ++i)
+                if (i < m) v = fma(uu[i], Gsrc[(size_t)(1 + i) * n * n + e], v);
+            Gu[(e / n) * ld + (e % n)] = v;
+        }
     }
     __syncwarp();
     // theta = |dt| * ||G(u)||_1 (max column abs sum), identical summation order in every role
@@ -362,7 +366,7 @@ __global__ void __launch_bounds__(128) bilinear_dmma_kernel(DProb P, int ii, con
                         term[mt][nt][0] = F[mt][nt][0];
                         term[mt][nt][1] = F[mt][nt][1];
                     }
-                for (int t = 1; t <= ser.terms; ++t) {
+                for (int t = 1; t <= ser.terms - 2; ++t) {  // value series only: two terms fewer than the derivative rows
                     const double c = dt / ((double)t * (double)ser.stages);
                     double nw[MT][NT][2];
                     frag_zero(nw);

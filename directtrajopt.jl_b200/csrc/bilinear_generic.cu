@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(32) bilinear_generic_kernel(DProb P, int ii, c
     const double theta = fabs(dt) * warp_max(cmax);
     int s_stages = 1, T = 2;
     if (theta < 1e8) {
-        s_stages = theta > 1.0 ? (int)ceil(theta) : 1;
+        s_stages = theta > 4.0 ? (int)ceil(theta * 0.25) : 1;
         double ths = theta / s_stages, term = ths;
         T = 1;
         while (term > 1.3877787807814457e-17 && T < 60) {

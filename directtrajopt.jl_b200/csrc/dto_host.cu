@@ -180,6 +180,14 @@ extern "C" int dto_create(const dto_problem_desc* d, dto_handle** out) {
             const size_t cnt = s.G_batch_stride ? (size_t)s.G_batch_stride * (d->batch - 1) + per : per;
             I.G = dev_upload(h, s.G, cnt);
             I.G_stride = s.G_batch_stride;
+            {
+                std::vector<double> rm(cnt);
+                const size_t nmat = cnt / nn;
+                for (size_t q = 0; q < nmat; ++q)
+                    for (int r = 0; r < s.x_dim; ++r)
+                        for (int c = 0; c < s.x_dim; ++c) rm[q * nn + (size_t)r * s.x_dim + c] = s.G[q * nn + (size_t)c * s.x_dim + r];
+                I.Grm = dev_upload(h, rm.data(), cnt);
+            }
             I.hs_stride = (s.u_dim + 1) * s.x_dim + (s.u_dim + 1) * (s.u_dim + 1);
             I.variant = bilinear_dmma_supported(s.x_dim, s.u_dim) ? DTO_VAR_DMMA : DTO_VAR_GENERIC;
             if (s.x_dim > 96) return fail_create(h, DTO_ERR_UNSUPPORTED, "bilinear integrator: state dimension > 96 not supported");

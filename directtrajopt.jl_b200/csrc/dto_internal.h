@@ -22,7 +22,8 @@ struct DInt {
     int variant;        // kernel variant chosen on the host
     long long row_off;  // local row of this integrator's first residual
     long long G_stride;
-    const double* G;
+    const double* G;    // column-major matrices
+    const double* Grm;  // bilinear: row-major copies of the same matrices
     const double *A, *B, *omega, *phi, *D, *omega_d, *phi_d;
     double* hs;         // [batch][n_intervals][hs_stride]
 };

@@ -34,24 +34,38 @@ __host__ __device__ inline HDual hd_sqrt(const HDual& a) {
 }
 __host__ __device__ inline double hd_sqrt(double a) { return sqrt(a); }
 
+// Variable accessors: the knot's variables are never copied into a per-thread array -- `V(i)` builds the
+// i-th (hyper-dual) variable on the fly from the trajectory, seeded in directions a and c.
+struct ValueVars {
+    const double* zk;
+    const int* offs;
+    __host__ __device__ double operator()(int i) const { return zk[offs[i]]; }
+};
+struct SeededVars {
+    const double* zk;
+    const int* offs;
+    int a, c;  // seed directions of d1 and d2 (-1: none)
+    __host__ __device__ HDual operator()(int i) const { return HDual(zk[offs[i]], i == a ? 1.0 : 0.0, i == c ? 1.0 : 0.0, 0.0); }
+};
+
 // ---- constraint functions g(v; p) -> out[gd] ---------------------------------------------------
-template <class T>
-__host__ __device__ inline void knot_cfun(int fn, const T* v, int nv, const double* p, T* out, int gd) {
+template <class T, class Vars>
+__host__ __device__ inline void knot_cfun(int fn, const Vars& v, int nv, const double* p, T* out, int gd) {
     switch (fn) {
         case DTO_G_NORM_MINUS_C: {  // [norm(v) - c]
             T s = T(0.0);
-            for (int i = 0; i < nv; ++i) s = s + v[i] * v[i];
+            for (int i = 0; i < nv; ++i) s = s + v(i) * v(i);
             out[0] = hd_sqrt(s) - p[0];
         } break;
         case DTO_G_NORMSQ_MINUS_C: {  // [norm(v)^2 - c]
             T s = T(0.0);
-            for (int i = 0; i < nv; ++i) s = s + v[i] * v[i];
+            for (int i = 0; i < nv; ++i) s = s + v(i) * v(i);
             out[0] = s - p[0];
         } break;
         case DTO_G_SQDIST_MINUS_C: {  // [norm(v - p[1:])^2 - p[0]]
             T s = T(0.0);
             for (int i = 0; i < nv; ++i) {
-                T d = v[i] - p[1 + i];
+                T d = v(i) - p[1 + i];
                 s = s + d * d;
             }
             out[0] = s - p[0];
@@ -59,7 +73,7 @@ __host__ __device__ inline void knot_cfun(int fn, const T* v, int nv, const doub
         case DTO_G_LINEAR: {  // A v - b, p = [gd, A (gd x nv column-major), b]
             for (int a = 0; a < gd; ++a) {
                 T s = T(0.0);
-                for (int i = 0; i < nv; ++i) s = s + v[i] * p[1 + a + (long long)i * gd];
+                for (int i = 0; i < nv; ++i) s = s + v(i) * p[1 + a + (long long)i * gd];
                 out[a] = s - p[1 + (long long)gd * nv + a];
             }
         } break;
@@ -69,33 +83,33 @@ __host__ __device__ inline void knot_cfun(int fn, const T* v, int nv, const doub
 }
 
 // ---- objective functions l(v; p) -> scalar ------------------------------------------------------
-template <class T>
-__host__ __device__ inline T knot_lfun(int fn, const T* v, int nv, const double* p) {
+template <class T, class Vars>
+__host__ __device__ inline T knot_lfun(int fn, const Vars& v, int nv, const double* p) {
     switch (fn) {
         case DTO_L_NORMSQ_PLUS_P: {
             T s = T(0.0);
-            for (int i = 0; i < nv; ++i) s = s + v[i] * v[i];
+            for (int i = 0; i < nv; ++i) s = s + v(i) * v(i);
             return s + p[0];
         }
         case DTO_L_SQDIST: {
             T s = T(0.0);
             for (int i = 0; i < nv; ++i) {
-                T d = v[i] - p[i];
+                T d = v(i) - p[i];
                 s = s + d * d;
             }
             return s;
         }
         case DTO_L_LINEAR: {
             T s = T(0.0);
-            for (int i = 0; i < nv; ++i) s = s + v[i] * p[i];
+            for (int i = 0; i < nv; ++i) s = s + v(i) * p[i];
             return s;
         }
         case DTO_L_ISO_INFIDELITY: {  // 1 - |<goal|psi>|^2, v = [re; im], p = [gre; gim]
             int h = nv / 2;
             T a = T(0.0), b = T(0.0);
             for (int i = 0; i < h; ++i) {
-                a = a + v[i] * p[i] + v[h + i] * p[h + i];
-                b = b + v[h + i] * p[i] - v[i] * p[h + i];
+                a = a + v(i) * p[i] + v(h + i) * p[h + i];
+                b = b + v(h + i) * p[i] - v(i) * p[h + i];
             }
             return 1.0 - (a * a + b * b);
         }

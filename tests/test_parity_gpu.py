@@ -18,8 +18,37 @@ def relerr(got, ref):
     return np.abs(got - ref).max() / scale if ref.size else 0.0
 
 
+def catalogue_problem(N=7, seed=3):
+    """Every entry of the device knot-function catalogue, multi-variable constraints, per-time
+    parameters, a structurally-zero derivative (dropped from the stored pattern) and a baseline."""
+    rng = np.random.default_rng(seed)
+    G, traj = pt.bilinear_dynamics_and_trajectory(N=N, seed=seed)
+    integrators = [dto.BilinearIntegrator(G, "x", "u", traj), dto.DerivativeIntegrator("u", "du", traj),
+                   dto.DerivativeIntegrator("du", "ddu", traj)]
+    J = dto.TerminalObjective(dto.IsoInfidelity(traj.goal["x"]), "x", traj, Q=3.0)
+    J = J + 0.5 * dto.KnotPointObjective(dto.NormSqPlus(per_time=[1.0, 2.0]), "u", traj, times=[1, N], Qs=[1.0, 2.0])
+    J = J + dto.KnotPointObjective(dto.LinearCost(rng.standard_normal(6)), ["x", "du"], traj, times=[2, 3])
+    J = J + dto.KnotPointObjective(dto.SqDist(rng.standard_normal(2)), "ddu", traj)
+    J = J + dto.QuadraticRegularizer("du", traj, [0.3, 0.7], baseline=rng.standard_normal((2, N)), times=[1, 3, N])
+    J = J + 2.0 * dto.MinimumTimeObjective(traj, D=0.7)
+    A = rng.standard_normal((2, 6))
+    A[1, 2] = 0.0  # never stored: SparseArrays drops the zero derivative
+    cons = [
+        dto.NonlinearKnotPointConstraint(dto.NormSqMinus(0.5), "x", traj, times=[1, 4], equality=True),
+        dto.NonlinearKnotPointConstraint(dto.SqDistMinus(rng.standard_normal(4), 0.1), ["u", "du"], traj, times=[2, 3, N], equality=False),
+        dto.NonlinearKnotPointConstraint(dto.LinearMap(A, rng.standard_normal(2)), ["x", "u"], traj, equality=True),
+        dto.NonlinearKnotPointConstraint(dto.NormMinus(1.0), "u", traj, times=range(2, N), equality=False),
+    ]
+    return dto.DirectTrajOptProblem(traj, J, integrators, constraints=cons)
+
+
 PROBLEMS = {
     "readme_c1": lambda: pt.readme_problem(N=50),
+    "catalogue": catalogue_problem,
+    "scaled_n8_stages": lambda: pt.scaled_problem(N=6, state_dim=8, n_controls=2, generator_scale=8.0),
+    "scaled_n6_stages": lambda: pt.scaled_problem(N=5, state_dim=6, n_controls=3, generator_scale=9.0),
+    "scaled_n24_m3": lambda: pt.scaled_problem(N=6, state_dim=24, n_controls=3, generator_scale=0.5),
+    "scaled_n48_m1": lambda: pt.scaled_problem(N=4, state_dim=48, n_controls=1, generator_scale=0.3),
     "standard": lambda: pt.standard_problem(N=10),
     "evaluator_test": lambda: pt.evaluator_test_problem(N=10),
     "benchmark_N51": lambda: pt.bilinear_benchmark(N=51),
