@@ -171,7 +171,7 @@ extern "C" int dto_create(const dto_problem_desc* d, dto_handle** out) {
         I.n_carrier = s.n_carrier;
         I.doff = doff;
         I.row_off = loff;
-        I.steps = s.tdb_steps > 0 ? s.tdb_steps : 8;
+        I.steps = s.tdb_steps > 0 ? s.tdb_steps : 1;
         if (s.x_dim < 1 || s.x_off < 0 || s.x_off + s.x_dim > z) return fail_create(h, DTO_ERR_INVALID, "integrator state component outside the knot");
         const size_t nn = (size_t)s.x_dim * s.x_dim;
         if (s.kind == DTO_INT_BILINEAR) {
@@ -211,6 +211,7 @@ extern "C" int dto_create(const dto_problem_desc* d, dto_handle** out) {
             const int np = (s.spline_order == 1 ? 2 * s.u_dim : s.u_dim) + 2;
             I.hs_stride = np * s.x_dim + np * np;
             if (s.spline_order == 1) P.any_cross = 1;
+            if (!tdb_fits(I)) return fail_create(h, DTO_ERR_UNSUPPORTED, "tdbilinear integrator: too many drives/carriers or state too large for shared memory");
             if (s.x_dim > 96) return fail_create(h, DTO_ERR_UNSUPPORTED, "tdbilinear integrator: state dimension > 96 not supported");
         } else {
             return fail_create(h, DTO_ERR_UNSUPPORTED, "unknown integrator kind");

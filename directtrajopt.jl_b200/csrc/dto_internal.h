@@ -102,6 +102,7 @@ bool launch_bilinear_dmma(const DProb& P, int ii, const double* Z, const double*
                           cudaStream_t st, long long* launches);
 bool bilinear_dmma_supported(int n, int m);
 bool tdb_available();
+bool tdb_fits(const DInt& I);
 void launch_tdb(const DProb& P, int ii, const double* Z, const double* mu, double* g, double* jac, EvalFlags f, cudaStream_t st,
                 long long* launches);
 void launch_analytic(const DProb& P, const double* Z, double* g, double* jac, EvalFlags f, cudaStream_t st, long long* launches);

@@ -168,3 +168,46 @@ def test_unsupported_components_raise_at_construction():
         dto.BilinearIntegrator(lambda u: pt.GZ + u[0] ** 2 * pt.GX, "x", "u", traj)
     with pytest.raises(dto.UnsupportedComponent):
         dto.NonlinearKnotPointConstraint(lambda u: [u[0]], "u", traj)
+
+
+# ---- TimeDependentBilinearIntegrator (K7) --------------------------------------------------------------
+TDB_TOL = 1e-9  # fixed-order extrapolation integrator vs the oracle's rtol=1e-13 variational solve (DESIGN.md "TDBI parity")
+
+
+@pytest.mark.parametrize("order,n,m,carriers", [(1, 4, 2, 0), (0, 4, 2, 0), (1, 6, 1, 2), (1, 16, 2, 0)])
+def test_tdbilinear_matches_exact_variational_solution(order, n, m, carriers):
+    rng = np.random.default_rng(9)
+    prob = pt.carrier_problem(N=5, state_dim=n, n_drives=m, spline_order=order, dt=0.2)
+    if carriers:
+        g = prob.integrators[0].G
+
+        def skew():
+            M = rng.standard_normal((n, n))
+            return 0.3 * (M - M.T) / n
+
+        prob.integrators[0].G = dto.CarrierGenerator(g.G0, g.A, g.B, g.omega, g.phi + 0.3, D=np.stack([skew() for _ in range(carriers)]),
+                                                     omega_d=1.0 + rng.random(carriers), phi_d=rng.random(carriers))
+    spec = prob.to_spec()
+    ev = dto.Evaluator(prob)
+    Z0 = prob.trajectory.datavec.copy()
+    Z = Z0 + 0.02 * rng.standard_normal(Z0.size)
+    jst, hst = orc.jacobian_structure(spec, Z0), orc.hessian_structure(spec, Z0)
+    jr, jc = ev.jacobian_structure()
+    hr, hc = ev.hessian_lagrangian_structure()
+    assert np.array_equal(jr, jst[0]) and np.array_equal(jc, jst[1]) and np.array_equal(hr, hst[0]) and np.array_equal(hc, hst[1])
+    mu = rng.random(ev.n_constraints)
+    g = np.empty(ev.n_constraints)
+    ev.eval_constraint(g, Z)
+    assert relerr(g, orc.eval_constraint(spec, Z)) <= TDB_TOL
+    J = np.empty(ev.nnz_jacobian)
+    ev.eval_constraint_jacobian(J, Z)
+    assert relerr(J, orc.eval_constraint_jacobian(spec, Z, jst)) <= TDB_TOL
+    H = np.empty(ev.nnz_hessian)
+    ev.eval_hessian_lagrangian(H, Z, 1.5, mu)
+    Href = orc.eval_hessian_lagrangian(spec, Z, 1.5, mu, hst)
+    assert relerr(H, Href) <= TDB_TOL
+    if order == 1:  # cross-knot Hessian entries are genuinely nonzero for the linear spline
+        z = spec["z"]
+        cross = (hr - 1) // z != (hc - 1) // z
+        assert np.abs(Href[cross]).max() > 1e-6
+    ev.close()
