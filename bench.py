@@ -34,8 +34,12 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: (builder kwargs, description)
-    "c2": dict(N=2000, levels=16, n_drives=4),
+    # BASELINE.json configs[1] (default, the configuration the metric is quoted on): one problem per GPU, weak scaling
+    "c2": dict(kind="gate", N=2000, levels=16, n_drives=4),
+    # configs[3]: ONE long trajectory, knot ranges sharded over the ranks with a one-knot NVLink halo (strong scaling)
+    "c4": dict(kind="scaled", N=100000, state_dim=16, n_controls=2, generator_scale=0.25),
+    # configs[4]: 4096 independent 8-state problems, problem-parallel over the ranks (strong scaling)
+    "c5": dict(kind="scaled", N=200, state_dim=8, n_controls=2, generator_scale=0.35, batch=4096),
 }
 FP64_PEAK_TFLOPS = 37.1  # measured on this pool's B200: DMMA m8n8k4 saturation (profiles/r01_fp64_peaks_and_box_probe.log)
 TAYLOR_T = 20            # canonical term count of SURVEY.md section 8d (C1)
@@ -54,8 +58,12 @@ def canonical_flops_per_interval(n, m, T=TAYLOR_T, s=0):
 def build_problem(workload, seed):
     import dto_b200 as dto
 
-    kw = WORKLOADS[workload]
-    return dto.problem_templates.quantum_gate_problem(seed=seed, **kw)
+    kw = dict(WORKLOADS[workload])
+    kind = kw.pop("kind")
+    kw.pop("batch", None)
+    if kind == "gate":
+        return dto.problem_templates.quantum_gate_problem(seed=seed, **kw)
+    return dto.problem_templates.scaled_problem(seed=seed, **kw)
 
 
 class ClockSampler(threading.Thread):
@@ -118,7 +126,7 @@ def run_reference(args, rank, world):
         "config": {"workload": f"{args.workload}: bilinear quantum gate, state dim {t.dims['x']}, {t.dims['u']} drives, N={t.N}, free dt + MinimumTime"},
         "cpu_baseline": {"value": v, "unit": "evals/s", "cores": info["threads"], "kind": "port", "sample": info["sample"]},
         "e2e": {"value": v, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "reference is Julia (absent here and on the GPU box); this arm times oracle/dto_oracle.c, a C restatement of the reference's ForwardDiff-through-expv algorithm, OpenMP over knot intervals",
+        "note": "reference is Julia (absent here and on the GPU box); this arm times oracle/dto_oracle.c, a C restatement of the reference's ForwardDiff-through-expv algorithm, POSIX threads over knot intervals, all host cores",
     }
     print(json.dumps(line), flush=True)
 
@@ -129,9 +137,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=list(WORKLOADS))
-    ap.add_argument("--cpu-sample", type=int, default=24, help="knot intervals timed for cpu_baseline")
-    ap.add_argument("--ref-sample", type=int, default=32, help="knot intervals per step of --impl reference")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c4", "c5"])
+    ap.add_argument("--cpu-sample", type=int, default=256, help="knot intervals timed for cpu_baseline (about 30 CPU-seconds at c2)")
+    ap.add_argument("--ref-sample", type=int, default=64, help="knot intervals per step of --impl reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -155,30 +163,59 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    prob = build_problem(args.workload, seed=42 + rank)  # an independent problem per rank
+    from dto_b200.sharding import ShardedEvaluator, split_batch
+
+    mode = {"c2": "replicas", "c4": "knot_shards", "c5": "batch_split"}[args.workload]
+    prob = build_problem(args.workload, seed=42 + (rank if mode == "replicas" else 0))
     t = prob.trajectory
     n, m = t.dims["x"], t.dims["u"]
-    ev = dto.Evaluator(prob, device=local_rank)
     rng = np.random.default_rng(1234 + rank)
-    Z = t.datavec.copy()
-    mu = rng.random(ev.n_constraints)
+    sharded = None
+    batch_local = 1
+    if mode == "replicas":  # an independent problem per rank
+        ev = dto.Evaluator(prob, device=local_rank)
+        Z = t.datavec.copy()
+    elif mode == "knot_shards":
+        sharded = ShardedEvaluator(prob, rank, world, device=local_rank, dist=dist if world > 1 else None)
+        ev = sharded.local
+        Z = sharded.local_slice(t.datavec)
+    else:
+        b0, b1 = split_batch(WORKLOADS[args.workload]["batch"], world)[rank]
+        batch_local = b1 - b0
+        ev = dto.Evaluator(prob, device=local_rank, batch=batch_local)
+        Z = np.tile(t.datavec, batch_local) + 0.01 * rng.standard_normal(batch_local * ev.n_vars)
+    mu = rng.random(batch_local * ev.n_constraints)
     sigma = 1.0
+    n_grad = batch_local * (ev.shard_layout.z_end - ev.shard_layout.z_begin)
 
     dev = torch.device("cuda", local_rank)
     stream = torch.cuda.ExternalStream(ev.stream, device=dev)
     dZ = torch.from_numpy(Z).to(dev)
     dmu = torch.from_numpy(mu).to(dev)
-    dJ = torch.empty(1, dtype=torch.float64, device=dev)
-    dgrad = torch.empty(ev.n_vars, dtype=torch.float64, device=dev)
-    dg = torch.empty(ev.n_constraints, dtype=torch.float64, device=dev)
-    djac = torch.empty(ev.nnz_jacobian, dtype=torch.float64, device=dev)
-    dhess = torch.empty(ev.nnz_hessian, dtype=torch.float64, device=dev)
+    dJ = torch.empty(batch_local, dtype=torch.float64, device=dev)
+    dviol = torch.zeros(batch_local, dtype=torch.float64, device=dev)
+    dgrad = torch.empty(n_grad, dtype=torch.float64, device=dev)
+    dg = torch.empty(batch_local * ev.n_constraints, dtype=torch.float64, device=dev)
+    djac = torch.empty(batch_local * ev.nnz_jacobian, dtype=torch.float64, device=dev)
+    dhess = torch.empty(batch_local * ev.nnz_hessian, dtype=torch.float64, device=dev)
     flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)  # > 126 MB L2
+    zptr = dZ.data_ptr()
+    if sharded is not None:
+        # the shard's iterate lives in the evaluator's own buffer: that is what the left neighbour's kernels
+        # read the halo knot from (CUDA-IPC mapped peer pointer over NVLink)
+        zptr = ev.local_Z_ptr
+        ev.eval_objective(Z)  # uploads Z into the resident buffer
     torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
 
     def step_dev():
-        ev.eval_all_dev(dZ.data_ptr(), sigma, dmu.data_ptr(), dJ.data_ptr(), dgrad.data_ptr(), dg.data_ptr(), djac.data_ptr(),
-                        dhess.data_ptr())
+        ev.eval_all_dev(zptr, sigma, dmu.data_ptr(), dJ.data_ptr(), dgrad.data_ptr(), dg.data_ptr(), djac.data_ptr(), dhess.data_ptr())
+        if sharded is not None and world > 1:
+            # the only collective of the sharded path: objective (sum) and violation (max), two scalars
+            ev.violation_dev(dg.data_ptr(), dviol.data_ptr())
+            dist.all_reduce(dJ, op=dist.ReduceOp.SUM)
+            dist.all_reduce(dviol, op=dist.ReduceOp.MAX)
 
     def barrier():
         if world > 1:
@@ -215,11 +252,11 @@ def main():
     # ---- end-to-end through the host-pointer C ABI (pinned host buffers) -------------------------
     hZ = torch.from_numpy(Z).pin_memory()
     hmu = torch.from_numpy(mu).pin_memory()
-    hJ = torch.empty(1, dtype=torch.float64).pin_memory()
-    hgrad = torch.empty(ev.n_vars, dtype=torch.float64).pin_memory()
-    hg = torch.empty(ev.n_constraints, dtype=torch.float64).pin_memory()
-    hjac = torch.empty(ev.nnz_jacobian, dtype=torch.float64).pin_memory()
-    hhess = torch.empty(ev.nnz_hessian, dtype=torch.float64).pin_memory()
+    hJ = torch.empty(batch_local, dtype=torch.float64).pin_memory()
+    hgrad = torch.empty(n_grad, dtype=torch.float64).pin_memory()
+    hg = torch.empty(batch_local * ev.n_constraints, dtype=torch.float64).pin_memory()
+    hjac = torch.empty(batch_local * ev.nnz_jacobian, dtype=torch.float64).pin_memory()
+    hhess = torch.empty(batch_local * ev.nnz_hessian, dtype=torch.float64).pin_memory()
     nz, nmu = hZ.numpy(), hmu.numpy()
     outs = [a.numpy() for a in (hJ, hgrad, hg, hjac, hhess)]
     for _ in range(args.warmup):
@@ -233,7 +270,7 @@ def main():
     sampler.stop_flag.set()
     sampler.join()
     h2d = 8 * (Z.size + mu.size)
-    d2h = 8 * (1 + ev.n_vars + ev.n_constraints + ev.nnz_jacobian + ev.nnz_hessian)
+    d2h = 8 * (hJ.numel() + hgrad.numel() + hg.numel() + hjac.numel() + hhess.numel())
 
     # parity guard on the timed outputs: the device-resident and host paths must agree bit for bit
     same = bool(np.array_equal(outs[3], djac.cpu().numpy()) and np.array_equal(outs[4], dhess.cpu().numpy()))
@@ -245,19 +282,28 @@ def main():
     dev_ms_max, e2e_s_max, k1_avg_ms = agg.tolist()
 
     if rank == 0:
-        evals = world * args.steps
+        # units: problem evaluations.  replicas: one problem per rank per step (weak); knot_shards: the ranks
+        # share ONE problem (strong); batch_split: the ranks share the batch (strong)
+        per_step = {"replicas": world, "knot_shards": 1, "batch_split": WORKLOADS[args.workload].get("batch", 1)}[mode]
+        evals = per_step * args.steps
         value = evals / (dev_ms_max * 1e-3)
         e2e_value = evals / e2e_s_max
-        flops_launch = canonical_flops_per_interval(n, m) * (t.N - 1)
+        # algorithmic flops of ONE launch of the dominant kernel on this rank
+        intervals_per_launch = {"replicas": t.N - 1, "knot_shards": int(ev.n_dynamics_constraints // max(1, sum(i.x_dim for i in prob.integrators))),
+                                "batch_split": batch_local * (t.N - 1)}[mode]
+        flops_launch = canonical_flops_per_interval(n, m) * intervals_per_launch
         achieved = flops_launch / (k1_avg_ms * 1e-3) * 1e-12
         line = {
             "metric": "full NLP evals/sec (constraint+Jacobian+Hessian)", "value": value, "unit": "evals/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": "weak" if mode == "replicas" else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {
-                "workload": f"{args.workload}: bilinear quantum gate, state dim {n}, {m} drives, N={t.N}, free dt + MinimumTime "
-                            f"(z={t.dim}, {ev.n_vars} vars, {ev.n_constraints} rows, {ev.nnz_jacobian} Jac nnz, {ev.nnz_hessian} Hess nnz)",
-                "per_rank": "one independent problem per GPU (problem-parallel, no collective)",
+                "workload": f"{args.workload}: " + ("bilinear quantum gate" if mode == "replicas" else "random dense bilinear (make_scaled_problem)") +
+                            f", state dim {n}, {m} drives, N={t.N}" + (f", batch {WORKLOADS[args.workload]['batch']}" if mode == "batch_split" else "") +
+                            f" (z={t.dim}; rank 0: {ev.n_vars} vars, {ev.n_constraints} rows, {ev.nnz_jacobian} Jac nnz, {ev.nnz_hessian} Hess nnz per problem)",
+                "per_rank": {"replicas": "one independent problem per GPU (problem-parallel, no collective)",
+                             "knot_shards": "contiguous knot range of ONE trajectory per GPU; one-knot halo read through a CUDA-IPC peer pointer (NVLink) inside the kernels; NCCL all-reduce of 2 scalars (objective, violation) per step",
+                             "batch_split": "contiguous block of the problem batch per GPU (no collective)"}[mode],
                 "l2": "256 MB memset between timed steps (outside the per-step CUDA events)",
                 "step": "objective+gradient+constraint+Jacobian+Hessian of one iterate, outputs left in HBM",
                 "kernel_variant": ev.kernel_variant(0),
@@ -269,7 +315,7 @@ def main():
             "roofline": {
                 "bound": "tensor", "achieved": achieved, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": achieved / FP64_PEAK_TFLOPS,
                 "traffic": None, "kernel": "bilinear interval kernel (K1)", "kernel_ms": k1_avg_ms,
-                "kernel_share_of_step": k1_avg_ms / (dev_ms_max / args.steps),
+                "kernel_share_of_step": k1_avg_ms * max(1, sum(1 for i in prob.integrators if type(i).__name__ != "DerivativeIntegrator")) / (dev_ms_max / args.steps),
                 "algorithmic_flops_per_launch": flops_launch,
                 "peak_source": "FP64 DMMA m8n8k4 saturation measured on this pool (profiles/r01_fp64_peaks_and_box_probe.log); "
                                "MEASURED_PEAKS.json carries no FP64 figure; cuBLAS DGEMM 8192^3 measured 35.5 TFLOP/s",

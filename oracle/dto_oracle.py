@@ -678,3 +678,55 @@ def eval_hessian_lagrangian(spec, Z, sigma, mu, structure):
     rows, cols, vals = np.concatenate(rows), np.concatenate(cols), np.concatenate(vals)
     keep = rows <= cols  # 'if row <= col' (evaluator.jl:589, :614, :637)
     return _lookup(rows[keep], cols[keep], vals[keep], srows, scols, (N * z, N * z), True)
+
+
+# --------------------------------------------------------------------------------------------
+# per-knot / per-row ownership views (used by the multi-process tests of the knot-range sharding)
+# --------------------------------------------------------------------------------------------
+
+
+def objective_by_knot(spec, Z):
+    """Objective split by the knot each term belongs to (sum == eval_objective)."""
+    N, z = spec["N"], spec["z"]
+    out = np.zeros(N)
+    for ob in spec["objectives"]:
+        w = ob.get("weight", 1.0)
+        if ob["kind"] in ("quadreg", "knot"):
+            for i, k in enumerate(ob["times"]):
+                one = dict(ob)
+                one["times"] = [k]
+                if ob["kind"] == "knot":
+                    one["params"] = [ob["params"][i]]
+                    one["Qs"] = [ob["Qs"][i]]
+                out[k - 1] += w * _objective_term(spec, one, Z, False, False)[0]
+        elif ob["kind"] == "mintime":
+            dto = dt_offset(spec)
+            out[: N - 1] += w * ob["D"] * Z[np.arange(N - 1) * z + dto]
+    return out
+
+
+def row_owner_knot(spec):
+    """1-based knot that owns each constraint row (interval k -> knot k; knot constraint -> its time)."""
+    N = spec["N"]
+    owners = []
+    for it in spec["integrators"]:
+        d = integrator_dim(spec, it)
+        owners.append(np.repeat(np.arange(1, N), d))
+    for c in spec.get("constraints", []):
+        gd = constraint_dim(spec, c) // len(c["times"])
+        owners.append(np.repeat(np.asarray(c["times"]), gd))
+    return np.concatenate(owners) if owners else np.zeros(0, int)
+
+
+def violation(spec, g):
+    """max(|g_eq|, max(0, g_ineq)) with the row bounds of solve.jl:30-65."""
+    nd, _ = n_constraints(spec)
+    eq = np.ones(g.size, bool)
+    off = nd
+    for c in spec.get("constraints", []):
+        cd = constraint_dim(spec, c)
+        if not c.get("equality", True):
+            eq[off : off + cd] = False
+        off += cd
+    v = np.where(eq, np.abs(g), np.maximum(g, 0.0))
+    return v, eq

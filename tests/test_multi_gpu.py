@@ -1,0 +1,93 @@
+"""Two-process NCCL run of the knot-range sharding on two GPUs of one box: the halo knot is read from the
+right neighbour's HBM through a CUDA-IPC mapped pointer, the scalars are all-reduced over NCCL, and the
+reassembled outputs equal the single-GPU evaluation bit for bit.  Skipped on boxes with fewer than 2 GPUs
+(the same logic runs single-GPU in test_batch_shard_gpu.py and on CPU in test_sharding_gloo.py)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+
+    import dto_b200 as dto
+    from dto_b200 import problem_templates as pt
+    from dto_b200.sharding import ShardedEvaluator
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    prob = pt.scaled_problem(N=41, state_dim=16, n_controls=2, generator_scale=0.3)
+    rng = np.random.default_rng(0)
+    Z = prob.trajectory.datavec + 0.01 * rng.standard_normal(prob.trajectory.datavec.size)
+    sh = ShardedEvaluator(prob, rank, world, device=rank, dist=dist)
+    ev = sh.local
+    rows, jpos, hpos = ev.shard_maps()
+    mu_all = np.random.default_rng(1).random(int(rows.max()) + 1 if rank == world - 1 else 10**6)[: 10**6]
+    mu_all = np.random.default_rng(1).random(2 * 40 * 16 + 40 * 2 + 10)
+    Zloc = sh.local_slice(Z)
+    if sh.peer_halo and sh.z_halo_end > sh.z_end:
+        Zloc = Zloc.copy()
+        Zloc[sh.z_end - sh.z_begin:] = np.nan  # must come from the peer, not from the local halo slot
+    ev.eval_objective(Zloc)  # make the shard's Z resident
+    dist.barrier()
+    J = np.empty(1)
+    grad = np.empty(sh.z_end - sh.z_begin)
+    g, jac, hess = np.empty(ev.n_constraints), np.empty(ev.nnz_jacobian), np.empty(ev.nnz_hessian)
+    ev.eval_all(Zloc, 1.2, mu_all[rows], J, grad, g, jac, hess)
+    lo, _ = ev.constraint_bounds()
+    viol = float(np.where(lo == 0, np.abs(g), np.maximum(g, 0)).max())
+    Jt, vt = sh.reduce_scalars(float(J[0]), viol, device=torch.device("cuda", rank))
+    q.put((rank, rows, jpos, hpos, sh.z_begin, sh.z_end, grad, g, jac, hess, Jt, vt))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_gpu_knot_shards_with_ipc_halo():
+    import torch.multiprocessing as mp
+
+    import dto_b200 as dto
+    from dto_b200 import problem_templates as pt
+
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    prob = pt.scaled_problem(N=41, state_dim=16, n_controls=2, generator_scale=0.3)
+    rng = np.random.default_rng(0)
+    Z = prob.trajectory.datavec + 0.01 * rng.standard_normal(prob.trajectory.datavec.size)
+    whole = dto.Evaluator(prob, device=0)
+    mu_all = np.random.default_rng(1).random(2 * 40 * 16 + 40 * 2 + 10)
+    mu = mu_all[: whole.n_constraints]
+    J = np.empty(1)
+    grad, g = np.empty(whole.n_vars), np.empty(whole.n_constraints)
+    jac, hess = np.empty(whole.nnz_jacobian), np.empty(whole.nnz_hessian)
+    whole.eval_all(Z, 1.2, mu, J, grad, g, jac, hess)
+    grad2, g2, jac2, hess2 = [np.full_like(a, np.nan) for a in (grad, g, jac, hess)]
+    for rank, rows, jpos, hpos, zb, ze, gr, gg, jj, hh, Jt, vt in res:
+        grad2[zb:ze], g2[rows], jac2[jpos], hess2[hpos] = gr, gg, jj, hh
+        assert abs(Jt - J[0]) <= 1e-12 * max(1, abs(J[0]))
+        lo, _ = whole.constraint_bounds()
+        assert vt == np.where(lo == 0, np.abs(g), np.maximum(g, 0)).max()
+    assert np.array_equal(grad2, grad) and np.array_equal(g2, g) and np.array_equal(jac2, jac) and np.array_equal(hess2, hess)
