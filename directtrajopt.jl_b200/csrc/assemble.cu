@@ -35,8 +35,12 @@ __device__ double block_sum(double v, double* red) {
 // ------------------------------------------------------------------------------------------------
 // K2: DerivativeIntegrator  f = x+ - x - dt*xdot : residual and full d x 2z block (zeros included)
 // ------------------------------------------------------------------------------------------------
-__global__ void analytic_kernel(DProb P, const double* __restrict__ Z, double* __restrict__ g, double* __restrict__ jac) {
-    const int b = blockIdx.x / P.nI, kl = blockIdx.x % P.nI, z = P.z;
+__global__ void analytic_kernel(DProb P, const double* __restrict__ Z, double* __restrict__ g, double* __restrict__ jac,
+                                long long total) {
+    // one warp per (problem, interval)
+    const long long item = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (item >= total) return;
+    const int b = (int)(item / P.nI), kl = (int)(item % P.nI), z = P.z, lane = threadIdx.x & 31;
     const double* zk = Z + (long long)b * P.n_vars_local + (long long)kl * z;
     const double* zk1 = zk + z;
     if (P.halo != nullptr && kl + 1 == P.nK - 1) zk1 = P.halo;
@@ -47,13 +51,13 @@ __global__ void analytic_kernel(DProb P, const double* __restrict__ Z, double* _
         const int d = I.n;
         if (g != nullptr) {
             double* gp = g + (long long)b * P.n_cons_local + I.row_off + (long long)kl * d;
-            for (int a = threadIdx.x; a < d; a += blockDim.x) gp[a] = zk1[I.x_off + a] - zk[I.x_off + a] - dt * zk[I.u_off + a];
+            for (int a = lane; a < d; a += 32) gp[a] = zk1[I.x_off + a] - zk[I.x_off + a] - dt * zk[I.u_off + a];
         }
         if (jac != nullptr) {
             double* jp = jac + (long long)b * P.nnz_jac_local;
             const long long own_off = jac_own_off(P, kl, I.doff, d);
             const long long prev_off = jac_prev_off(P, kl + 1, I.doff);
-            for (int e = threadIdx.x; e < 2 * z * d; e += blockDim.x) {
+            for (int e = lane; e < 2 * z * d; e += 32) {
                 const int l = e / d, a = e % d;
                 double v = 0.0;
                 long long pos;
@@ -133,21 +137,23 @@ __device__ __forceinline__ int int_nparam(const DInt& I) {
     return I.kind == DTO_INT_BILINEAR ? I.m + 1 : (I.order == 1 ? 2 * I.m : I.m) + 2;
 }
 
+// One WARP per (problem, owned knot); several knots per CTA, each with its own z x z tile(s) in shared memory.
 __global__ void hessian_assemble_kernel(DProb P, const double* __restrict__ Z, double sigma, const double* __restrict__ mu,
-                                        double* __restrict__ hess) {
+                                        double* __restrict__ hess, int warps_per_cta, long long total) {
     extern __shared__ double sm[];
-    const int z = P.z, tid = threadIdx.x, nt = blockDim.x;
-    const int b = blockIdx.x / P.nOwn, kl = blockIdx.x % P.nOwn;
-    double* diag = sm;                               // z*z, entries (i<=l) used
-    double* cross = sm + z * z;                      // z*z if any_cross: cross[i*z + l] = H[knot kl-1 comp i][knot kl comp l]
-    double* red = sm + (P.any_cross ? 2 : 1) * z * z;  // 32
+    const int z = P.z, tid = threadIdx.x & 31, nt = 32;
+    const int warp = threadIdx.x >> 5;
+    const long long item = (long long)blockIdx.x * warps_per_cta + warp;
+    if (item >= total) return;
+    const int b = (int)(item / P.nOwn), kl = (int)(item % P.nOwn);
+    const int tiles = P.any_cross ? 2 : 1;
+    double* diag = sm + (size_t)warp * tiles * z * z;  // z*z, entries (i<=l) used
+    double* cross = diag + z * z;                      // z*z if any_cross: cross[i*z + l] = H[knot kl-1 comp i][knot kl comp l]
     const double* zk = Z + (long long)b * P.n_vars_local + (long long)kl * z;
     const double* mub = mu + (long long)b * P.n_cons_local;
     const bool has_cross = hess_knot_has_cross(P, kl);
-    for (int e = tid; e < z * z; e += nt) diag[e] = 0.0;
-    if (P.any_cross)
-        for (int e = tid; e < z * z; e += nt) cross[e] = 0.0;
-    __syncthreads();
+    for (int e = tid; e < tiles * z * z; e += nt) diag[e] = 0.0;
+    __syncwarp();
 
     for (int ii = 0; ii < P.n_int; ++ii) {
         const DInt& I = P.in[ii];
@@ -156,7 +162,7 @@ __global__ void hessian_assemble_kernel(DProb P, const double* __restrict__ Z, d
                 const double* mup = mub + I.row_off + (long long)kl * I.n;
                 for (int a = tid; a < I.n; a += nt) sym_add(diag, z, I.u_off + a, P.dt_off, -mup[a]);
             }
-            __syncthreads();
+            __syncwarp();
             continue;
         }
         const int np = int_nparam(I), n = I.n;
@@ -169,7 +175,7 @@ __global__ void hessian_assemble_kernel(DProb P, const double* __restrict__ Z, d
                 int_param(I, P.dt_off, p, nx, comp);
                 if (!nx) sym_add(diag, z, I.x_off + a, comp, hs[e]);
             }
-            __syncthreads();
+            __syncwarp();
             for (int e = tid; e < np * np; e += nt) {
                 const int p = e / np, q = e % np;
                 if (p > q) continue;
@@ -178,7 +184,7 @@ __global__ void hessian_assemble_kernel(DProb P, const double* __restrict__ Z, d
                 int_param(I, P.dt_off, q, nxq, cq);
                 if (!nxp && !nxq) sym_add(diag, z, cp, cq, hpp[e]);
             }
-            __syncthreads();
+            __syncwarp();
         }
         if (I.kind == DTO_INT_TDBILINEAR && I.order == 1 && kl >= 1) {
             // previous interval: (next,next) -> this knot's diagonal block; (own,next) -> cross block
@@ -190,7 +196,7 @@ __global__ void hessian_assemble_kernel(DProb P, const double* __restrict__ Z, d
                 int_param(I, P.dt_off, p, nx, comp);
                 if (nx) cross[(I.x_off + a) * z + comp] += hs[e];
             }
-            __syncthreads();
+            __syncwarp();
             for (int e = tid; e < np * np; e += nt) {
                 const int p = e / np, q = e % np;
                 int nxp, cp, nxq, cq;
@@ -202,7 +208,7 @@ __global__ void hessian_assemble_kernel(DProb P, const double* __restrict__ Z, d
                     cross[cp * z + cq] += hpp[e];
                 }
             }
-            __syncthreads();
+            __syncwarp();
         }
     }
 
@@ -224,7 +230,7 @@ __global__ void hessian_assemble_kernel(DProb P, const double* __restrict__ Z, d
                 sym_add(diag, z, C.var_offs[a], C.var_offs[c], s);
             }
         }
-        __syncthreads();
+        __syncwarp();
     }
 
     // objective: sigma * sum_i w_i Hess J_i   (skipped entirely when sigma == 0, evaluator.jl:626)
@@ -245,58 +251,93 @@ __global__ void hessian_assemble_kernel(DProb P, const double* __restrict__ Z, d
                         if (va <= P.dt_off && va != P.dt_off) diag[va * z + P.dt_off] += sw * 2.0 * dt * O.R[a] * dv;
                         part += O.R[a] * dv * dv;
                     }
-                    const double q = block_sum(part, red);
+                    const double q = warp_sum(part);
+                    __syncwarp();
                     if (tid == 0) diag[P.dt_off * z + P.dt_off] += sw * q;
                 }
-                __syncthreads();
-            } else if (O.kind == DTO_OBJ_KNOT) {
-                const int j = O.knot_to_own[kl];
-                if (j >= 0) {
-                    const int nv = O.nv;
-                    const double* p = O.params + (long long)O.own_ti[j] * O.np;
-                    const double sw = sigma * O.weight * O.Qs[O.own_ti[j]];
-                    for (int e = tid; e < nv * nv; e += nt) {
-                        const int a = e / nv, c = e % nv;
-                        if (a > c) continue;
-                        const HDual r = knot_lfun<HDual>(O.fn, SeededVars{zk, O.var_offs, a, c}, nv, p);
-                        sym_add(diag, z, O.var_offs[a], O.var_offs[c], sw * r.d12);
-                    }
-                }
-                __syncthreads();
+                __syncwarp();
             }
+            // knot objectives are added by knot_objective_hessian_kernel (one thread per hyper-dual pair)
         }
     }
 
-    // stream the knot's region out in COO order: per column l: [z cross rows][l+1 diagonal rows]
+    // stream the knot's region out in COO order: per column l: [z cross rows][l+1 diagonal rows]; the region is
+    // contiguous, so the warp walks it linearly (coalesced) and decodes (column, row) incrementally
     double* hp = hess + (long long)b * P.nnz_hess_local + hess_knot_base(P, kl);
-    const int warp = tid >> 5, lane = tid & 31, nwarp = nt >> 5;
-    for (int l = warp; l < z; l += nwarp) {
-        const long long cs = has_cross ? (long long)l * z + (long long)l * (l + 1) / 2 : (long long)l * (l + 1) / 2;
-        const int ncross = has_cross ? z : 0;
-        for (int i = lane; i < ncross + l + 1; i += 32) {
+    const int ncross = has_cross ? z : 0;
+    const int region = ncross * z + z * (z + 1) / 2;
+    {
+        // lane-private (column l, row-in-column i) cursor advanced by 32 entries per iteration
+        int l = 0, i = tid;
+        while (l < z && i >= ncross + l + 1) {
+            i -= ncross + l + 1;
+            ++l;
+        }
+        for (int e = tid; e < region; e += 32) {
             double v;
             if (i < ncross) v = P.any_cross ? cross[i * z + l] : 0.0;
             else v = diag[(i - ncross) * z + l];
-            hp[cs + i] = v;
+            hp[e] = v;
+            i += 32;
+            while (l < z && i >= ncross + l + 1) {
+                i -= ncross + l + 1;
+                ++l;
+            }
         }
     }
 }
 
+// Knot-objective Hessians: sigma * w * Q * Hess l, one thread per (problem, listed knot, variable pair), added to the
+// already assembled COO values (a terminal cost on a 32- or 64-dimensional state is one knot with ~500-2000 pairs,
+// which would serialise inside the per-knot warp of the assembler).
+__global__ void knot_objective_hessian_kernel(DProb P, int oi, const double* __restrict__ Z, double sigma, double* __restrict__ hess,
+                                              long long total) {
+    const DObj& O = P.ob[oi];
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const int nv = O.nv, npairs = nv * (nv + 1) / 2, z = P.z;
+    const int pair = (int)(t % npairs);
+    const long long r = t / npairs;
+    const int j = (int)(r % O.nt_own), b = (int)(r / O.nt_own);
+    int a = 0, p = pair;
+    while (p >= nv - a) {
+        p -= nv - a;
+        ++a;
+    }
+    const int c = a + p;
+    const int kl = O.own_knot[j];
+    const double* zk = Z + (long long)b * P.n_vars_local + (long long)kl * z;
+    const double* prm = O.params + (long long)O.own_ti[j] * O.np;
+    const HDual res = knot_lfun<HDual>(O.fn, SeededVars{zk, O.var_offs, a, c}, nv, prm);
+    const double v = sigma * O.weight * O.Qs[O.own_ti[j]] * res.d12;
+    int i = O.var_offs[a], l = O.var_offs[c];
+    if (i > l) {
+        const int q = i;
+        i = l;
+        l = q;
+    }
+    const int ncross = hess_knot_has_cross(P, kl) ? z : 0;
+    const long long pos = hess_knot_base(P, kl) + (long long)l * ncross + (long long)l * (l + 1) / 2 + ncross + i;
+    atomicAdd(hess + (long long)b * P.nnz_hess_local + pos, v);
+}
+
 // ------------------------------------------------------------------------------------------------
-// K6: objective value + gradient, one CTA per (problem, owned knot); partial sums reduced in a
+// K6: objective value + gradient, one WARP per (problem, owned knot); partial sums reduced in a
 // second, deterministic pass.
 // ------------------------------------------------------------------------------------------------
-__global__ void objective_kernel(DProb P, const double* __restrict__ Z, double* __restrict__ grad, double* __restrict__ partials) {
+__global__ void objective_kernel(DProb P, const double* __restrict__ Z, double* __restrict__ grad, double* __restrict__ partials,
+                                 int warps_per_cta, long long total) {
     extern __shared__ double sm[];
-    const int z = P.z, tid = threadIdx.x, nt = blockDim.x;
-    const int b = blockIdx.x / P.nOwn, kl = blockIdx.x % P.nOwn;
-    double* gz = sm;        // z
-    double* red = sm + z;   // 32
+    const int z = P.z, tid = threadIdx.x & 31, nt = 32, warp = threadIdx.x >> 5;
+    const long long item = (long long)blockIdx.x * warps_per_cta + warp;
+    if (item >= total) return;
+    const int b = (int)(item / P.nOwn), kl = (int)(item % P.nOwn);
+    double* gz = sm + (size_t)warp * z;
     const double* zk = Z + (long long)b * P.n_vars_local + (long long)kl * z;
     const long long kg = (long long)P.kb - 1 + kl;  // global 0-based knot
     for (int e = tid; e < z; e += nt) gz[e] = 0.0;
-    __syncthreads();
-    double Jk = 0.0;  // meaningful in thread 0 only
+    __syncwarp();
+    double Jk = 0.0;  // meaningful in lane 0 only
     for (int oi = 0; oi < P.n_obj; ++oi) {
         const DObj& O = P.ob[oi];
         if (O.kind == DTO_OBJ_QUADREG) {
@@ -308,19 +349,20 @@ __global__ void objective_kernel(DProb P, const double* __restrict__ Z, double* 
                     gz[O.var_offs[a]] += O.weight * dt * dt * O.R[a] * dv;
                     part += O.R[a] * dv * dv;
                 }
-                const double q = block_sum(part, red);
+                const double q = warp_sum(part);
+                __syncwarp();
                 if (tid == 0) {
                     Jk += O.weight * 0.5 * dt * dt * q;
                     gz[P.dt_off] += O.weight * q * dt;
                 }
             }
-            __syncthreads();
+            __syncwarp();
         } else if (O.kind == DTO_OBJ_MINTIME) {
             if (tid == 0 && kg < P.N - 1) {
                 Jk += O.weight * O.D * zk[P.dt_off];
                 gz[P.dt_off] += O.weight * O.D;
             }
-            __syncthreads();
+            __syncwarp();
         } else if (O.kind == DTO_OBJ_KNOT) {
             const int j = O.knot_to_own[kl];
             if (j >= 0) {
@@ -330,15 +372,26 @@ __global__ void objective_kernel(DProb P, const double* __restrict__ Z, double* 
                 for (int a = tid; a < nv; a += nt) {
                     const HDual r = knot_lfun<HDual>(O.fn, SeededVars{zk, O.var_offs, a, -1}, nv, p);
                     gz[O.var_offs[a]] += w * r.d1;
-                    if (a == 0) Jk += w * r.v;  // a == 0 is handled by thread 0
+                    if (a == 0) Jk += w * r.v;  // a == 0 is handled by lane 0
                 }
             }
-            __syncthreads();
+            __syncwarp();
         }
     }
     if (grad != nullptr)
         for (int e = tid; e < z; e += nt) grad[((long long)b * P.nOwn + kl) * z + e] = gz[e];
     if (tid == 0 && partials != nullptr) partials[(long long)b * P.nOwn + kl] = Jk;
+}
+
+// deterministic two-level sum: fixed chunking, fixed tree
+__global__ void objective_chunk_kernel(int nOwn, int chunk, const double* __restrict__ partials, double* __restrict__ chunks) {
+    const int b = blockIdx.y, c = blockIdx.x;
+    const int k0 = c * chunk, k1 = min(nOwn, k0 + chunk);
+    double s = 0.0;
+    for (int k = k0 + threadIdx.x; k < k1; k += blockDim.x) s += partials[(long long)b * nOwn + k];
+    __shared__ double red[32];
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) chunks[(long long)b * gridDim.x + c] = s;
 }
 
 __global__ void objective_reduce_kernel(int nOwn, const double* __restrict__ partials, double* __restrict__ J) {
@@ -382,7 +435,8 @@ void launch_analytic(const DProb& P, const double* Z, double* g, double* jac, Ev
     bool any_deriv = false;
     for (int i = 0; i < P.n_int; ++i) any_deriv |= P.in[i].kind == DTO_INT_DERIVATIVE;
     if (any_deriv && P.nI > 0) {
-        analytic_kernel<<<P.nI * P.batch, 128, 0, st>>>(P, Z, f.want_g ? g : nullptr, f.want_jac ? jac : nullptr);
+        const long long total = (long long)P.nI * P.batch;
+        analytic_kernel<<<(unsigned)((total + 7) / 8), 256, 0, st>>>(P, Z, f.want_g ? g : nullptr, f.want_jac ? jac : nullptr, total);
         ++*launches;
     }
     for (int ci = 0; ci < P.n_con; ++ci) {
@@ -410,25 +464,49 @@ void launch_constraint_pattern_probe(const DProb& P, const double* Z, double* de
 void launch_hessian_assemble(const DProb& P, const double* Z, double sigma, const double* mu, double* hess, cudaStream_t st,
                              long long* launches) {
     if (P.nOwn <= 0) return;
-    const size_t smem = sizeof(double) * ((size_t)P.z * P.z * (P.any_cross ? 2 : 1) + 32);
+    const size_t per_warp = sizeof(double) * (size_t)P.z * P.z * (P.any_cross ? 2 : 1);
+    int W = 8;
+    while (W > 1 && W * per_warp > 64 * 1024) W >>= 1;
+    const size_t smem = W * per_warp;
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
         cudaFuncSetAttribute(hessian_assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         configured = 227 * 1024;
     }
-    hessian_assemble_kernel<<<P.nOwn * P.batch, 128, smem, st>>>(P, Z, sigma, mu, hess);
+    const long long total = (long long)P.nOwn * P.batch;
+    hessian_assemble_kernel<<<(unsigned)((total + W - 1) / W), W * 32, smem, st>>>(P, Z, sigma, mu, hess, W, total);
     ++*launches;
+    if (sigma != 0.0)
+        for (int oi = 0; oi < P.n_obj; ++oi) {
+            const DObj& O = P.ob[oi];
+            if (O.kind != DTO_OBJ_KNOT || O.nt_own == 0) continue;
+            const long long tot = (long long)P.batch * O.nt_own * (O.nv * (O.nv + 1) / 2);
+            knot_objective_hessian_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(P, oi, Z, sigma, hess, tot);
+            ++*launches;
+        }
 }
 
 void launch_objective(const DProb& P, const double* Z, double* J, double* grad, double* partials, cudaStream_t st,
                       long long* launches) {
     if (P.nOwn <= 0) return;
-    const size_t smem = sizeof(double) * (P.z + 32);
-    objective_kernel<<<P.nOwn * P.batch, 64, smem, st>>>(P, Z, grad, J ? partials : nullptr);
+    const int W = 8;
+    const size_t smem = sizeof(double) * (size_t)P.z * W;
+    const long long total = (long long)P.nOwn * P.batch;
+    objective_kernel<<<(unsigned)((total + W - 1) / W), W * 32, smem, st>>>(P, Z, grad, J ? partials : nullptr, W, total);
     ++*launches;
     if (J) {
-        objective_reduce_kernel<<<P.batch, 256, 0, st>>>(P.nOwn, partials, J);
-        ++*launches;
+        // partials layout: [batch][nOwn] followed by [batch][nchunks] of scratch
+        const int chunk = 2048;
+        const int nchunks = (P.nOwn + chunk - 1) / chunk;
+        if (nchunks > 1) {
+            double* chunks = partials + (long long)P.batch * P.nOwn;
+            objective_chunk_kernel<<<dim3(nchunks, P.batch), 256, 0, st>>>(P.nOwn, chunk, partials, chunks);
+            objective_reduce_kernel<<<P.batch, 256, 0, st>>>(nchunks, chunks, J);
+            *launches += 2;
+        } else {
+            objective_reduce_kernel<<<P.batch, 256, 0, st>>>(P.nOwn, partials, J);
+            ++*launches;
+        }
     }
 }
 

@@ -253,7 +253,7 @@ extern "C" int dto_create(const dto_problem_desc* d, dto_handle** out) {
             for (int v2 = 0; v2 < v; ++v2)
                 if (s.var_offs[v2] == s.var_offs[v]) return fail_create(h, DTO_ERR_UNSUPPORTED, "objective: repeated variable");
         }
-        std::vector<int> k2o(P.nK, -1), own;
+        std::vector<int> k2o(P.nK, -1), own, ownk;
         for (int t = 0; t < s.n_times; ++t) {
             const int k = s.times[t];
             if (k < 1 || k > N) return fail_create(h, DTO_ERR_INVALID, "objective: time index outside 1..N");
@@ -261,10 +261,13 @@ extern "C" int dto_create(const dto_problem_desc* d, dto_handle** out) {
                 if (k2o[k - h->k0] >= 0) return fail_create(h, DTO_ERR_UNSUPPORTED, "objective: repeated time index");
                 k2o[k - h->k0] = (int)own.size();
                 own.push_back(t);
+                ownk.push_back(k - h->k0);
             }
         }
         O.var_offs = dev_upload(h, s.var_offs, s.n_vars);
         O.own_ti = dev_upload(h, own.data(), own.size());
+        O.own_knot = dev_upload(h, ownk.data(), ownk.size());
+        O.nt_own = (int)own.size();
         O.knot_to_own = dev_upload(h, k2o.data(), k2o.size());
         if (s.kind == DTO_OBJ_QUADREG) {
             if (!s.R) return fail_create(h, DTO_ERR_INVALID, "quadratic regularizer: missing R");
@@ -467,7 +470,7 @@ extern "C" int dto_create(const dto_problem_desc* d, dto_handle** out) {
     h->dgrad = dev_upload<double>(h, nullptr, B * (size_t)P.nOwn * z);
     h->dJ = dev_upload<double>(h, nullptr, B);
     h->dviol = dev_upload<double>(h, nullptr, B);
-    h->dpartials = dev_upload<double>(h, nullptr, B * (size_t)P.nOwn);
+    h->dpartials = dev_upload<double>(h, nullptr, B * ((size_t)P.nOwn + (size_t)(P.nOwn + 2047) / 2048));
     if (d->eval_hessian) h->dhess = dev_upload<double>(h, nullptr, B * (size_t)std::max<long long>(P.nnz_hess_local, 1));
     if (!h->dZ || !h->dmu || !h->dg || !h->djac || !h->dgrad || !h->dJ || !h->dpartials || (d->eval_hessian && !h->dhess))
         return fail_create(h, DTO_ERR_ALLOC, "device allocation failed (work buffers)");

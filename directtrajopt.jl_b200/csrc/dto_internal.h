@@ -35,6 +35,8 @@ struct DObj {
     double D;
     const int* var_offs;
     const int* own_ti;        // owned entries -> index into params/Qs (original position in `times`)
+    const int* own_knot;      // owned entries -> local knot (0-based)
+    int nt_own;
     const int* knot_to_own;   // [local knots] -> owned entry index or -1
     const double* R;
     const double* baseline;   // nv x N (global knots), may be null
