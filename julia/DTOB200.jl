@@ -1,0 +1,209 @@
+# DTOB200.jl -- reference-side binding of libdto_b200.so: a drop-in `MOI.AbstractNLPEvaluator`
+# for DirectTrajOpt.jl's `Solvers.Evaluator` (src/solvers/evaluator.jl:66-456).
+#
+# STATUS: written against include/dto_b200.h, NOT executed -- there is no Julia toolchain in the build
+# container or on the GPU box (profiles/r01_fp64_peaks_and_box_probe.log).  The same ABI is exercised
+# end to end through the Python ctypes mirror (directtrajopt.jl_b200/_lib.py, tests/).
+#
+# Usage inside DirectTrajOpt.jl (the only two construction sites of the evaluator):
+#   src/solvers/ipopt_solver/solver.jl:68-69   evaluator = DTOB200.B200Evaluator(prob; eval_hessian = options.eval_hessian)
+#   ext/MadNLPSolverExt/solver.jl:81           evaluator = DTOB200.B200Evaluator(prob; eval_hessian = true)
+# Everything above `MOI.NLPBlockData(nl_cons, evaluator, true)` stays the reference's Julia.
+module DTOB200
+
+import MathOptInterface as MOI
+using NamedTrajectories
+using DirectTrajOpt
+
+const LIB = get(ENV, "DTO_B200_LIB", joinpath(@__DIR__, "..", "directtrajopt.jl_b200", "lib", "libdto_b200.so"))
+const ABI_VERSION = Cint(1)
+
+# ---- mirror of the C descriptor structs (include/dto_b200.h) -------------------------------------
+struct IntegratorDesc
+    kind::Cint; x_off::Cint; x_dim::Cint; u_off::Cint; u_dim::Cint; t_off::Cint; spline_order::Cint; n_carrier::Cint
+    G::Ptr{Cdouble}; G_batch_stride::Int64
+    A::Ptr{Cdouble}; B::Ptr{Cdouble}; omega::Ptr{Cdouble}; phi::Ptr{Cdouble}
+    D::Ptr{Cdouble}; omega_d::Ptr{Cdouble}; phi_d::Ptr{Cdouble}
+    tdb_steps::Cint; _pad::Cint
+end
+struct ObjectiveDesc
+    kind::Cint; fn::Cint; weight::Cdouble; n_vars::Cint; n_times::Cint
+    var_offs::Ptr{Cint}; times::Ptr{Cint}; R::Ptr{Cdouble}; baseline::Ptr{Cdouble}; D::Cdouble
+    n_params::Cint; _pad::Cint; params::Ptr{Cdouble}; Qs::Ptr{Cdouble}
+end
+struct ConstraintDesc
+    fn::Cint; equality::Cint; n_vars::Cint; n_times::Cint
+    var_offs::Ptr{Cint}; times::Ptr{Cint}; g_dim::Cint; n_params::Cint; params::Ptr{Cdouble}
+end
+struct ProblemDesc
+    abi_version::Cint; N::Cint; z::Cint; dt_off::Cint; batch::Cint; eval_hessian::Cint
+    shard_k0::Cint; shard_k1::Cint; device::Cint; n_integrators::Cint; n_objectives::Cint; n_constraints::Cint
+    integrators::Ptr{IntegratorDesc}; objectives::Ptr{ObjectiveDesc}; constraints::Ptr{ConstraintDesc}; Z0::Ptr{Cdouble}
+end
+struct SizeInfo
+    n_vars::Int64; n_dynamics_cons::Int64; n_nonlinear_cons::Int64; n_cons::Int64; nnz_jac::Int64; nnz_hess::Int64
+end
+
+# ---- device catalogue of knot functions (the Julia closures g, l cannot cross a C ABI) -------------
+abstract type KnotFunction end
+struct NormMinus <: KnotFunction; c::Float64; end            # g(v) = [norm(v) - c]
+struct NormSqMinus <: KnotFunction; c::Float64; end          # g(v) = [norm(v)^2 - c]
+struct SqDist <: KnotFunction; target::Vector{Float64}; end  # l(v) = norm(v - target)^2
+struct IsoInfidelity <: KnotFunction; goal::Vector{Float64}; end
+cfun_id(::NormMinus) = Cint(1); cfun_id(::NormSqMinus) = Cint(2)
+lfun_id(::SqDist) = Cint(2); lfun_id(::IsoInfidelity) = Cint(4)
+params(f::NormMinus) = [f.c]; params(f::NormSqMinus) = [f.c]; params(f::SqDist) = f.target; params(f::IsoInfidelity) = f.goal
+
+"""Lower `G::Function` of a BilinearIntegrator to (G_drift, G_drives) by probing; error if G is not affine in u
+(no CPU fallback: unsupported components raise at construction, never mid-solve)."""
+function lower_generator(G, m::Int)
+    G0 = Matrix{Float64}(G(zeros(m)))
+    drives = [Matrix{Float64}(G([i == j ? 1.0 : 0.0 for j = 1:m])) - G0 for i = 1:m]
+    u = randn(m)
+    Gt = G0 + sum(u[i] * drives[i] for i = 1:m; init = zero(G0))
+    isapprox(Matrix{Float64}(G(u)), Gt; rtol = 1e-12, atol = 1e-12 * (1 + maximum(abs, Gt))) ||
+        error("BilinearIntegrator: G(u) is not affine in u and cannot be lowered to the device")
+    return G0, drives
+end
+
+mutable struct B200Evaluator <: MOI.AbstractNLPEvaluator
+    handle::Ptr{Cvoid}
+    trajectory::NamedTrajectory
+    objective::Any
+    integrators::Vector
+    constraints::Vector
+    jacobian_structure::Vector{Tuple{Int,Int}}
+    hessian_structure::Vector{Tuple{Int,Int}}
+    n_dynamics_constraints::Int
+    n_nonlinear_constraints::Int
+    n_constraints::Int
+    eval_hessian::Bool
+end
+
+check(rc::Cint, h) = rc == 0 || error("libdto_b200: " * unsafe_string(ccall((:dto_last_error, LIB), Cstring, (Ptr{Cvoid},), h)))
+
+"""
+    B200Evaluator(prob::DirectTrajOptProblem; eval_hessian=true, knot_functions=Dict())
+
+`knot_functions` maps each `NonlinearKnotPointConstraint` / `KnotPointObjective` of `prob` to its catalogue entry
+(e.g. `g_u_norm => NormMinus(1.0)`, `J_terminal => SqDist(traj.goal.x)`).
+"""
+function B200Evaluator(prob; eval_hessian = true, knot_functions = Dict())
+    traj = prob.trajectory
+    keep = Any[]  # GC roots for every array the descriptor points into (only needed until dto_create returns)
+    off(name) = Cint(first(traj.components[name]) - 1)
+    ints = IntegratorDesc[]
+    for it in prob.integrators
+        if it isa BilinearIntegrator
+            m = traj.dims[it.u_name]
+            # it.f closes over G; DirectTrajOpt keeps G reachable as `it.f.G` (closure field)
+            G0, drives = lower_generator(it.f.G, m)
+            Gs = vcat(vec(G0), (vec(d) for d in drives)...)   # column-major matrices, drift first
+            push!(keep, Gs)
+            push!(ints, IntegratorDesc(1, off(it.x_name), it.x_dim, off(it.u_name), m, -1, 0, 0, pointer(Gs), 0,
+                                       C_NULL, C_NULL, C_NULL, C_NULL, C_NULL, C_NULL, C_NULL, 0, 0))
+        elseif it isa DerivativeIntegrator
+            push!(ints, IntegratorDesc(2, off(it.x_name), it.x_dim, off(it.ẋ_name), it.x_dim, -1, 0, 0, C_NULL, 0,
+                                       C_NULL, C_NULL, C_NULL, C_NULL, C_NULL, C_NULL, C_NULL, 0, 0))
+        else
+            error("integrator $(typeof(it)) has no device lowering (TimeDependentBilinearIntegrator needs a CarrierGenerator)")
+        end
+    end
+    objs = ObjectiveDesc[]
+    terms = prob.objective isa DirectTrajOpt.Objectives.CompositeObjective ?
+            collect(zip(prob.objective.objectives, prob.objective.weights)) : [(prob.objective, 1.0)]
+    for (ob, w) in terms
+        if ob isa QuadraticRegularizer
+            vo = Cint.(collect(traj.components[ob.name]) .- 1); tm = Cint.(ob.times); R = copy(ob.R); base = copy(ob.baseline)
+            append!(keep, (vo, tm, R, base))
+            push!(objs, ObjectiveDesc(1, 0, w, length(vo), length(tm), pointer(vo), pointer(tm), pointer(R),
+                                      any(!iszero, base) ? pointer(base) : C_NULL, 0.0, 0, 0, C_NULL, C_NULL))
+        elseif ob isa MinimumTimeObjective
+            push!(objs, ObjectiveDesc(2, 0, w, 0, 0, C_NULL, C_NULL, C_NULL, C_NULL, ob.D, 0, 0, C_NULL, C_NULL))
+        elseif ob isa KnotPointObjective
+            f = get(knot_functions, ob, nothing)
+            f === nothing && error("KnotPointObjective needs a catalogue entry in `knot_functions`")
+            vo = Cint.(vcat([collect(traj.components[n]) for n in ob.var_names]...) .- 1); tm = Cint.(ob.times)
+            pr = repeat(params(f), length(tm)); Qs = copy(ob.Qs)
+            append!(keep, (vo, tm, pr, Qs))
+            push!(objs, ObjectiveDesc(3, lfun_id(f), w, length(vo), length(tm), pointer(vo), pointer(tm), C_NULL, C_NULL, 0.0,
+                                      length(params(f)), 0, pointer(pr), pointer(Qs)))
+        elseif ob isa NullObjective
+            push!(objs, ObjectiveDesc(4, 0, w, 0, 0, C_NULL, C_NULL, C_NULL, C_NULL, 0.0, 0, 0, C_NULL, C_NULL))
+        else
+            error("objective $(typeof(ob)) has no device lowering")
+        end
+    end
+    nl = filter(c -> c isa DirectTrajOpt.Constraints.AbstractNonlinearConstraint, prob.constraints)
+    cons = ConstraintDesc[]
+    for c in nl
+        f = get(knot_functions, c, nothing)
+        (c isa NonlinearKnotPointConstraint && f !== nothing) || error("constraint $(typeof(c)) needs a catalogue entry")
+        vo = Cint.(vcat([collect(traj.components[n]) for n in c.var_names]...) .- 1); tm = Cint.(c.times)
+        pr = repeat(params(f), length(tm)); append!(keep, (vo, tm, pr))
+        push!(cons, ConstraintDesc(cfun_id(f), c.equality, length(vo), length(tm), pointer(vo), pointer(tm), c.g_dim,
+                                   length(params(f)), pointer(pr)))
+    end
+    Z0 = collect(traj.datavec)
+    desc = Ref(ProblemDesc(ABI_VERSION, traj.N, traj.dim, off(traj.timestep), 1, eval_hessian, 0, 0, -1,
+                           length(ints), length(objs), length(cons),
+                           pointer(ints), isempty(objs) ? C_NULL : pointer(objs), isempty(cons) ? C_NULL : pointer(cons), pointer(Z0)))
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve keep ints objs cons Z0 begin
+        rc = ccall((:dto_create, LIB), Cint, (Ref{ProblemDesc}, Ref{Ptr{Cvoid}}), desc, h)
+    end
+    rc == 0 || error("libdto_b200: " * unsafe_string(ccall((:dto_last_error, LIB), Cstring, (Ptr{Cvoid},), C_NULL)))
+    si = Ref(SizeInfo(0, 0, 0, 0, 0, 0))
+    check(ccall((:dto_sizes, LIB), Cint, (Ptr{Cvoid}, Ref{SizeInfo}), h[], si), h[])
+    jr = Vector{Int64}(undef, si[].nnz_jac); jc = similar(jr)
+    check(ccall((:dto_jac_structure, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}), h[], jr, jc), h[])
+    hr = Vector{Int64}(undef, si[].nnz_hess); hc = similar(hr)
+    check(ccall((:dto_hess_structure, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}), h[], hr, hc), h[])
+    ev = B200Evaluator(h[], traj, prob.objective, prob.integrators, collect(nl), collect(zip(jr, jc)), collect(zip(hr, hc)),
+                       si[].n_dynamics_cons, si[].n_nonlinear_cons, si[].n_cons, eval_hessian)
+    finalizer(e -> ccall((:dto_destroy, LIB), Cvoid, (Ptr{Cvoid},), e.handle), ev)
+    return ev
+end
+
+# ---- the MOI interface, signature for signature (src/solvers/evaluator.jl:291-456) ------------------
+MOI.initialize(::B200Evaluator, features) = nothing
+MOI.features_available(e::B200Evaluator) = e.eval_hessian ? [:Grad, :Jac, :Hess] : [:Grad, :Jac]
+MOI.jacobian_structure(e::B200Evaluator) = e.jacobian_structure
+MOI.hessian_lagrangian_structure(e::B200Evaluator) = e.hessian_structure
+
+dense(v::AbstractVector) = v isa Vector{Float64} ? v : collect(Float64, v)   # Z may be any AbstractVector
+
+function MOI.eval_objective(e::B200Evaluator, Z::AbstractVector)
+    J = Ref(0.0)
+    check(ccall((:dto_eval_objective, LIB), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Ref{Cdouble}), e.handle, dense(Z), J), e.handle)
+    return J[]
+end
+function MOI.eval_objective_gradient(e::B200Evaluator, g::AbstractVector, Z::AbstractVector)
+    check(ccall((:dto_eval_gradient, LIB), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}), e.handle, dense(Z), g), e.handle)
+    return nothing
+end
+function MOI.eval_constraint(e::B200Evaluator, g::AbstractVector, Z::AbstractVector)
+    check(ccall((:dto_eval_constraint, LIB), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}), e.handle, dense(Z), g), e.handle)
+    return nothing
+end
+function MOI.eval_constraint_jacobian(e::B200Evaluator, J::AbstractVector, Z::AbstractVector)
+    check(ccall((:dto_eval_jacobian, LIB), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}), e.handle, dense(Z), J), e.handle)
+    return nothing
+end
+function MOI.eval_hessian_lagrangian(e::B200Evaluator, H::AbstractVector{T}, Z::AbstractVector{T}, σ::T, μ::AbstractVector{T}) where {T}
+    check(ccall((:dto_eval_hessian, LIB), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Cdouble, Ptr{Cdouble}, Ptr{Cdouble}),
+                e.handle, dense(Z), σ, dense(μ), H), e.handle)
+    return nothing
+end
+function MOI.eval_constraint_jacobian_product(e::B200Evaluator, y::AbstractVector{T}, x::AbstractVector{T}, w::AbstractVector{T}) where {T}
+    check(ccall((:dto_eval_jacobian_product, LIB), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}),
+                e.handle, dense(x), dense(w), y), e.handle)
+    return nothing
+end
+function MOI.eval_constraint_jacobian_transpose_product(e::B200Evaluator, y::AbstractVector{T}, x::AbstractVector{T}, w::AbstractVector{T}) where {T}
+    check(ccall((:dto_eval_jacobian_transpose_product, LIB), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}),
+                e.handle, dense(x), dense(w), y), e.handle)
+    return nothing
+end
+
+end # module
