@@ -3,6 +3,7 @@
 // (/root/reference/src/solvers/evaluator.jl:99-288), device residency, and the C ABI of
 // include/dto_b200.h.  No torch types, no CPU compute fallback: every value comes from a kernel.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -190,6 +191,15 @@ extern "C" int dto_create(const dto_problem_desc* d, dto_handle** out) {
             }
             I.hs_stride = (s.u_dim + 1) * s.x_dim + (s.u_dim + 1) * (s.u_dim + 1);
             I.variant = bilinear_dmma_supported(s.x_dim, s.u_dim) ? DTO_VAR_DMMA : DTO_VAR_GENERIC;
+            // DTO_B200_KERNEL=generic|dmma pins an older variant (A/B measurements, parity tests of every variant)
+            const char* pin = getenv("DTO_B200_KERNEL");
+            const bool pin_generic = pin && strcmp(pin, "generic") == 0, pin_dmma = pin && strcmp(pin, "dmma") == 0;
+            if (bilinear_persistent_supported(s.x_dim, s.u_dim) && s.G_batch_stride == 0 && !pin_dmma && !pin_generic) {
+                I.variant = DTO_VAR_PERSISTENT;
+                I.wq = dev_upload<unsigned long long>(h, nullptr, 4);
+                if (!I.wq) return fail_create(h, DTO_ERR_ALLOC, "device allocation failed (work queue)");
+            }
+            if (pin_generic) I.variant = DTO_VAR_GENERIC;
             if (s.x_dim > 96) return fail_create(h, DTO_ERR_UNSUPPORTED, "bilinear integrator: state dimension > 96 not supported");
         } else if (s.kind == DTO_INT_DERIVATIVE) {
             if (s.u_dim != s.x_dim || s.u_off < 0 || s.u_off + s.u_dim > z) return fail_create(h, DTO_ERR_INVALID, "derivative integrator: derivative component must match the variable's dimension");
@@ -224,7 +234,7 @@ extern "C" int dto_create(const dto_problem_desc* d, dto_handle** out) {
         goff += (long long)s.x_dim * (N - 1);
         loff += (long long)s.x_dim * P.nI;
         doff += s.x_dim;
-        h->variants.push_back(s.kind == DTO_INT_BILINEAR ? (I.variant == DTO_VAR_DMMA ? "dmma" : "generic")
+        h->variants.push_back(s.kind == DTO_INT_BILINEAR ? (I.variant == DTO_VAR_PERSISTENT ? "persistent" : I.variant == DTO_VAR_DMMA ? "dmma" : "generic")
                                                          : (s.kind == DTO_INT_DERIVATIVE ? "analytic" : "rk"));
     }
     P.Dsum = doff;
@@ -664,7 +674,8 @@ static int run_eval(dto_handle* h, const double* dZ, double sigma, const double*
             if (timed) cudaEventRecord(h->ev_pool[h->ev_used].first, h->stream);
             if (P.in[i].kind == DTO_INT_BILINEAR) {
                 bool done = false;
-                if (P.in[i].variant == DTO_VAR_DMMA) done = launch_bilinear_dmma(P, i, dZ, dmu, dg, djac, f, h->stream, &h->launches);
+                if (P.in[i].variant == DTO_VAR_PERSISTENT) done = launch_bilinear_persistent(P, i, dZ, dmu, dg, djac, f, h->stream, &h->launches);
+                if (!done && P.in[i].variant >= DTO_VAR_DMMA && bilinear_dmma_supported(P.in[i].n, P.in[i].m)) done = launch_bilinear_dmma(P, i, dZ, dmu, dg, djac, f, h->stream, &h->launches);
                 if (!done) launch_bilinear_generic(P, i, dZ, dmu, dg, djac, f, h->stream, &h->launches);
             } else if (P.in[i].kind == DTO_INT_TDBILINEAR) {
                 launch_tdb(P, i, dZ, dmu, dg, djac, f, h->stream, &h->launches);

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -26,6 +27,7 @@ struct DInt {
     const double* Grm;  // bilinear: row-major copies of the same matrices
     const double *A, *B, *omega, *phi, *D, *omega_d, *phi_d;
     double* hs;         // [batch][n_intervals][hs_stride]
+    unsigned long long* wq;  // bilinear, persistent variant: three work-queue counters (FWD, EXP, ADJ)
 };
 
 struct DObj {
@@ -92,7 +94,7 @@ __host__ __device__ inline long long hess_knot_base(const DProb& P, int kl) {
 __host__ __device__ inline bool hess_knot_has_cross(const DProb& P, int kl) { return kl > 0 || P.first_has_cross; }
 
 // variants of the bilinear kernel
-enum { DTO_VAR_GENERIC = 0, DTO_VAR_DMMA = 1 };
+enum { DTO_VAR_GENERIC = 0, DTO_VAR_DMMA = 1, DTO_VAR_PERSISTENT = 2 };
 
 // ---- kernel launchers (defined in the .cu files) ------------------------------------------------
 struct EvalFlags {
@@ -103,6 +105,9 @@ void launch_bilinear_generic(const DProb& P, int ii, const double* Z, const doub
 bool launch_bilinear_dmma(const DProb& P, int ii, const double* Z, const double* mu, double* g, double* jac, EvalFlags f,
                           cudaStream_t st, long long* launches);
 bool bilinear_dmma_supported(int n, int m);
+bool launch_bilinear_persistent(const DProb& P, int ii, const double* Z, const double* mu, double* g, double* jac, EvalFlags f,
+                                cudaStream_t st, long long* launches);
+bool bilinear_persistent_supported(int n, int m);
 bool tdb_available();
 bool tdb_fits(const DInt& I);
 void launch_tdb(const DProb& P, int ii, const double* Z, const double* mu, double* g, double* jac, EvalFlags f, cudaStream_t st,

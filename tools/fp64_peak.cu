@@ -105,6 +105,34 @@ __global__ void dmma884_lds_kernel(double* out, int iters) {
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// mixed issue: every warp interleaves NACC DMMA.8x8x4 with NF independent DFMA per iteration.  If the time equals
+// max(DMMA-only, DFMA-only) the two are separate datapaths; if it equals the sum they share one.
+template <int NACC, int NF>
+__global__ void mixed_kernel(double* out, int iters, double fa, double fb) {
+    double c[NACC > 0 ? NACC : 1][2];
+    double x[NF > 0 ? NF : 1];
+    double a = threadIdx.x * 1e-3, b = 1.0 - threadIdx.x * 1e-4;
+#pragma unroll
+    for (int j = 0; j < NACC; ++j) { c[j][0] = j; c[j][1] = -j; }
+#pragma unroll
+    for (int j = 0; j < NF; ++j) x[j] = threadIdx.x + j;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int j = 0; j < (NACC > NF ? NACC : NF); ++j) {
+            if (j < NACC)
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                             : "+d"(c[j][0]), "+d"(c[j][1]) : "d"(a), "d"(b));
+            if (j < NF) asm volatile("fma.rn.f64 %0, %0, %1, %2;\n" : "+d"(x[j]) : "d"(fa), "d"(fb));
+        }
+    }
+    double s = 0;
+#pragma unroll
+    for (int j = 0; j < NACC; ++j) s += c[j][0] + c[j][1];
+#pragma unroll
+    for (int j = 0; j < NF; ++j) s += x[j];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 template <typename F>
 float time_ms(F launch, int reps) {
     cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
@@ -151,6 +179,19 @@ int main() {
             double flops = 2.0 * 8 * 8 * 4 * 8.0 * iters * (double)blocks * wps;
             printf("DMMA m8n8k4+LDS warps/SM %2d acc8 : %.3f ms  %.2f TFLOP/s\n", wps, ms, flops / ms * 1e-9);
         }
+    }
+    // are DFMA and DMMA one datapath or two?  (8 warps/SM; per iteration 8 DMMA = 4096 flop/warp, NF DFMA = 64*NF flop/warp)
+    {
+        int blocks = nsm, threads = 8 * 32;
+        float m0 = time_ms([&] { mixed_kernel<8, 0><<<blocks, threads>>>(out, iters, 1.0000001, 1e-9); }, 5);
+        float f16 = time_ms([&] { mixed_kernel<0, 16><<<blocks, threads>>>(out, iters, 1.0000001, 1e-9); }, 5);
+        float f64 = time_ms([&] { mixed_kernel<0, 64><<<blocks, threads>>>(out, iters, 1.0000001, 1e-9); }, 5);
+        float x16 = time_ms([&] { mixed_kernel<8, 16><<<blocks, threads>>>(out, iters, 1.0000001, 1e-9); }, 5);
+        float x64 = time_ms([&] { mixed_kernel<8, 64><<<blocks, threads>>>(out, iters, 1.0000001, 1e-9); }, 5);
+        printf("MIXED 8 warps/SM: 8 DMMA only %.3f ms | 16 DFMA only %.3f ms | 64 DFMA only %.3f ms | 8 DMMA + 16 DFMA %.3f ms | 8 DMMA + 64 DFMA %.3f ms\n",
+               m0, f16, f64, x16, x64);
+        double fl = (4096.0 + 64.0 * 64) * iters * (double)blocks * 8;
+        printf("MIXED 8 DMMA + 64 DFMA combined rate: %.2f TFLOP/s\n", fl / x64 * 1e-9);
     }
     // dependent-chain latency: one warp per SM, single accumulator
     {
