@@ -40,7 +40,8 @@ __global__ void analytic_kernel(DProb P, const double* __restrict__ Z, double* _
     // one warp per (problem, interval)
     const long long item = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (item >= total) return;
-    const int b = (int)(item / P.nI), kl = (int)(item % P.nI), z = P.z, lane = threadIdx.x & 31;
+    const int nIc = min(P.kc1, P.nI) - P.kc0;  // intervals of the active range
+    const int b = (int)(item / nIc), kl = P.kc0 + (int)(item % nIc), z = P.z, lane = threadIdx.x & 31;
     const double* zk = Z + (long long)b * P.n_vars_local + (long long)kl * z;
     const double* zk1 = zk + z;
     if (P.halo != nullptr && kl + 1 == P.nK - 1) zk1 = P.halo;
@@ -145,7 +146,8 @@ __global__ void hessian_assemble_kernel(DProb P, const double* __restrict__ Z, d
     const int warp = threadIdx.x >> 5;
     const long long item = (long long)blockIdx.x * warps_per_cta + warp;
     if (item >= total) return;
-    const int b = (int)(item / P.nOwn), kl = (int)(item % P.nOwn);
+    const int nKc = min(P.kc1, P.nOwn) - P.kc0;  // owned knots of the active range
+    const int b = (int)(item / nKc), kl = P.kc0 + (int)(item % nKc);
     const int tiles = P.any_cross ? 2 : 1;
     double* diag = sm + (size_t)warp * tiles * z * z;  // z*z, entries (i<=l) used
     double* cross = diag + z * z;                      // z*z if any_cross: cross[i*z + l] = H[knot kl-1 comp i][knot kl comp l]
@@ -306,6 +308,7 @@ __global__ void knot_objective_hessian_kernel(DProb P, int oi, const double* __r
     }
     const int c = a + p;
     const int kl = O.own_knot[j];
+    if (kl < P.kc0 || kl >= P.kc1) return;  // assembled (and added to) by another launch of the pipeline
     const double* zk = Z + (long long)b * P.n_vars_local + (long long)kl * z;
     const double* prm = O.params + (long long)O.own_ti[j] * O.np;
     const HDual res = knot_lfun<HDual>(O.fn, SeededVars{zk, O.var_offs, a, c}, nv, prm);
@@ -434,11 +437,15 @@ __global__ void jac_product_kernel(long long nnz, long long n_rows, long long n_
 void launch_analytic(const DProb& P, const double* Z, double* g, double* jac, EvalFlags f, cudaStream_t st, long long* launches) {
     bool any_deriv = false;
     for (int i = 0; i < P.n_int; ++i) any_deriv |= P.in[i].kind == DTO_INT_DERIVATIVE;
-    if (any_deriv && P.nI > 0) {
-        const long long total = (long long)P.nI * P.batch;
+    const int nIc = std::min(P.kc1, P.nI) - P.kc0;
+    if (any_deriv && nIc > 0) {
+        const long long total = (long long)nIc * P.batch;
         analytic_kernel<<<(unsigned)((total + 7) / 8), 256, 0, st>>>(P, Z, f.want_g ? g : nullptr, f.want_jac ? jac : nullptr, total);
         ++*launches;
     }
+}
+
+void launch_constraints(const DProb& P, const double* Z, double* g, double* jac, EvalFlags f, cudaStream_t st, long long* launches) {
     for (int ci = 0; ci < P.n_con; ++ci) {
         const long long tot = (long long)P.batch * P.co[ci].nt_own;
         if (tot == 0) continue;
@@ -463,7 +470,8 @@ void launch_constraint_pattern_probe(const DProb& P, const double* Z, double* de
 
 void launch_hessian_assemble(const DProb& P, const double* Z, double sigma, const double* mu, double* hess, cudaStream_t st,
                              long long* launches) {
-    if (P.nOwn <= 0) return;
+    const int nKc = std::min(P.kc1, P.nOwn) - P.kc0;
+    if (nKc <= 0) return;
     const size_t per_warp = sizeof(double) * (size_t)P.z * P.z * (P.any_cross ? 2 : 1);
     int W = 8;
     while (W > 1 && W * per_warp > 64 * 1024) W >>= 1;
@@ -473,13 +481,14 @@ void launch_hessian_assemble(const DProb& P, const double* Z, double sigma, cons
         cudaFuncSetAttribute(hessian_assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         configured = 227 * 1024;
     }
-    const long long total = (long long)P.nOwn * P.batch;
+    const long long total = (long long)nKc * P.batch;
     hessian_assemble_kernel<<<(unsigned)((total + W - 1) / W), W * 32, smem, st>>>(P, Z, sigma, mu, hess, W, total);
     ++*launches;
     if (sigma != 0.0)
         for (int oi = 0; oi < P.n_obj; ++oi) {
             const DObj& O = P.ob[oi];
             if (O.kind != DTO_OBJ_KNOT || O.nt_own == 0) continue;
+            if (O.own_kmax < P.kc0 || O.own_kmin >= P.kc1) continue;  // no listed knot in the active range
             const long long tot = (long long)P.batch * O.nt_own * (O.nv * (O.nv + 1) / 2);
             knot_objective_hessian_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(P, oi, Z, sigma, hess, tot);
             ++*launches;

@@ -819,7 +819,8 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1)
         }
     }
 
-    const unsigned long long nItems = (unsigned long long)P.batch * (unsigned long long)P.nI;
+    const int nIc = min(P.kc1, P.nI) - P.kc0;  // intervals of the active range
+    const unsigned long long nItems = (unsigned long long)P.batch * (unsigned long long)nIc;
     // Paterson-Stockmeyer warps clear the propagators first and then join the others; when no warp has
     // spare matrices (nE == 0) the propagators run in series mode on every warp, after the forward items
     int order[3];
@@ -835,7 +836,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1)
             if (lane == 0) id = atomicAdd(&wq[role], 1ULL);
             id = __shfl_sync(0xffffffffu, id, 0);
             if (id >= nItems) break;
-            const int b = (int)(id / (unsigned long long)P.nI), kk = (int)(id % (unsigned long long)P.nI);
+            const int b = (int)(id / (unsigned long long)nIc), kk = P.kc0 + (int)(id % (unsigned long long)nIc);
             __syncwarp();
 #ifndef DTO_SKIP_FWD
             if (role == ROLE_FWD) role_forward<NT, MT>(c, b, kk, src, coef);
@@ -896,7 +897,7 @@ bool launch_variant(const DProb& P, int ii, const double* Z, const double* mu, d
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return false;
         configured = true;
     }
-    const long long items = (long long)P.batch * P.nI;
+    const long long items = (long long)P.batch * (std::min(P.kc1, P.nI) - P.kc0);
     const long long roles = 1 + (f.want_jac ? 1 : 0) + (f.want_hess ? 1 : 0);
     const long long want_ctas = (items * roles + W - 1) / W;
     const int grid = (int)std::max<long long>(1, std::min<long long>(sms, want_ctas));
@@ -916,7 +917,7 @@ bool bilinear_persistent_supported(int n, int m) {
 bool launch_bilinear_persistent(const DProb& P, int ii, const double* Z, const double* mu, double* g, double* jac, EvalFlags f,
                                 cudaStream_t st, long long* launches) {
     const DInt& I = P.in[ii];
-    if (P.nI <= 0) return true;
+    if (std::min(P.kc1, P.nI) - P.kc0 <= 0) return true;
     if (!bilinear_persistent_supported(I.n, I.m) || I.G_stride != 0 || I.wq == nullptr) return false;
     const int nrows = f.want_hess ? 1 + I.m + I.m * (I.m + 1) / 2 : 1 + I.m;
     const bool two = nrows > 8;

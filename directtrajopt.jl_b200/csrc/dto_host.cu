@@ -53,6 +53,10 @@ struct dto_handle {
     long long *d_rows0 = nullptr, *d_cols0 = nullptr;
     void* ipc_peer = nullptr;
     long long launches = 0;
+    // host-pointer path: outputs leave over PCIe while later knot ranges are still being computed
+    cudaStream_t copy_stream = nullptr;
+    std::vector<cudaEvent_t> chunk_events;
+    std::vector<double> pipeline_fracs;  // cumulative interval fractions of the chunk boundaries (empty = no pipelining)
     std::vector<std::string> variants;
     // optional device timing of the interval kernels (bench.py's roofline numerator)
     int timing = 0;
@@ -101,6 +105,8 @@ extern "C" void dto_destroy(dto_handle* h) {
         cudaEventDestroy(e.second);
     }
     for (void* p : h->allocs) cudaFree(p);
+    for (cudaEvent_t e : h->chunk_events) cudaEventDestroy(e);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -149,6 +155,8 @@ extern "C" int dto_create(const dto_problem_desc* d, dto_handle** out) {
     P.nOwn = h->k1 - h->k0 + 1;
     P.nK = P.nOwn + (h->k1 < N ? 1 : 0);
     P.nI = P.nK - 1;
+    P.kc0 = 0;
+    P.kc1 = P.nK;
     P.first_has_cross = h->k0 > 1;
     P.n_int = d->n_integrators;
     P.n_obj = d->n_objectives;
@@ -278,6 +286,8 @@ extern "C" int dto_create(const dto_problem_desc* d, dto_handle** out) {
         O.own_ti = dev_upload(h, own.data(), own.size());
         O.own_knot = dev_upload(h, ownk.data(), ownk.size());
         O.nt_own = (int)own.size();
+        O.own_kmin = ownk.empty() ? 0 : *std::min_element(ownk.begin(), ownk.end());
+        O.own_kmax = ownk.empty() ? -1 : *std::max_element(ownk.begin(), ownk.end());
         O.knot_to_own = dev_upload(h, k2o.data(), k2o.size());
         if (s.kind == DTO_OBJ_QUADREG) {
             if (!s.R) return fail_create(h, DTO_ERR_INVALID, "quadratic regularizer: missing R");
@@ -484,6 +494,24 @@ extern "C" int dto_create(const dto_problem_desc* d, dto_handle** out) {
     if (d->eval_hessian) h->dhess = dev_upload<double>(h, nullptr, B * (size_t)std::max<long long>(P.nnz_hess_local, 1));
     if (!h->dZ || !h->dmu || !h->dg || !h->djac || !h->dgrad || !h->dJ || !h->dpartials || (d->eval_hessian && !h->dhess))
         return fail_create(h, DTO_ERR_ALLOC, "device allocation failed (work buffers)");
+    {
+        // chunk boundaries of the host-pointer pipeline as cumulative fractions of the intervals; DTO_B200_PIPELINE=0
+        // disables it, DTO_B200_PIPELINE=0.1,0.4,0.7 overrides the plan
+        const char* env = getenv("DTO_B200_PIPELINE");
+        if (!env) h->pipeline_fracs = {0.1, 0.4, 0.7};
+        else if (strcmp(env, "0") != 0) {
+            std::string t(env);
+            size_t pos = 0;
+            while (pos < t.size()) {
+                size_t nx = t.find(',', pos);
+                if (nx == std::string::npos) nx = t.size();
+                const double v = atof(t.substr(pos, nx - pos).c_str());
+                if (v > 0.0 && v < 1.0) h->pipeline_fracs.push_back(v);
+                pos = nx + 1;
+            }
+            std::sort(h->pipeline_fracs.begin(), h->pipeline_fracs.end());
+        }
+    }
     if (cudaStreamSynchronize(h->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess)
         return fail_create(h, DTO_ERR_CUDA, "CUDA failure during construction");
     *out = h;
@@ -655,9 +683,37 @@ extern "C" int dto_constraint_bounds(const dto_handle* h, double* lower, double*
 }
 
 // ---- evaluation ------------------------------------------------------------------------------------
-static int run_eval(dto_handle* h, const double* dZ, double sigma, const double* dmu, double* dJ, double* dgrad, double* dg,
-                    double* djac, double* dhess) {
-    const DProb& P = h->P;
+// Knot constraints and objective: independent of the interval kernels, cheap, whole trajectory at once.
+static void eval_prologue(dto_handle* h, const DProb& P, const double* dZ, double* dJ, double* dgrad, double* dg, double* djac,
+                          EvalFlags f) {
+    if (f.want_g || f.want_jac) launch_constraints(P, dZ, dg, djac, f, h->stream, &h->launches);
+    if (dJ || dgrad) launch_objective(P, dZ, dJ, dgrad, h->dpartials, h->stream, &h->launches);
+}
+
+// Interval kernels, analytic integrators and the Hessian assembler over the active knot range of P.
+static void eval_range(dto_handle* h, const DProb& P, const double* dZ, double sigma, const double* dmu, double* dg, double* djac,
+                       double* dhess, EvalFlags f) {
+    if (!(f.want_g || f.want_jac || f.want_hess)) return;
+    for (int i = 0; i < P.n_int; ++i) {
+        if (P.in[i].kind == DTO_INT_DERIVATIVE) continue;
+        const bool timed = h->timing && h->ev_used < h->ev_pool.size();
+        if (timed) cudaEventRecord(h->ev_pool[h->ev_used].first, h->stream);
+        if (P.in[i].kind == DTO_INT_BILINEAR) {
+            bool done = false;
+            if (P.in[i].variant == DTO_VAR_PERSISTENT) done = launch_bilinear_persistent(P, i, dZ, dmu, dg, djac, f, h->stream, &h->launches);
+            if (!done && P.in[i].variant >= DTO_VAR_DMMA && bilinear_dmma_supported(P.in[i].n, P.in[i].m))
+                done = launch_bilinear_dmma(P, i, dZ, dmu, dg, djac, f, h->stream, &h->launches);
+            if (!done) launch_bilinear_generic(P, i, dZ, dmu, dg, djac, f, h->stream, &h->launches);
+        } else if (P.in[i].kind == DTO_INT_TDBILINEAR) {
+            launch_tdb(P, i, dZ, dmu, dg, djac, f, h->stream, &h->launches);
+        }
+        if (timed) cudaEventRecord(h->ev_pool[h->ev_used++].second, h->stream);
+    }
+    if (f.want_g || f.want_jac) launch_analytic(P, dZ, dg, djac, f, h->stream, &h->launches);
+    if (f.want_hess) launch_hessian_assemble(P, dZ, sigma, dmu, dhess, h->stream, &h->launches);
+}
+
+static int check_eval_args(dto_handle* h, const double* dmu, const double* dhess) {
     if (dhess && !h->eval_hessian) {
         h->err = "evaluator was created with eval_hessian = false";
         return DTO_ERR_INVALID;
@@ -666,28 +722,28 @@ static int run_eval(dto_handle* h, const double* dZ, double sigma, const double*
         h->err = "Hessian evaluation needs mu";
         return DTO_ERR_INVALID;
     }
+    return DTO_OK;
+}
+
+static int run_eval(dto_handle* h, const double* dZ, double sigma, const double* dmu, double* dJ, double* dgrad, double* dg,
+                    double* djac, double* dhess) {
+    const DProb& P = h->P;
+    int rc = check_eval_args(h, dmu, dhess);
+    if (rc != DTO_OK) return rc;
     EvalFlags f{dg != nullptr, djac != nullptr, dhess != nullptr};
-    if (f.want_g || f.want_jac || f.want_hess) {
-        for (int i = 0; i < P.n_int; ++i) {
-            if (P.in[i].kind == DTO_INT_DERIVATIVE) continue;
-            const bool timed = h->timing && h->ev_used < h->ev_pool.size();
-            if (timed) cudaEventRecord(h->ev_pool[h->ev_used].first, h->stream);
-            if (P.in[i].kind == DTO_INT_BILINEAR) {
-                bool done = false;
-                if (P.in[i].variant == DTO_VAR_PERSISTENT) done = launch_bilinear_persistent(P, i, dZ, dmu, dg, djac, f, h->stream, &h->launches);
-                if (!done && P.in[i].variant >= DTO_VAR_DMMA && bilinear_dmma_supported(P.in[i].n, P.in[i].m)) done = launch_bilinear_dmma(P, i, dZ, dmu, dg, djac, f, h->stream, &h->launches);
-                if (!done) launch_bilinear_generic(P, i, dZ, dmu, dg, djac, f, h->stream, &h->launches);
-            } else if (P.in[i].kind == DTO_INT_TDBILINEAR) {
-                launch_tdb(P, i, dZ, dmu, dg, djac, f, h->stream, &h->launches);
-            }
-            if (timed) cudaEventRecord(h->ev_pool[h->ev_used++].second, h->stream);
-        }
-        if (f.want_g || f.want_jac) launch_analytic(P, dZ, dg, djac, f, h->stream, &h->launches);
-        if (f.want_hess) launch_hessian_assemble(P, dZ, sigma, dmu, dhess, h->stream, &h->launches);
-    }
-    if (dJ || dgrad) launch_objective(P, dZ, dJ, dgrad, h->dpartials, h->stream, &h->launches);
+    eval_range(h, P, dZ, sigma, dmu, dg, djac, dhess, f);
+    eval_prologue(h, P, dZ, dJ, dgrad, dg, djac, f);
     CUDA_TRY(h, cudaGetLastError());
     return DTO_OK;
+}
+
+// Every interval kernel of the problem honours DProb::kc0/kc1 (only the persistent bilinear variant does)
+static bool range_capable(const dto_handle* h) {
+    const DProb& P = h->P;
+    if (P.batch != 1 || P.any_cross) return false;
+    for (int i = 0; i < P.n_int; ++i)
+        if (P.in[i].kind != DTO_INT_DERIVATIVE && !(P.in[i].kind == DTO_INT_BILINEAR && P.in[i].variant == DTO_VAR_PERSISTENT)) return false;
+    return true;
 }
 
 extern "C" int dto_eval_all_dev(dto_handle* h, const double* dZ, double sigma, const double* dmu, double* dJ, double* dgrad,
@@ -712,24 +768,68 @@ extern "C" int dto_eval_all(dto_handle* h, const double* Z, double sigma, const 
         h->err = "evaluator was created with eval_hessian = false";
         return DTO_ERR_INVALID;
     }
+    if (hess && !mu) {
+        h->err = "Hessian evaluation needs mu";
+        return DTO_ERR_INVALID;
+    }
     CUDA_TRY(h, cudaSetDevice(h->device));
     CUDA_TRY(h, cudaMemcpyAsync(h->dZ, Z, sizeof(double) * B * P.n_vars_local, cudaMemcpyHostToDevice, h->stream));
-    if (hess) {
-        if (!mu) {
-            h->err = "Hessian evaluation needs mu";
-            return DTO_ERR_INVALID;
+    if (hess) CUDA_TRY(h, cudaMemcpyAsync(h->dmu, mu, sizeof(double) * B * P.n_cons_local, cudaMemcpyHostToDevice, h->stream));
+    double* dJ = J ? h->dJ : nullptr;
+    double* dgrad = grad ? h->dgrad : nullptr;
+    double* dg = g ? h->dg : nullptr;
+    double* djac = jac ? h->djac : nullptr;
+    double* dhess = hess ? h->dhess : nullptr;
+    EvalFlags f{dg != nullptr, djac != nullptr, dhess != nullptr};
+
+    // Large sparse outputs: cut the trajectory into a few knot ranges; the Jacobian columns and Hessian
+    // blocks of a finished range go out on the copy engine while the next range is being computed.
+    const long long out_bytes = 8LL * ((jac ? P.nnz_jac_local : 0) + (hess ? P.nnz_hess_local : 0));
+    const bool pipelined = !h->pipeline_fracs.empty() && (jac || hess) && out_bytes >= (8LL << 20) && P.nI >= 512 && range_capable(h);
+    if (!pipelined) {
+        int rc = run_eval(h, h->dZ, sigma, h->dmu, dJ, dgrad, dg, djac, dhess);
+        if (rc != DTO_OK) return rc;
+        if (jac) CUDA_TRY(h, cudaMemcpyAsync(jac, h->djac, sizeof(double) * B * P.nnz_jac_local, cudaMemcpyDeviceToHost, h->stream));
+        if (hess) CUDA_TRY(h, cudaMemcpyAsync(hess, h->dhess, sizeof(double) * B * P.nnz_hess_local, cudaMemcpyDeviceToHost, h->stream));
+    } else {
+        if (!h->copy_stream) CUDA_TRY(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        std::vector<int> bounds{0};
+        for (double fr : h->pipeline_fracs) {
+            const int k = (int)(fr * P.nI);
+            if (k > bounds.back() && k < P.nI) bounds.push_back(k);
         }
-        CUDA_TRY(h, cudaMemcpyAsync(h->dmu, mu, sizeof(double) * B * P.n_cons_local, cudaMemcpyHostToDevice, h->stream));
+        bounds.push_back(P.nK);
+        while (h->chunk_events.size() + 1 < bounds.size()) {
+            cudaEvent_t e;
+            CUDA_TRY(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            h->chunk_events.push_back(e);
+        }
+        eval_prologue(h, P, h->dZ, dJ, dgrad, dg, djac, f);  // knot-constraint entries land before any column leaves
+        DProb Pr = P;
+        for (size_t c = 0; c + 1 < bounds.size(); ++c) {
+            Pr.kc0 = bounds[c];
+            Pr.kc1 = bounds[c + 1];
+            eval_range(h, Pr, h->dZ, sigma, h->dmu, dg, djac, dhess, f);
+            CUDA_TRY(h, cudaEventRecord(h->chunk_events[c], h->stream));
+            CUDA_TRY(h, cudaStreamWaitEvent(h->copy_stream, h->chunk_events[c], 0));
+            if (jac) {
+                // columns of knots [kc0, kc1): their own-interval rows were written by this range, the
+                // previous-interval rows of knot kc0 by the range before
+                const long long p0 = h->jac_colptr[(size_t)Pr.kc0 * P.z], p1 = h->jac_colptr[(size_t)Pr.kc1 * P.z];
+                CUDA_TRY(h, cudaMemcpyAsync(jac + p0, h->djac + p0, sizeof(double) * (p1 - p0), cudaMemcpyDeviceToHost, h->copy_stream));
+            }
+            if (hess) {
+                const long long p0 = hess_knot_base(P, Pr.kc0), p1 = hess_knot_base(P, std::min(Pr.kc1, P.nOwn));
+                CUDA_TRY(h, cudaMemcpyAsync(hess + p0, h->dhess + p0, sizeof(double) * (p1 - p0), cudaMemcpyDeviceToHost, h->copy_stream));
+            }
+        }
+        CUDA_TRY(h, cudaGetLastError());
     }
-    int rc = run_eval(h, h->dZ, sigma, h->dmu, J ? h->dJ : nullptr, grad ? h->dgrad : nullptr, g ? h->dg : nullptr,
-                      jac ? h->djac : nullptr, hess ? h->dhess : nullptr);
-    if (rc != DTO_OK) return rc;
     if (J) CUDA_TRY(h, cudaMemcpyAsync(J, h->dJ, sizeof(double) * B, cudaMemcpyDeviceToHost, h->stream));
     if (grad) CUDA_TRY(h, cudaMemcpyAsync(grad, h->dgrad, sizeof(double) * B * P.nOwn * P.z, cudaMemcpyDeviceToHost, h->stream));
     if (g) CUDA_TRY(h, cudaMemcpyAsync(g, h->dg, sizeof(double) * B * P.n_cons_local, cudaMemcpyDeviceToHost, h->stream));
-    if (jac) CUDA_TRY(h, cudaMemcpyAsync(jac, h->djac, sizeof(double) * B * P.nnz_jac_local, cudaMemcpyDeviceToHost, h->stream));
-    if (hess) CUDA_TRY(h, cudaMemcpyAsync(hess, h->dhess, sizeof(double) * B * P.nnz_hess_local, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (pipelined) CUDA_TRY(h, cudaStreamSynchronize(h->copy_stream));
     return DTO_OK;
 }
 

@@ -39,6 +39,7 @@ struct DObj {
     const int* own_ti;        // owned entries -> index into params/Qs (original position in `times`)
     const int* own_knot;      // owned entries -> local knot (0-based)
     int nt_own;
+    int own_kmin, own_kmax;   // smallest / largest owned local knot (host-side launch pruning)
     const int* knot_to_own;   // [local knots] -> owned entry index or -1
     const double* R;
     const double* baseline;   // nv x N (global knots), may be null
@@ -64,6 +65,7 @@ struct DProb {
     int nK;         // local knots including the right halo knot (if any)
     int nOwn;       // owned knots
     int nI;         // local intervals (owned knots that have a successor)
+    int kc0, kc1;   // active local-knot range of this launch [kc0, kc1): intervals kc0 <= k < min(kc1, nI), owned knots kc0 <= k < min(kc1, nOwn)
     int first_has_cross;  // shard does not start at knot 1: its first knot still owns a cross block
     int any_cross;        // some integrator produces cross-knot Hessian entries (tdbilinear order 1)
     int n_int, n_obj, n_con;
@@ -113,6 +115,7 @@ bool tdb_fits(const DInt& I);
 void launch_tdb(const DProb& P, int ii, const double* Z, const double* mu, double* g, double* jac, EvalFlags f, cudaStream_t st,
                 long long* launches);
 void launch_analytic(const DProb& P, const double* Z, double* g, double* jac, EvalFlags f, cudaStream_t st, long long* launches);
+void launch_constraints(const DProb& P, const double* Z, double* g, double* jac, EvalFlags f, cudaStream_t st, long long* launches);
 void launch_hessian_assemble(const DProb& P, const double* Z, double sigma, const double* mu, double* hess, cudaStream_t st,
                              long long* launches);
 void launch_objective(const DProb& P, const double* Z, double* J, double* grad, double* partials, cudaStream_t st,

@@ -211,3 +211,26 @@ def test_tdbilinear_matches_exact_variational_solution(order, n, m, carriers):
         cross = (hr - 1) // z != (hc - 1) // z
         assert np.abs(Href[cross]).max() > 1e-6
     ev.close()
+
+
+def test_host_pipeline_matches_single_pass(monkeypatch):
+    """dto_eval_all with host buffers cuts large problems into knot ranges whose Jacobian columns and Hessian
+    blocks leave over PCIe while later ranges are computed; the result must be bit-identical to the
+    single-pass evaluation, whatever the chunk plan (and with knot constraints + a derivative integrator)."""
+    prob = pt.scaled_problem(N=700, state_dim=32, n_controls=2, generator_scale=0.3)
+    Z = prob.trajectory.datavec.copy()
+    outs = {}
+    for plan in ("0", "0.12,0.55", "0.05,0.2,0.5,0.9"):
+        monkeypatch.setenv("DTO_B200_PIPELINE", plan)
+        ev = dto.Evaluator(prob)
+        mu = np.random.default_rng(5).random(ev.n_constraints)
+        bufs = [np.full(1, np.nan), np.full(ev.n_vars, np.nan), np.full(ev.n_constraints, np.nan),
+                np.full(ev.nnz_jacobian, np.nan), np.full(ev.nnz_hessian, np.nan)]
+        ev.eval_all(Z, 1.7, mu, *bufs)
+        assert all(np.isfinite(b).all() for b in bufs), plan
+        outs[plan] = bufs
+        ev.close()
+    ref = outs["0"]
+    for plan, got in outs.items():
+        for a, b in zip(ref, got):
+            assert np.array_equal(np.asarray(a), np.asarray(b)), plan
