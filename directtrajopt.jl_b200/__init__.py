@@ -11,7 +11,7 @@ from . import _lib
 from ._lib import DtoError
 from .components import (AbstractIntegrator, AbstractNonlinearConstraint, AbstractObjective, BilinearIntegrator,
                          CarrierGenerator, CompositeObjective, DerivativeIntegrator, IsoInfidelity, KnotFunction,
-                         KnotPointObjective, LinearCost, LinearMap, MinimumTimeObjective, NonlinearKnotPointConstraint,
+                         KnotPointObjective, LinearCost, LinearMap, LinearRegularizer, MinimumTimeObjective, NonlinearKnotPointConstraint,
                          NormMinus, NormSqMinus, NormSqPlus, NullObjective, QuadraticRegularizer, SqDist, SqDistMinus,
                          TerminalObjective, TimeDependentBilinearIntegrator, UnsupportedComponent)
 from .evaluator import DirectTrajOptProblem, Evaluator

@@ -12,7 +12,7 @@ DTO_OK, DTO_ERR_INVALID, DTO_ERR_UNSUPPORTED, DTO_ERR_CUDA, DTO_ERR_ALLOC = 0, -
 ABI_VERSION = 1
 
 INT_BILINEAR, INT_DERIVATIVE, INT_TDBILINEAR = 1, 2, 3
-OBJ_QUADREG, OBJ_MINTIME, OBJ_KNOT, OBJ_NULL = 1, 2, 3, 4
+OBJ_QUADREG, OBJ_MINTIME, OBJ_KNOT, OBJ_NULL, OBJ_LINREG = 1, 2, 3, 4, 5
 G_FUNCS = {"norm_minus_c": 1, "normsq_minus_c": 2, "sqdist_minus_c": 3, "linear": 4}
 L_FUNCS = {"normsq_plus_p": 1, "sqdist": 2, "linear": 3, "iso_infidelity": 4}
 

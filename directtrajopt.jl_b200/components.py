@@ -252,6 +252,21 @@ class QuadraticRegularizer(AbstractObjective):
         return {"kind": "quadreg", "name": self.name, "R": self.R, "baseline": self.baseline, "times": self.times}
 
 
+class LinearRegularizer(AbstractObjective):
+    """``LinearRegularizer(name, traj, R; times)``: J = sum_t dt_t R'v_t   (regularizers.jl:207-313)."""
+
+    def __init__(self, name, traj, R, times=None):
+        d = traj.dims[name]
+        self.name = name
+        self.R = np.full(d, float(R)) if np.isscalar(R) else np.asarray(R, float)
+        if self.R.shape != (d,):
+            raise ValueError("length(R) must equal the component dimension")
+        self.times = list(range(1, traj.N + 1)) if times is None else [int(t) for t in times]
+
+    def to_spec(self, traj):
+        return {"kind": "linreg", "name": self.name, "R": self.R, "times": self.times}
+
+
 class MinimumTimeObjective(AbstractObjective):
     """``MinimumTimeObjective(traj; D=1.0)``: J = D sum_{k<N} dt_k (minimum_time_objective.jl:24-49)."""
 

@@ -259,6 +259,15 @@ __global__ void hessian_assemble_kernel(DProb P, const double* __restrict__ Z, d
                 }
                 __syncwarp();
             }
+            if (O.kind == DTO_OBJ_LINREG) {
+                // d2J/(dv ddt) = R, written at (row v, col dt) only (regularizers.jl:287-313): kept iff v precedes dt
+                if (O.knot_to_own[kl] >= 0)
+                    for (int a = tid; a < O.nv; a += nt) {
+                        const int va = O.var_offs[a];
+                        if (va < P.dt_off) diag[va * z + P.dt_off] += sigma * O.weight * O.R[a];
+                    }
+                __syncwarp();
+            }
             // knot objectives are added by knot_objective_hessian_kernel (one thread per hyper-dual pair)
         }
     }
@@ -357,6 +366,23 @@ __global__ void objective_kernel(DProb P, const double* __restrict__ Z, double* 
                 if (tid == 0) {
                     Jk += O.weight * 0.5 * dt * dt * q;
                     gz[P.dt_off] += O.weight * q * dt;
+                }
+            }
+            __syncwarp();
+        } else if (O.kind == DTO_OBJ_LINREG) {
+            // J = sum_t dt_t R'v_t (regularizers.jl:241-270)
+            if (O.knot_to_own[kl] >= 0) {
+                const double dt = zk[P.dt_off];
+                double part = 0.0;
+                for (int a = tid; a < O.nv; a += nt) {
+                    gz[O.var_offs[a]] += O.weight * dt * O.R[a];
+                    part += O.R[a] * zk[O.var_offs[a]];
+                }
+                const double q = warp_sum(part);
+                __syncwarp();
+                if (tid == 0) {
+                    Jk += O.weight * dt * q;
+                    gz[P.dt_off] += O.weight * q;
                 }
             }
             __syncwarp();

@@ -263,7 +263,7 @@ extern "C" int dto_create(const dto_problem_desc* d, dto_handle** out) {
         O.np = s.n_params;
         O.D = s.D;
         if (s.kind == DTO_OBJ_MINTIME || s.kind == DTO_OBJ_NULL) continue;
-        if (s.kind != DTO_OBJ_QUADREG && s.kind != DTO_OBJ_KNOT) return fail_create(h, DTO_ERR_UNSUPPORTED, "unknown objective kind");
+        if (s.kind != DTO_OBJ_QUADREG && s.kind != DTO_OBJ_KNOT && s.kind != DTO_OBJ_LINREG) return fail_create(h, DTO_ERR_UNSUPPORTED, "unknown objective kind");
         if (s.kind == DTO_OBJ_KNOT && !knot_lfun_known(s.fn)) return fail_create(h, DTO_ERR_UNSUPPORTED, "knot objective function is not in the device catalogue");
         if (s.n_vars < 1 || s.n_vars > DTO_MAX_KNOTFN_VARS || !s.var_offs) return fail_create(h, DTO_ERR_INVALID, "objective: bad variable list");
         for (int v = 0; v < s.n_vars; ++v) {
@@ -289,10 +289,12 @@ extern "C" int dto_create(const dto_problem_desc* d, dto_handle** out) {
         O.own_kmin = ownk.empty() ? 0 : *std::min_element(ownk.begin(), ownk.end());
         O.own_kmax = ownk.empty() ? -1 : *std::max_element(ownk.begin(), ownk.end());
         O.knot_to_own = dev_upload(h, k2o.data(), k2o.size());
-        if (s.kind == DTO_OBJ_QUADREG) {
-            if (!s.R) return fail_create(h, DTO_ERR_INVALID, "quadratic regularizer: missing R");
+        if (s.kind == DTO_OBJ_QUADREG || s.kind == DTO_OBJ_LINREG) {
+            if (!s.R) return fail_create(h, DTO_ERR_INVALID, "regularizer: missing R");
+            for (int v = 0; v < s.n_vars; ++v)
+                if (s.var_offs[v] == d->dt_off) return fail_create(h, DTO_ERR_UNSUPPORTED, "regularizer on the timestep component itself is not supported");
             O.R = dev_upload(h, s.R, s.n_vars);
-            O.baseline = s.baseline ? dev_upload(h, s.baseline, (size_t)s.n_vars * N) : nullptr;
+            O.baseline = (s.kind == DTO_OBJ_QUADREG && s.baseline) ? dev_upload(h, s.baseline, (size_t)s.n_vars * N) : nullptr;
         } else {
             if (!s.Qs || (s.n_params > 0 && !s.params)) return fail_create(h, DTO_ERR_INVALID, "knot objective: missing Qs/params");
             O.params = dev_upload(h, s.params, (size_t)std::max(1, s.n_params) * s.n_times);

@@ -12,7 +12,7 @@ import numpy as np
 from . import _lib
 from .components import (AbstractIntegrator, AbstractNonlinearConstraint, AbstractObjective, BilinearIntegrator,
                          CompositeObjective, DerivativeIntegrator, KnotPointObjective, MinimumTimeObjective, NullObjective,
-                         QuadraticRegularizer, TimeDependentBilinearIntegrator, UnsupportedComponent)
+                         LinearRegularizer, QuadraticRegularizer, TimeDependentBilinearIntegrator, UnsupportedComponent)
 
 
 class DirectTrajOptProblem:
@@ -137,6 +137,13 @@ class Evaluator:
                 keep += [vo, tm, R, base]
                 d.n_vars, d.var_offs, d.n_times, d.times, d.R = len(vo), _ip(vo), len(tm), _ip(tm), _dp(R)
                 d.baseline = _dp(base) if np.any(base) else None
+            elif isinstance(ob, LinearRegularizer):
+                d.kind = _lib.OBJ_LINREG
+                vo = np.asarray(list(t.components[ob.name]), dtype=np.int32)
+                tm = np.asarray(ob.times, dtype=np.int32)
+                R = _f64(ob.R)
+                keep += [vo, tm, R]
+                d.n_vars, d.var_offs, d.n_times, d.times, d.R = len(vo), _ip(vo), len(tm), _ip(tm), _dp(R)
             elif isinstance(ob, MinimumTimeObjective):
                 d.kind = _lib.OBJ_MINTIME
                 d.D = ob.D

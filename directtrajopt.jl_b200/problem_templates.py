@@ -4,6 +4,7 @@ built through this package's mirror of the reference API with synthetic (seeded 
   readme_problem            README.md:68-95 (BASELINE config c1)
   standard_problem          test/test_snippets.jl:27-54 + test/test_utils.jl:113-178 (evaluator test problem)
   evaluator_test_problem    src/solvers/evaluator.jl:656-684
+  linear_regularizer_problem  standard problem + LinearRegularizer terms (src/objectives/regularizers.jl:207-313)
   bilinear_benchmark        benchmark/problem_utils.jl:10-42  (published micro-benchmark shape, N=51)
   scaled_problem            benchmark/problem_utils.jl:49-77  (BASELINE config c5 shape, c4 shape)
   quantum_gate_problem      BASELINE config c2: isomorphic state dim 32, 4 drives, free dt + MinimumTime
@@ -13,7 +14,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from .components import (BilinearIntegrator, CarrierGenerator, DerivativeIntegrator, MinimumTimeObjective,
+from .components import (BilinearIntegrator, CarrierGenerator, DerivativeIntegrator, LinearRegularizer, MinimumTimeObjective,
                          NonlinearKnotPointConstraint, NormMinus, QuadraticRegularizer, SqDist, TerminalObjective,
                          TimeDependentBilinearIntegrator)
 from .evaluator import DirectTrajOptProblem
@@ -62,6 +63,18 @@ def standard_problem(N=10, seed=0):
     J = J + MinimumTimeObjective(traj)
     g_u_norm = NonlinearKnotPointConstraint(NormMinus(1.0), "u", traj, times=range(2, traj.N), equality=False)
     return DirectTrajOptProblem(traj, J, integrators, constraints=[g_u_norm])
+
+
+def linear_regularizer_problem(N=8, seed=1):
+    """The standard problem with LinearRegularizer terms (regularizers.jl:207-313): vector R, a subset of
+    times, a scaled term inside the composite."""
+    G, traj = bilinear_dynamics_and_trajectory(N=N, seed=seed)
+    integrators = [BilinearIntegrator(G, "x", "u", traj), DerivativeIntegrator("u", "du", traj), DerivativeIntegrator("du", "ddu", traj)]
+    J = TerminalObjective(SqDist(traj.goal["x"]), "x", traj)
+    J = J + LinearRegularizer("u", traj, [0.3, -0.7])
+    J = J + 2.5 * LinearRegularizer("ddu", traj, 0.4, times=[1, 3, N])
+    J = J + QuadraticRegularizer("du", traj, 1.0)
+    return DirectTrajOptProblem(traj, J, integrators)
 
 
 def evaluator_test_problem(N=10, seed=0):

@@ -62,7 +62,7 @@ typedef enum {
 /* integrator kinds (src/integrators/) */
 enum { DTO_INT_BILINEAR = 1, DTO_INT_DERIVATIVE = 2, DTO_INT_TDBILINEAR = 3 };
 /* objective kinds (src/objectives/) */
-enum { DTO_OBJ_QUADREG = 1, DTO_OBJ_MINTIME = 2, DTO_OBJ_KNOT = 3, DTO_OBJ_NULL = 4 };
+enum { DTO_OBJ_QUADREG = 1, DTO_OBJ_MINTIME = 2, DTO_OBJ_KNOT = 3, DTO_OBJ_NULL = 4, DTO_OBJ_LINREG = 5 };
 /* device catalogue of knot constraint functions g(v; p) (replaces the Julia closure of
  * src/constraints/nonlinear/knot_point_constraint.jl:76-83) */
 enum { DTO_G_NORM_MINUS_C = 1, DTO_G_NORMSQ_MINUS_C = 2, DTO_G_SQDIST_MINUS_C = 3, DTO_G_LINEAR = 4 };
@@ -105,7 +105,8 @@ typedef struct {
     int32_t n_times;
     const int32_t* var_offs; /* 0-based positions inside a knot of the variables the term reads */
     const int32_t* times;    /* 1-based knots (quadreg: `times`; knot: `times`) */
-    const double* R;         /* quadreg: n_vars diagonal weights (src/objectives/regularizers.jl:38-43) */
+    const double* R;         /* quadreg: n_vars diagonal weights (src/objectives/regularizers.jl:38-43);
+                              * linreg: n_vars linear weights, J = sum_t dt_t R'v_t (regularizers.jl:207-313) */
     const double* baseline;  /* quadreg: n_vars x N column-major, may be NULL (= zeros) */
     double D;                /* mintime scale (src/objectives/minimum_time_objective.jl:24-26) */
     int32_t n_params;        /* knot: doubles of parameters per listed time */

@@ -118,6 +118,10 @@ function B200Evaluator(prob; eval_hessian = true, knot_functions = Dict())
             append!(keep, (vo, tm, R, base))
             push!(objs, ObjectiveDesc(1, 0, w, length(vo), length(tm), pointer(vo), pointer(tm), pointer(R),
                                       any(!iszero, base) ? pointer(base) : C_NULL, 0.0, 0, 0, C_NULL, C_NULL))
+        elseif ob isa LinearRegularizer
+            vo = Cint.(collect(traj.components[ob.name]) .- 1); tm = Cint.(ob.times); R = copy(ob.R)
+            append!(keep, (vo, tm, R))
+            push!(objs, ObjectiveDesc(5, 0, w, length(vo), length(tm), pointer(vo), pointer(tm), pointer(R), C_NULL, 0.0, 0, 0, C_NULL, C_NULL))
         elseif ob isa MinimumTimeObjective
             push!(objs, ObjectiveDesc(2, 0, w, 0, 0, C_NULL, C_NULL, C_NULL, C_NULL, ob.D, 0, 0, C_NULL, C_NULL))
         elseif ob isa KnotPointObjective

@@ -447,6 +447,14 @@ def objective_hessian_pattern(spec, ob):
             rr, cc = np.meshgrid(vi, vi, indexing="ij")
             rows += [rr.ravel(), vi, [di]]
             cols += [cc.ravel(), np.full(vi.size, di), [di]]
+    elif ob["kind"] == "linreg":
+        # only the cross terms d2J/(dv ddt), marked at (v, dt)  (regularizers.jl:272-292)
+        vc = comp_range(spec, ob["name"])
+        dto = dt_offset(spec)
+        for k in ob["times"]:
+            vi = knot_slice(k, vc, z)
+            rows.append(vi)
+            cols.append(np.full(vi.size, (k - 1) * z + dto))
     elif ob["kind"] == "knot":
         comps = _vars_of(spec, ob["names"])
         for k in ob["times"]:
@@ -530,6 +538,22 @@ def _objective_term(spec, ob, Z, want_grad, want_hess):
                 hr.append(di)
                 hc.append(di)
                 hv.append(dv @ (R * dv))
+    elif ob["kind"] == "linreg":
+        # J = sum_t dt_t R'v_t; gradient R dt / R'v; Hessian (v, dt) = R  (regularizers.jl:241-313)
+        vc = comp_range(spec, ob["name"])
+        dto = dt_offset(spec)
+        R = np.asarray(ob["R"], float)
+        for k in ob["times"]:
+            vi = knot_slice(k, vc, z)
+            di = (k - 1) * z + dto
+            J += Z[di] * (R @ Z[vi])
+            if want_grad:
+                g[vi] += R * Z[di]
+                g[di] += R @ Z[vi]
+            if want_hess:
+                hr += list(vi)
+                hc += [di] * vi.size
+                hv += list(R)
     elif ob["kind"] == "mintime":
         dto = dt_offset(spec)
         idx = np.arange(N - 1) * z + dto
@@ -691,7 +715,7 @@ def objective_by_knot(spec, Z):
     out = np.zeros(N)
     for ob in spec["objectives"]:
         w = ob.get("weight", 1.0)
-        if ob["kind"] in ("quadreg", "knot"):
+        if ob["kind"] in ("quadreg", "knot", "linreg"):
             for i, k in enumerate(ob["times"]):
                 one = dict(ob)
                 one["times"] = [k]

@@ -32,6 +32,7 @@ PROBLEMS = {
     "evaluator_test": lambda: pt.evaluator_test_problem(N=5),
     "scaled": lambda: pt.scaled_problem(N=4, state_dim=5, n_controls=2, generator_scale=0.7),
     "gate": lambda: pt.quantum_gate_problem(N=4, levels=3, n_drives=2),
+    "linreg": lambda: pt.linear_regularizer_problem(N=5),
 }
 
 

@@ -58,6 +58,7 @@ PROBLEMS = {
     "gate_n32": lambda: pt.quantum_gate_problem(N=12, levels=16, n_drives=4),
     "gate_n6": lambda: pt.quantum_gate_problem(N=7, levels=3, n_drives=2),
     "gate_n64": lambda: pt.quantum_gate_problem(N=5, levels=32, n_drives=2),
+    "linreg": lambda: pt.linear_regularizer_problem(N=8),
 }
 
 
