@@ -55,6 +55,19 @@ def canonical_flops_per_interval(n, m, T=TAYLOR_T, s=0):
     return i + ii + iii
 
 
+def recorded_traffic(workload, variant):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the committed
+    `ncu --set full` capture of this workload and kernel variant (profiles/); None when no capture matches."""
+    path = os.path.join(ROOT, "profiles", f"r01_ncu_summary_{workload}.json")
+    try:
+        full = json.load(open(path))["k1_ncu_set_full"]
+        if variant in full["kernel"]:
+            return float(full["dram_bytes_per_launch"]), os.path.relpath(path, ROOT)
+    except Exception:
+        pass
+    return None, None
+
+
 def build_problem(workload, seed):
     import dto_b200 as dto
 
@@ -293,6 +306,7 @@ def main():
                                 "batch_split": batch_local * (t.N - 1)}[mode]
         flops_launch = canonical_flops_per_interval(n, m) * intervals_per_launch
         achieved = flops_launch / (k1_avg_ms * 1e-3) * 1e-12
+        traffic, traffic_src = recorded_traffic(args.workload, ev.kernel_variant(0)) if world == 1 or mode == "replicas" else (None, None)
         line = {
             "metric": "full NLP evals/sec (constraint+Jacobian+Hessian)", "value": value, "unit": "evals/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
@@ -307,6 +321,7 @@ def main():
                 "l2": "256 MB memset between timed steps (outside the per-step CUDA events)",
                 "step": "objective+gradient+constraint+Jacobian+Hessian of one iterate, outputs left in HBM",
                 "kernel_variant": ev.kernel_variant(0),
+                "e2e_path": "dto_eval_all with pinned host buffers; knot-range pipeline (D2H of finished ranges overlaps the next range) unless DTO_B200_PIPELINE=0",
             },
             "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_s_max / args.steps * 1e3, "matches_device_path": same},
@@ -314,7 +329,8 @@ def main():
             "clocks": sampler.summary(),
             "roofline": {
                 "bound": "tensor", "achieved": achieved, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": achieved / FP64_PEAK_TFLOPS,
-                "traffic": None, "kernel": "bilinear interval kernel (K1)", "kernel_ms": k1_avg_ms,
+                "traffic": traffic, "traffic_unit": "bytes per launch (dram read + write, ncu --set full)", "traffic_source": traffic_src,
+                "kernel": "bilinear interval kernel (K1)", "kernel_ms": k1_avg_ms,
                 "kernel_share_of_step": k1_avg_ms * max(1, sum(1 for i in prob.integrators if type(i).__name__ != "DerivativeIntegrator")) / (dev_ms_max / args.steps),
                 "algorithmic_flops_per_launch": flops_launch,
                 "peak_source": "FP64 DMMA m8n8k4 saturation measured on this pool (profiles/r01_fp64_peaks_and_box_probe.log); "
