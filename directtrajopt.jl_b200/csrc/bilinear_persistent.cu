@@ -47,6 +47,42 @@ __constant__ double kInvFact[64] = {
     1.4064725544496498e-75, 2.4674957095607893e-77, 4.254302947518602e-79, 7.2106829618959365e-81,
     1.2017804936493226e-82, 1.9701319568021682e-84, 3.1776321883905942e-86, 5.043860616493007e-88};
 
+// kTermThr[T] = (2^-56 T!)^(1/T): theta <= kTermThr[T]  <=>  theta^T / T! <= 2^-56;  kInv[t] = 1/t
+__constant__ double kTermThr[64] = {
+    0.0, 1.3877787807814457e-17, 5.268356063861754e-09, 4.366738290990188e-06,
+    0.00013509300777591815, 0.0011073892359697531, 0.004640970307744105, 0.013203184215395689,
+    0.029408989058618194, 0.05554895835340545, 0.09337020827678473, 0.14404487618659187,
+    0.20823549866087968, 0.2861946964536857, 0.3778659482136564, 0.4829712994609099,
+    0.6010820235361274, 0.7316729269701641, 0.8741627421291117, 1.0279434021622011,
+    1.1924007567545727, 1.366928857608371, 1.5509394972483046, 1.7438682928017233,
+    1.9451782866329281, 2.1543617854833412, 2.3709409688061474, 2.594467653547391,
+    2.8245224960110504, 3.060713832769101, 3.3026763048201806, 3.5500693669735828,
+    3.802575753674299, 4.059899950157507, 4.3217667016810974, 4.5879195819761005,
+    4.858119633758812, 5.132144088270396, 5.409785166693326, 5.690848963457876,
+    5.975154409543074, 6.262532312636557, 6.552824470257129, 6.845882851524014,
+    7.141568843076471, 7.43975255463284, 7.740312179775477, 8.043133407718637,
+    8.348108882032204, 8.65513770253534, 8.964124966826535, 9.27498134817052,
+    9.587622706711219, 9.901969731219332, 10.217947608810235, 10.535485720281251,
+    10.854517358916425, 11.174979470791282, 11.49681241478032, 11.819959740626354,
+    12.144367983574272, 12.46998647420296, 12.796767162208864, 13.124664453003925};
+__constant__ double kInv[64] = {
+    0.0, 1.0, 0.5, 0.3333333333333333,
+    0.25, 0.2, 0.16666666666666666, 0.14285714285714285,
+    0.125, 0.1111111111111111, 0.1, 0.09090909090909091,
+    0.08333333333333333, 0.07692307692307693, 0.07142857142857142, 0.06666666666666667,
+    0.0625, 0.058823529411764705, 0.05555555555555555, 0.05263157894736842,
+    0.05, 0.047619047619047616, 0.045454545454545456, 0.043478260869565216,
+    0.041666666666666664, 0.04, 0.038461538461538464, 0.037037037037037035,
+    0.03571428571428571, 0.034482758620689655, 0.03333333333333333, 0.03225806451612903,
+    0.03125, 0.030303030303030304, 0.029411764705882353, 0.02857142857142857,
+    0.027777777777777776, 0.02702702702702703, 0.02631578947368421, 0.02564102564102564,
+    0.025, 0.024390243902439025, 0.023809523809523808, 0.023255813953488372,
+    0.022727272727272728, 0.022222222222222223, 0.021739130434782608, 0.02127659574468085,
+    0.020833333333333332, 0.02040816326530612, 0.02, 0.0196078431372549,
+    0.019230769230769232, 0.018867924528301886, 0.018518518518518517, 0.01818181818181818,
+    0.017857142857142856, 0.017543859649122806, 0.017241379310344827, 0.01694915254237288,
+    0.016666666666666666, 0.01639344262295082, 0.016129032258064516, 0.015873015873015872};
+
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
@@ -105,24 +141,30 @@ __device__ __forceinline__ void frag_zero(double (&f)[MT][NT][2]) {
 
 struct Series {
     int stages, terms;
+    double inv_stages;
 };
 
 // number of Taylor terms T with theta^T / T! <= 2^-56
 __device__ __forceinline__ int taylor_terms(double ths) {
-    double term = ths;
-    int T = 1;
-    while (term > 1.3877787807814457e-17 && T < 60) {
-        ++T;
-        term *= ths / T;
+    // smallest T in [1, 60] with ths <= kTermThr[T] (the table is increasing): binary search, no divisions
+    int lo = 1, hi = 60;
+#pragma unroll
+    for (int it = 0; it < 6; ++it) {
+        const int mid = (lo + hi) >> 1;
+        if (ths <= kTermThr[mid]) hi = mid;
+        else lo = mid + 1;
     }
-    return T;
+    return hi;
 }
 
 __device__ __forceinline__ Series choose_series(double theta) {
-    Series s{1, 2};
+    Series s{1, 2, 1.0};
     if (theta < 1e8) {
-        s.stages = theta > 4.0 ? (int)ceil(theta * 0.25) : 1;  // one stage up to ||dt G||_1 = 4 (e^4 round-off amplification)
-        s.terms = taylor_terms(theta / s.stages) + 2;           // +2: the derivative rows lag the value row
+        if (theta > 4.0) {  // one stage up to ||dt G||_1 = 4 (e^4 round-off amplification)
+            s.stages = (int)ceil(theta * 0.25);
+            s.inv_stages = 1.0 / (double)s.stages;
+        }
+        s.terms = taylor_terms(theta * s.inv_stages) + 2;  // +2: the derivative rows lag the value row
     }
     return s;
 }
@@ -207,7 +249,7 @@ __device__ __forceinline__ void role_forward(const Ctx<NT>& c, int b, int kk, co
                 term[mt][nt][1] = F[mt][nt][1];
             }
         for (int t = 1; t <= ser.terms; ++t) {
-            const double cf = dt / ((double)t * (double)ser.stages);
+            const double cf = dt * ser.inv_stages * kInv[t];
             double nw[MT][NT][2];
             frag_zero(nw);
             mma_apply<MT, NT, MT>(nw, term, Gu, lane);
@@ -381,7 +423,7 @@ __device__ __forceinline__ void role_exp_series(const Ctx<NT>& c, int b, int kk)
                     term[mt][nt][1] = F[mt][nt][1];
                 }
             for (int t = 1; t <= ser.terms - 2; ++t) {  // value series only
-                const double cf = dt / ((double)t * (double)ser.stages);
+                const double cf = dt * ser.inv_stages * kInv[t];
                 double nw[MT][NT][2];
                 frag_zero(nw);
                 mma_apply<MT, NT, MT>(nw, term, c.Gu, lane);
@@ -679,7 +721,7 @@ __device__ __forceinline__ void role_adjoint(const Ctx<NT>& c, int b, int kk) {
             term[0][nt][1] = F[0][nt][1];
         }
         for (int t = 1; t <= ser.terms; ++t) {
-            const double cf = dt / ((double)t * (double)ser.stages);
+            const double cf = dt * ser.inv_stages * kInv[t];
             // y_i = G_i' a on the FP64 pipe: lane s reads column s of G_i (row-major rows, conflict-free)
             if (row8 == 0) {
 #pragma unroll
@@ -749,10 +791,17 @@ __device__ __forceinline__ void role_adjoint(const Ctx<NT>& c, int b, int kk) {
 // ------------------------------------------------------------------------------------------------------------------
 // the persistent kernel
 // ------------------------------------------------------------------------------------------------------------------
+// warps per CTA the register file allows: 24 x 80 registers at n = 8, 16 x 128 at n = 16, 12 x 168 above
+template <int NT>
+constexpr int max_warps() {
+    return NT == 1 ? 24 : (NT == 2 ? 16 : kMaxWarps);
+}
+
 template <int NT, int MT>
-__global__ void __launch_bounds__(kMaxWarps * 32, 1)
+__global__ void __launch_bounds__(max_warps<NT>() * 32, 1)
     bilinear_persistent_kernel(DProb P, int ii, const double* __restrict__ Z, const double* __restrict__ mu, double* __restrict__ g,
-                               double* __restrict__ jac, int want_jac, int want_hess, unsigned long long* __restrict__ wq, int nE) {
+                               double* __restrict__ jac, int want_jac, int want_hess, unsigned long long* __restrict__ wq, int nE,
+                               int fetch) {
     extern __shared__ __align__(16) double sm[];
     constexpr int n = 8 * NT, nn = n * n;
     const DInt& I = P.in[ii];
@@ -832,10 +881,11 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1)
     for (int ri = 0; ri < nroles; ++ri) {
         const int role = order[ri];
         while (true) {
-            unsigned long long id = 0;
-            if (lane == 0) id = atomicAdd(&wq[role], 1ULL);
-            id = __shfl_sync(0xffffffffu, id, 0);
-            if (id >= nItems) break;
+            unsigned long long id0 = 0;
+            if (lane == 0) id0 = atomicAdd(&wq[role], (unsigned long long)fetch);  // `fetch` consecutive items per round trip
+            id0 = __shfl_sync(0xffffffffu, id0, 0);
+            if (id0 >= nItems) break;
+            for (unsigned long long id = id0; id < id0 + fetch && id < nItems; ++id) {
             const int b = (int)(id / (unsigned long long)nIc), kk = P.kc0 + (int)(id % (unsigned long long)nIc);
             __syncwarp();
 #ifndef DTO_SKIP_FWD
@@ -851,6 +901,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1)
             if (role == ROLE_EXP && !ps) role_exp_series<NT, (NT <= 2 ? 2 : 1)>(c, b, kk);
 #endif
             __syncwarp();
+            }
         }
     }
 }
@@ -870,7 +921,7 @@ bool launch_variant(const DProb& P, int ii, const double* Z, const double* mu, d
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     // warps per CTA and how many of them carry the two spare matrices: prefer full occupancy, then
     // one Paterson-Stockmeyer warp per three
-    int W = (int)std::min<size_t>(kMaxWarps, (budget - shared_part) / slot);
+    int W = (int)std::min<size_t>(max_warps<NT>(), (budget - shared_part) / slot);
     int nE = 0;
     if (f.want_jac) {
         int bestW = W, bestE = 0;
@@ -902,7 +953,10 @@ bool launch_variant(const DProb& P, int ii, const double* Z, const double* mu, d
     const long long want_ctas = (items * roles + W - 1) / W;
     const int grid = (int)std::max<long long>(1, std::min<long long>(sms, want_ctas));
     if (cudaMemsetAsync(I.wq, 0, 3 * sizeof(unsigned long long), st) != cudaSuccess) return false;
-    kern<<<grid, W * 32, smem, st>>>(P, ii, Z, mu, f.want_g ? g : nullptr, jac, f.want_jac ? 1 : 0, f.want_hess ? 1 : 0, I.wq, nE);
+    // small items (n <= 16) are fetched several at a time: the atomic's round trip is as long as the item itself
+    const long long per_warp = items / ((long long)grid * W);
+    const int fetch = (NT <= 2) ? (int)std::max<long long>(1, std::min<long long>(8, per_warp / 8)) : 1;
+    kern<<<grid, W * 32, smem, st>>>(P, ii, Z, mu, f.want_g ? g : nullptr, jac, f.want_jac ? 1 : 0, f.want_hess ? 1 : 0, I.wq, nE, fetch);
     ++*launches;
     return true;
 }

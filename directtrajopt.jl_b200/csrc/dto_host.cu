@@ -226,9 +226,32 @@ extern "C" int dto_create(const dto_problem_desc* d, dto_handle** out) {
             I.D = dev_upload(h, s.D, nn * s.n_carrier);
             I.omega_d = dev_upload(h, s.omega_d, s.n_carrier);
             I.phi_d = dev_upload(h, s.phi_d, s.n_carrier);
+            if (s.x_dim % 8 == 0 && s.x_dim <= 64) {
+                // swizzled row-major copies for the tensor-core variant (layout of dmma_tiles.cuh)
+                const int nd = s.x_dim;
+                const bool swz = (nd / 8) % 2 == 0;
+                auto swizzled = [&](const double* src, int count) {
+                    std::vector<double> out((size_t)count * nn);
+                    for (int qm = 0; qm < count; ++qm)
+                        for (int r = 0; r < nd; ++r)
+                            for (int c = 0; c < nd; ++c)
+                                out[(size_t)qm * nn + (size_t)r * nd + (swz ? (c ^ ((r & 1) << 3)) : c)] = src[(size_t)qm * nn + (size_t)c * nd + r];
+                    return out;
+                };
+                I.Grm = dev_upload(h, swizzled(s.G, 1).data(), nn);
+                if (s.u_dim > 0) {
+                    I.Asw = dev_upload(h, swizzled(s.A, s.u_dim).data(), nn * s.u_dim);
+                    I.Bsw = dev_upload(h, swizzled(s.B, s.u_dim).data(), nn * s.u_dim);
+                }
+                if (s.n_carrier > 0) I.Dsw = dev_upload(h, swizzled(s.D, s.n_carrier).data(), nn * s.n_carrier);
+            }
             const int np = (s.spline_order == 1 ? 2 * s.u_dim : s.u_dim) + 2;
             I.hs_stride = np * s.x_dim + np * np;
             if (s.spline_order == 1) P.any_cross = 1;
+            {
+                const char* pin = getenv("DTO_B200_KERNEL");
+                I.variant = (I.Asw != nullptr && tdb_dmma_supported(I) && !(pin && strcmp(pin, "generic") == 0)) ? DTO_VAR_DMMA : DTO_VAR_GENERIC;
+            }
             if (!tdb_fits(I)) return fail_create(h, DTO_ERR_UNSUPPORTED, "tdbilinear integrator: too many drives/carriers or state too large for shared memory");
             if (s.x_dim > 96) return fail_create(h, DTO_ERR_UNSUPPORTED, "tdbilinear integrator: state dimension > 96 not supported");
         } else {
@@ -243,7 +266,7 @@ extern "C" int dto_create(const dto_problem_desc* d, dto_handle** out) {
         loff += (long long)s.x_dim * P.nI;
         doff += s.x_dim;
         h->variants.push_back(s.kind == DTO_INT_BILINEAR ? (I.variant == DTO_VAR_PERSISTENT ? "persistent" : I.variant == DTO_VAR_DMMA ? "dmma" : "generic")
-                                                         : (s.kind == DTO_INT_DERIVATIVE ? "analytic" : "rk"));
+                                                         : (s.kind == DTO_INT_DERIVATIVE ? "analytic" : (I.variant == DTO_VAR_DMMA ? "gbs-dmma" : "gbs")));
     }
     P.Dsum = doff;
     const long long n_dyn_global = goff, n_dyn_local = loff;
@@ -707,7 +730,9 @@ static void eval_range(dto_handle* h, const DProb& P, const double* dZ, double s
                 done = launch_bilinear_dmma(P, i, dZ, dmu, dg, djac, f, h->stream, &h->launches);
             if (!done) launch_bilinear_generic(P, i, dZ, dmu, dg, djac, f, h->stream, &h->launches);
         } else if (P.in[i].kind == DTO_INT_TDBILINEAR) {
-            launch_tdb(P, i, dZ, dmu, dg, djac, f, h->stream, &h->launches);
+            bool done = false;
+            if (P.in[i].variant == DTO_VAR_DMMA) done = launch_tdb_dmma(P, i, dZ, dmu, dg, djac, f, h->stream, &h->launches);
+            if (!done) launch_tdb(P, i, dZ, dmu, dg, djac, f, h->stream, &h->launches);
         }
         if (timed) cudaEventRecord(h->ev_pool[h->ev_used++].second, h->stream);
     }

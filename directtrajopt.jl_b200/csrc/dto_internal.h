@@ -26,6 +26,7 @@ struct DInt {
     const double* G;    // column-major matrices
     const double* Grm;  // bilinear: row-major copies of the same matrices
     const double *A, *B, *omega, *phi, *D, *omega_d, *phi_d;
+    const double *Asw, *Bsw, *Dsw;  // tdbilinear, DMMA variant: swizzled row-major copies (Grm holds G0)
     double* hs;         // [batch][n_intervals][hs_stride]
     unsigned long long* wq;  // bilinear, persistent variant: three work-queue counters (FWD, EXP, ADJ)
 };
@@ -111,6 +112,9 @@ bool launch_bilinear_persistent(const DProb& P, int ii, const double* Z, const d
                                 cudaStream_t st, long long* launches);
 bool bilinear_persistent_supported(int n, int m);
 bool tdb_available();
+bool tdb_dmma_supported(const DInt& I);
+bool launch_tdb_dmma(const DProb& P, int ii, const double* Z, const double* mu, double* g, double* jac, EvalFlags f, cudaStream_t st,
+                     long long* launches);
 bool tdb_fits(const DInt& I);
 void launch_tdb(const DProb& P, int ii, const double* Z, const double* mu, double* g, double* jac, EvalFlags f, cudaStream_t st,
                 long long* launches);

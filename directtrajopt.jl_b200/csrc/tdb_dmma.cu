@@ -1,0 +1,624 @@
+// K7 (DMMA variant): TimeDependentBilinearIntegrator interval kernel on the FP64 tensor pipe.
+//
+// Same mathematics as tdb.cu (Gragg-Bulirsch-Stoer extrapolation of the exact first/second-order
+// variational equations of  dPhi/dtau = dt G(u(tau), t_k + tau dt) Phi  for the carrier family
+//     G(u, t) = G0 + sum_i u_i (cos(w_i t + phi_i) A_i + sin(w_i t + phi_i) B_i) + sum_j cos(wd_j t + phd_j) D_j,
+// replacing solve(ODEProblem, Tsit5()) + ForwardDiff of
+// /root/reference/src/integrators/time_dependent_bilinear_integrator.jl:102-128,145-244), different mapping:
+//
+// One CTA per (problem, interval).  Every warp owns ONE 8-row tile of vectors for the whole integration and
+// keeps it in registers in tensor-core fragment layout (dmma_tiles.cuh): the modified-midpoint update
+// z_{q+1} = z_{q-1} + 2h f(z_q) is element-wise, and the C fragment of G(tau) * tile is already the A
+// fragment of the next right-hand side, so the vectors never touch shared memory:
+//   FWD tiles  [x; dx/dtheta_a; d2x/dtheta_a dtheta_b], theta = [u_k (m), u_{k+1} (m, order 1), dt, t_k]
+//   EXP tiles  columns of the identity -> Phi(1), the -Phi Jacobian block
+//   ADJ tile   [lambda; dlambda/dtheta_a] in reflected time through G' -> (dPhi/dtheta)' mu
+// Per right-hand side the CTA (1) assembles G(tau) and G(1 - tau)' in shared memory from the basis matrices
+// (swizzled row-major copies in global memory, L2-resident), (2) every warp multiplies its tile by it, the
+// basis products A_i, B_i, D_j times the leading forward tile (needed by the parameter couplings) are spread
+// over the lightly loaded warps, the transposed basis products of lambda run on the FP64 FMA pipe, (3) the
+// couplings are added from the shared tables.  Two block barriers per right-hand side.
+#include "dmma_tiles.cuh"
+#include "dto_internal.h"
+
+namespace {
+
+using namespace dmma_tiles;
+
+constexpr int kMaxM = 4;      // drives
+constexpr int kMaxC = 4;      // carriers
+constexpr int kMaxCols = 10;  // extrapolation columns
+constexpr int kMaxWarpsT = 16;  // 16 warps x 128 registers (the allocation granularity makes 13..16 warps cost the same)
+
+struct Scal {  // per-evaluation scalars at time tau
+    double dt, tau, w0, w1;
+    double u[kMaxM], c[kMaxM], s[kMaxM], om[kMaxM];
+    double e[kMaxC], es[kMaxC], omd[kMaxC];
+};
+
+struct Ctx {
+    int n, m, nc, order, np;
+};
+
+__device__ void make_scal(const DInt& I, const double* zk, const double* zk1, int dt_off, double tau, Scal& S) {
+    S.dt = zk[dt_off];
+    S.tau = tau;
+    const double t = zk[I.t_off] + tau * S.dt;
+    S.w0 = I.order == 1 ? 1.0 - tau : 1.0;
+    S.w1 = I.order == 1 ? tau : 0.0;
+    for (int i = 0; i < I.m; ++i) {
+        const double u0 = zk[I.u_off + i], u1 = I.order == 1 ? zk1[I.u_off + i] : u0;
+        S.u[i] = S.w0 * u0 + S.w1 * u1;
+        S.om[i] = I.omega[i];
+        sincos(I.omega[i] * t + I.phi[i], &S.s[i], &S.c[i]);
+    }
+    for (int j = 0; j < I.n_carrier; ++j) {
+        S.omd[j] = I.omega_d[j];
+        sincos(I.omega_d[j] * t + I.phi_d[j], &S.es[j], &S.e[j]);
+    }
+}
+
+// ---- parameter couplings as linear combinations of table rows ------------------------------------------------
+// Tables (shared memory): T_0[v] = G Z_v (before the dt factor), T_{1+i}[v] = A_i Z_v, T_{1+m+i}[v] = B_i Z_v,
+// T_{1+2m+j}[v] = D_j Z_v.  Every coupling term of a row is  sum_t coef[t] * T_t[v'] ; the coefficients depend on
+// the node (tau) but not on the state index, so a lane builds them once per right-hand side and then streams
+// the table rows.  kMaxT = 1 + 2 kMaxM + kMaxC coefficient slots.
+constexpr int kMaxT = 1 + 2 * kMaxM + kMaxC;
+
+// coef += scale * (dG/dt applied to a vector) = scale * [sum_i u_i w_i (-s_i A_i + c_i B_i) - sum_j wd_j es_j D_j]
+__device__ __forceinline__ void add_Gt(double* coef, const Scal& S, const Ctx& C, double scale) {
+    for (int i = 0; i < C.m; ++i) {
+        coef[1 + i] += scale * S.u[i] * S.om[i] * (-S.s[i]);
+        coef[1 + C.m + i] += scale * S.u[i] * S.om[i] * S.c[i];
+    }
+    for (int j = 0; j < C.nc; ++j) coef[1 + 2 * C.m + j] += scale * (-S.omd[j] * S.es[j]);
+}
+// coef += scale * d2G/dt2
+__device__ __forceinline__ void add_Gtt(double* coef, const Scal& S, const Ctx& C, double scale) {
+    for (int i = 0; i < C.m; ++i) {
+        const double f = -scale * S.u[i] * S.om[i] * S.om[i];
+        coef[1 + i] += f * S.c[i];
+        coef[1 + C.m + i] += f * S.s[i];
+    }
+    for (int j = 0; j < C.nc; ++j) coef[1 + 2 * C.m + j] += -scale * S.omd[j] * S.omd[j] * S.e[j];
+}
+// coef += dM/dtheta_a, M = dt G(u(tau), t_k + tau dt), theta = [u_k (m), u_{k+1} (m, order 1), dt, t_k]
+__device__ __forceinline__ void add_Ma(double* coef, const Scal& S, const Ctx& C, int a) {
+    const int nu = C.np - 2;
+    if (a < nu) {
+        const int i = a % C.m;
+        const double w = S.dt * (a < C.m ? S.w0 : S.w1);
+        coef[1 + i] += w * S.c[i];
+        coef[1 + C.m + i] += w * S.s[i];
+    } else if (a == nu) {
+        coef[0] += 1.0;
+        add_Gt(coef, S, C, S.dt * S.tau);
+    } else {
+        add_Gt(coef, S, C, S.dt);
+    }
+}
+// coef += d2M/(dtheta_a dtheta_b), a <= b
+__device__ __forceinline__ void add_Mab(double* coef, const Scal& S, const Ctx& C, int a, int b) {
+    const int nu = C.np - 2;
+    if (b < nu) return;  // u-u
+    if (a < nu) {
+        const int i = a % C.m;
+        const double w = a < C.m ? S.w0 : S.w1;
+        // b == dt: w (C_i + dt tau C_i');  b == t: dt w C_i',  C_i = c A + s B, C_i' = om (-s A + c B)
+        const double f0 = b == nu ? w : 0.0, f1 = b == nu ? w * S.dt * S.tau : S.dt * w;
+        coef[1 + i] += f0 * S.c[i] + f1 * S.om[i] * (-S.s[i]);
+        coef[1 + C.m + i] += f0 * S.s[i] + f1 * S.om[i] * S.c[i];
+        return;
+    }
+    if (a == nu && b == nu) {
+        add_Gt(coef, S, C, 2.0 * S.tau);
+        add_Gtt(coef, S, C, S.dt * S.tau * S.tau);
+    } else if (a == nu) {
+        add_Gt(coef, S, C, 1.0);
+        add_Gtt(coef, S, C, S.dt * S.tau);
+    } else {
+        add_Gtt(coef, S, C, S.dt);
+    }
+}
+
+// D += sum_t coef[t] * T_t[row]  (tables are [t][rows][n], this lane's states 8 nt + 2q + {0,1})
+template <int NT>
+__device__ __forceinline__ void apply_terms(double (&D)[1][NT][2], const double* coef, int ntab, const double* tab, int rows, int row,
+                                            int q) {
+    constexpr int n = 8 * NT;
+#pragma unroll 1
+    for (int t = 0; t < ntab; ++t) {
+        const double cf = coef[t];
+        if (cf == 0.0) continue;
+        const double* src = tab + ((size_t)t * rows + row) * n + 2 * q;
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            const double2 x = *reinterpret_cast<const double2*>(src + 8 * nt);
+            D[0][nt][0] = fma(cf, x.x, D[0][nt][0]);
+            D[0][nt][1] = fma(cf, x.y, D[0][nt][1]);
+        }
+    }
+}
+
+enum { W_FWD = 0, W_EXP = 1, W_ADJ = 2, W_IDLE = 3 };
+
+// out += V * M' for one tile, the output n-tiles in two halves (half the B fragments live at a time)
+template <int NT>
+__device__ __forceinline__ void mma_tile(double (&out)[1][NT][2], const double (&v)[1][NT][2], const double* __restrict__ M, int lane) {
+    constexpr int n = 8 * NT, NH = (NT + 1) / 2;
+    const int row8 = lane >> 2;
+    const int d = (NT % 2 == 0) ? ((row8 & 1) << 3) : 0;
+    const double* base = M + row8 * n + 2 * (lane & 3);
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+            const int off = 8 * t + ((t & 1) ? -d : d);
+            double2 bf[NH];
+#pragma unroll
+            for (int x = 0; x < NH; ++x)
+                if (half * NH + x < NT) bf[x] = *reinterpret_cast<const double2*>(base + 8 * (half * NH + x) * n + off);
+#pragma unroll
+            for (int x = 0; x < NH; ++x)
+                if (half * NH + x < NT) dmma(out[0][half * NH + x][0], out[0][half * NH + x][1], v[0][t][0], bf[x].x);
+#pragma unroll
+            for (int x = 0; x < NH; ++x)
+                if (half * NH + x < NT) dmma(out[0][half * NH + x][0], out[0][half * NH + x][1], v[0][t][1], bf[x].y);
+        }
+    }
+}
+
+// basis matrix b (0..2m+nc-1) of the swizzled row-major copies
+__device__ __forceinline__ const double* basis_ptr(const DInt& I, int b, int nn) {
+    if (b < I.m) return I.Asw + (size_t)b * nn;
+    if (b < 2 * I.m) return I.Bsw + (size_t)(b - I.m) * nn;
+    return I.Dsw + (size_t)(b - 2 * I.m) * nn;
+}
+
+template <int NT>
+__global__ void __launch_bounds__(kMaxWarpsT * 32, 1)
+    tdb_dmma_kernel(DProb P, int ii, const double* __restrict__ Z, const double* __restrict__ mu, double* __restrict__ g,
+                    double* __restrict__ jac, int want_jac, int want_hess, int K, int steps, int TF, int TE, int TA, int split) {
+    extern __shared__ __align__(16) double sm[];
+    constexpr int n = 8 * NT, nn = n * n, FR = NT * 2 * 32;  // FR: doubles of one tile in per-lane fragment order
+    const DInt& I = P.in[ii];
+    const int m = I.m, nc = I.n_carrier, z = P.z;
+    Ctx C{n, m, nc, I.order, (I.order == 1 ? 2 * m : m) + 2};
+    const int np = C.np, npairs = np * (np + 1) / 2, nbasis = 2 * m + nc, nu = np - 2;
+    const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q = lane & 3, row8 = lane >> 2;
+    const int b = blockIdx.x / P.nI, kl = blockIdx.x % P.nI;
+    const double* zk = Z + (long long)b * P.n_vars_local + (long long)kl * z;
+    const double* zk1 = zk + z;
+    if (P.halo != nullptr && kl + 1 == P.nK - 1) zk1 = P.halo;
+    if (split) {  // two CTAs per interval: forward + adjoint tiles / propagator tiles
+        if (blockIdx.y == 0) TE = 0;
+        else TF = TA = 0;
+    }
+    const int nvecF = TF == 0 ? 0 : (want_hess ? 1 + np + npairs : (want_jac ? 1 + np : 1));
+    const bool couple = nvecF > 1;
+    const int nv1 = couple ? (want_hess ? 1 + np : 1) : 0;  // leading forward rows whose basis products are needed
+
+    int role = W_IDLE, tile = 0;
+    if (warp < TF) { role = W_FWD; tile = warp; }
+    else if (warp < TF + TE) { role = W_EXP; tile = warp - TF; }
+    else if (warp < TF + TE + TA) { role = W_ADJ; tile = 0; }
+    const int scal_warp = nwarps - 1;
+
+    // ---- shared memory -----------------------------------------------------------------------------------
+    double* Gf = sm;                                          // G(tau), swizzled row-major
+    double* Ga = Gf + nn;                                     // G(1 - tau)', swizzled row-major
+    Scal* scal = reinterpret_cast<Scal*>(Ga + nn);            // [2 buffers][forward, adjoint]
+    double* pub0 = reinterpret_cast<double*>(scal + 4);       // leading forward tile in fragment order
+    double* lam = pub0 + FR;                                  // lambda (n)
+    double* PG = lam + n;                                     // [8][n]    G Z_v (before the dt factor)
+    double* Pb = PG + 8 * n;                                  // [nbasis][8][n]
+    double* PGa = Pb + (size_t)nbasis * 8 * n;                // [n]       G' lambda
+    double* PT = PGa + n;                                     // [nbasis][n] basis' lambda
+    double* AccS = PT + (size_t)nbasis * n + (size_t)warp * 2 * FR;  // this warp's extrapolation accumulator
+    double* Y0S = AccS + FR;                                  // this warp's macro-step start
+
+    const int ntab = 1 + nbasis;  // PG/Pb and PGa/PT are laid out back to back: table t of the forward set is PG + t*8n
+
+    // extrapolation weights w_k = prod_{l != k} n_k^2 / (n_k^2 - n_l^2), n_k = 2(k+1)
+    double wk[kMaxCols];
+#pragma unroll
+    for (int k = 0; k < kMaxCols; ++k) {
+        double w = 1.0;
+        const double nk2 = 4.0 * (k + 1) * (k + 1);
+        for (int l = 0; l < K; ++l)
+            if (l != k) w *= nk2 / (nk2 - 4.0 * (l + 1) * (l + 1));
+        wk[k] = k < K ? w : 0.0;
+    }
+    const long long mu_off = (long long)b * P.n_cons_local + I.row_off + (long long)kl * n;
+
+    // ---- initial values (fragment element (nt, j): vector 8*tile + row8, state 8*nt + 2q + j) ------------
+    {
+        const int v = 8 * tile + row8;
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int r = 8 * nt + 2 * q + j;
+                double val = 0.0;
+                if (role == W_FWD) val = v == 0 ? zk[I.x_off + r] : 0.0;
+                else if (role == W_EXP) val = v == r ? 1.0 : 0.0;
+                else if (role == W_ADJ) val = v == 0 ? mu[mu_off + r] : 0.0;
+                if (role != W_IDLE) Y0S[(nt * 2 + j) * 32 + lane] = val;
+            }
+    }
+    if (warp == scal_warp && lane < 2) make_scal(I, zk, zk1, P.dt_off, lane == 0 ? 0.0 : 1.0, scal[lane]);
+    __syncthreads();
+
+    double Zp[1][NT][2], Zc[1][NT][2], D[1][NT][2];
+    int e = 0;  // right-hand sides evaluated so far (parity selects the scalar buffer)
+    for (int ms = 0; ms < steps; ++ms) {
+        const double H = 1.0 / steps, s0 = ms * H;
+        if (role != W_IDLE)
+            for (int i = lane; i < FR; i += 32) AccS[i] = 0.0;
+        for (int k = 0; k < K; ++k) {
+            const int nk = 2 * (k + 1);
+            const double h = H / nk;
+            if (role != W_IDLE) {
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    Zc[0][nt][0] = Y0S[(nt * 2) * 32 + lane];
+                    Zc[0][nt][1] = Y0S[(nt * 2 + 1) * 32 + lane];
+                }
+            }
+            for (int qq = 0; qq <= nk; ++qq, ++e) {
+                const Scal& Sf = scal[(e & 1) * 2];
+                const Scal& Sa = scal[(e & 1) * 2 + 1];
+                // ---- phase 1: generators of this node, published operands --------------------------------
+                for (int blk = warp; blk < nn / 32; blk += nwarps) {
+                    // a 4 x 8 block of the matrix per warp pass: 64-byte global segments, few bank conflicts
+                    // on both the straight and the transposed store
+                    const int r = (blk / NT) * 4 + (lane >> 3), c = (blk % NT) * 8 + (lane & 7);
+                    const int p = sw<NT>(r, c);
+                    double vf = I.Grm[p], va = vf;
+                    for (int i = 0; i < m; ++i) {
+                        const double a = I.Asw[(size_t)i * nn + p], bb = I.Bsw[(size_t)i * nn + p];
+                        vf = fma(Sf.u[i], fma(Sf.c[i], a, Sf.s[i] * bb), vf);
+                        va = fma(Sa.u[i], fma(Sa.c[i], a, Sa.s[i] * bb), va);
+                    }
+                    for (int j = 0; j < nc; ++j) {
+                        const double d = I.Dsw[(size_t)j * nn + p];
+                        vf = fma(Sf.e[j], d, vf);
+                        va = fma(Sa.e[j], d, va);
+                    }
+                    Gf[p] = vf;
+                    if (TA > 0) Ga[sw<NT>(c, r)] = va;
+                }
+                if (role == W_FWD && tile == 0 && couple) {
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt) {
+                        pub0[(nt * 2) * 32 + lane] = Zc[0][nt][0];
+                        pub0[(nt * 2 + 1) * 32 + lane] = Zc[0][nt][1];
+                    }
+                }
+                if (role == W_ADJ && row8 == 0) {
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt) {
+                        lam[8 * nt + 2 * q] = Zc[0][nt][0];
+                        lam[8 * nt + 2 * q + 1] = Zc[0][nt][1];
+                    }
+                }
+                __syncthreads();
+                // ---- phase 2: products ------------------------------------------------------------------
+                if (warp == scal_warp && lane < 2) {  // scalars of the next node, into the other buffer
+                    bool has_next = true;
+                    double sn;
+                    if (qq < nk) sn = (qq + 1 == nk) ? s0 + H : s0 + (qq + 1) * h;
+                    else if (k + 1 < K) sn = s0;
+                    else if (ms + 1 < steps) sn = s0 + H;
+                    else { has_next = false; sn = 0.0; }
+                    if (has_next) make_scal(I, zk, zk1, P.dt_off, lane == 0 ? sn : 1.0 - sn, scal[((e + 1) & 1) * 2 + lane]);
+                }
+                if (TA > 0) {
+                    // basis' lambda on the FMA pipe, one output per thread, taken from the top of the CTA
+                    for (int idx = (int)blockDim.x - 1 - (int)threadIdx.x; idx < nbasis * n; idx += blockDim.x) {
+                        const int bi = idx / n, s = idx % n;
+                        const double* Mb = basis_ptr(I, bi, nn);
+                        double acc = 0.0;
+#pragma unroll 8
+                        for (int kk = 0; kk < n; ++kk) acc = fma(Mb[sw<NT>(kk, s)], lam[kk], acc);
+                        PT[(size_t)bi * n + s] = acc;
+                    }
+                }
+                if (couple) {
+                    // basis products of the leading forward tile, one per warp, starting at the propagator warps
+                    for (int bi = 0; bi < nbasis; ++bi) {
+                        if ((TF + bi) % nwarps != warp) continue;
+                        const double* Mb = basis_ptr(I, bi, nn);
+                        double* out = Pb + (size_t)bi * 8 * n + (size_t)row8 * n + 2 * q;
+#pragma unroll
+                        for (int half = 0; half < 2; ++half) {
+                            constexpr int NH = (NT + 1) / 2;
+                            double acc[NH][2];
+#pragma unroll
+                            for (int x = 0; x < NH; ++x) acc[x][0] = acc[x][1] = 0.0;
+                            const int dsw = (NT % 2 == 0) ? ((row8 & 1) << 3) : 0;
+                            const double* base = Mb + row8 * n + 2 * q;
+#pragma unroll
+                            for (int t = 0; t < NT; ++t) {
+                                const double a0 = pub0[(t * 2) * 32 + lane], a1 = pub0[(t * 2 + 1) * 32 + lane];
+                                const int off = 8 * t + ((t & 1) ? -dsw : dsw);
+#pragma unroll
+                                for (int x = 0; x < NH; ++x) {
+                                    const int nt = half * NH + x;
+                                    if (nt < NT) {
+                                        const double2 bf = *reinterpret_cast<const double2*>(base + 8 * nt * n + off);
+                                        dmma(acc[x][0], acc[x][1], a0, bf.x);
+                                        dmma(acc[x][0], acc[x][1], a1, bf.y);
+                                    }
+                                }
+                            }
+#pragma unroll
+                            for (int x = 0; x < NH; ++x) {
+                                const int nt = half * NH + x;
+                                if (nt < NT) {
+                                    out[8 * nt] = acc[x][0];
+                                    out[8 * nt + 1] = acc[x][1];
+                                }
+                            }
+                        }
+                    }
+                }
+                if (role != W_IDLE) {
+                    frag_zero(D);
+                    mma_tile<NT>(D, Zc, role == W_ADJ ? Ga : Gf, lane);
+                    if (role == W_FWD && tile == 0 && couple) {
+#pragma unroll
+                        for (int nt = 0; nt < NT; ++nt) {
+                            PG[row8 * n + 8 * nt + 2 * q] = D[0][nt][0];
+                            PG[row8 * n + 8 * nt + 2 * q + 1] = D[0][nt][1];
+                        }
+                    }
+                    if (role == W_ADJ && row8 == 0) {
+#pragma unroll
+                        for (int nt = 0; nt < NT; ++nt) {
+                            PGa[8 * nt + 2 * q] = D[0][nt][0];
+                            PGa[8 * nt + 2 * q + 1] = D[0][nt][1];
+                        }
+                    }
+                    const double dts = Sf.dt;
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt) {
+                        D[0][nt][0] *= dts;
+                        D[0][nt][1] *= dts;
+                    }
+                }
+                __syncthreads();
+                // ---- phase 3: parameter couplings, midpoint update ---------------------------------------
+                if (role == W_FWD && couple) {
+                    const int v = 8 * tile + row8;
+                    if (v >= 1 && v < nvecF) {
+                        double coef[kMaxT];
+                        if (v <= np) {  // first-order row a: (dM/dtheta_a) x
+                            for (int t = 0; t < ntab; ++t) coef[t] = 0.0;
+                            add_Ma(coef, Sf, C, v - 1);
+                            apply_terms<NT>(D, coef, ntab, PG, 8, 0, q);
+                        } else {  // pair (a, bb): M_a Z_bb + M_bb Z_a + M_ab x
+                            int p = v - 1 - np, a = 0;
+                            while (p >= np - a) {
+                                p -= np - a;
+                                ++a;
+                            }
+                            const int bb = a + p;
+                            for (int t = 0; t < ntab; ++t) coef[t] = 0.0;
+                            add_Ma(coef, Sf, C, a);
+                            if (a == bb) {
+                                for (int t = 0; t < ntab; ++t) coef[t] *= 2.0;
+                                apply_terms<NT>(D, coef, ntab, PG, 8, 1 + a, q);
+                            } else {
+                                apply_terms<NT>(D, coef, ntab, PG, 8, 1 + bb, q);
+                                for (int t = 0; t < ntab; ++t) coef[t] = 0.0;
+                                add_Ma(coef, Sf, C, bb);
+                                apply_terms<NT>(D, coef, ntab, PG, 8, 1 + a, q);
+                            }
+                            for (int t = 0; t < ntab; ++t) coef[t] = 0.0;
+                            add_Mab(coef, Sf, C, a, bb);
+                            apply_terms<NT>(D, coef, ntab, PG, 8, 0, q);
+                        }
+                    }
+                } else if (role == W_ADJ) {
+                    const int v = row8;
+                    if (v >= 1 && v <= np) {  // d lambda^a = M' lambda^a + (M^a)' lambda
+                        double coef[kMaxT];
+                        for (int t = 0; t < ntab; ++t) coef[t] = 0.0;
+                        add_Ma(coef, Sa, C, v - 1);
+                        apply_terms<NT>(D, coef, ntab, PGa, 1, 0, q);
+                    }
+                }
+                if (role != W_IDLE) {
+                    if (qq == 0) {
+#pragma unroll
+                        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                            for (int j = 0; j < 2; ++j) {
+                                Zp[0][nt][j] = Zc[0][nt][j];
+                                Zc[0][nt][j] = fma(h, D[0][nt][j], Zc[0][nt][j]);
+                            }
+                    } else if (qq < nk) {
+#pragma unroll
+                        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                            for (int j = 0; j < 2; ++j) {
+                                const double znew = fma(2.0 * h, D[0][nt][j], Zp[0][nt][j]);
+                                Zp[0][nt][j] = Zc[0][nt][j];
+                                Zc[0][nt][j] = znew;
+                            }
+                    } else {
+#pragma unroll
+                        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                            for (int j = 0; j < 2; ++j)
+                                AccS[(nt * 2 + j) * 32 + lane] += wk[k] * 0.5 * (Zc[0][nt][j] + Zp[0][nt][j] + h * D[0][nt][j]);
+                    }
+                }
+            }
+        }
+        if (role != W_IDLE)
+            for (int i = lane; i < FR; i += 32) Y0S[i] = AccS[i];
+        __syncwarp();
+    }
+
+    // ---- outputs -----------------------------------------------------------------------------------------
+    if (role == W_IDLE) return;
+    double F[NT][2];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+        F[nt][0] = Y0S[(nt * 2) * 32 + lane];
+        F[nt][1] = Y0S[(nt * 2 + 1) * 32 + lane];
+    }
+    if (role == W_FWD) {
+        const int v = 8 * tile + row8;
+        if (g != nullptr && v == 0) {
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                g[mu_off + 8 * nt + 2 * q] = zk1[I.x_off + 8 * nt + 2 * q] - F[nt][0];
+                g[mu_off + 8 * nt + 2 * q + 1] = zk1[I.x_off + 8 * nt + 2 * q + 1] - F[nt][1];
+            }
+        }
+        if (want_jac) {
+            double* jp = jac + (long long)b * P.nnz_jac_local;
+            const long long own_off = jac_own_off(P, kl, I.doff, n);
+            const long long prev_off = jac_prev_off(P, kl + 1, I.doff);
+            if (v >= 1 && v <= np) {  // first-order rows are Jacobian columns
+                const int a = v - 1;
+                double* col;
+                if (a < m) col = jp + P.jac_colptr[(long long)kl * z + I.u_off + a] + own_off;
+                else if (a < nu) col = jp + P.jac_colptr[(long long)(kl + 1) * z + I.u_off + (a - m)] + prev_off;
+                else if (a == nu) col = jp + P.jac_colptr[(long long)kl * z + P.dt_off] + own_off;
+                else col = jp + P.jac_colptr[(long long)kl * z + I.t_off] + own_off;
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    col[8 * nt + 2 * q] = -F[nt][0];
+                    col[8 * nt + 2 * q + 1] = -F[nt][1];
+                }
+            }
+            if (tile == 0) {  // zero and identity columns
+                for (int e2 = lane; e2 < 2 * z * n; e2 += 32) {
+                    const int l = e2 / n, a = e2 % n;
+                    if (l < z) {
+                        if ((l >= I.x_off && l < I.x_off + n) || (l >= I.u_off && l < I.u_off + m) || l == P.dt_off || l == I.t_off) continue;
+                        jp[P.jac_colptr[(long long)kl * z + l] + own_off + a] = 0.0;
+                    } else {
+                        const int lp = l - z;
+                        if (I.order == 1 && lp >= I.u_off && lp < I.u_off + m) continue;
+                        jp[P.jac_colptr[(long long)(kl + 1) * z + lp] + prev_off + a] = (lp - I.x_off == a) ? 1.0 : 0.0;
+                    }
+                }
+            }
+        }
+        if (want_hess) {
+            // -mu' d2Phi x / (dtheta_a dtheta_b): every row reduces over its quad (uniform shuffles), pair rows store
+            double s1 = 0.0;
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+                s1 = fma(mu[mu_off + 8 * nt + 2 * q], F[nt][0], fma(mu[mu_off + 8 * nt + 2 * q + 1], F[nt][1], s1));
+            s1 = quad_sum(s1);
+            if (q == 0 && v > np && v < nvecF) {
+                int p = v - 1 - np, a = 0;
+                while (p >= np - a) {
+                    p -= np - a;
+                    ++a;
+                }
+                const int bb = a + p;
+                double* hpp = I.hs + ((long long)b * P.nI + kl) * I.hs_stride + (long long)np * n;
+                hpp[a * np + bb] = -s1;
+                hpp[bb * np + a] = -s1;
+            }
+        }
+    } else if (role == W_EXP) {
+        double* jp = jac + (long long)b * P.nnz_jac_local;
+        const long long own_off = jac_own_off(P, kl, I.doff, n);
+        const int col = 8 * tile + row8;
+        double* cp = jp + P.jac_colptr[(long long)kl * z + I.x_off + col] + own_off;
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            cp[8 * nt + 2 * q] = -F[nt][0];
+            cp[8 * nt + 2 * q + 1] = -F[nt][1];
+        }
+    } else {
+        double* hx = I.hs + ((long long)b * P.nI + kl) * I.hs_stride;
+        const int v = row8;
+        if (v >= 1 && v <= np) {
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                hx[(size_t)(v - 1) * n + 8 * nt + 2 * q] = -F[nt][0];
+                hx[(size_t)(v - 1) * n + 8 * nt + 2 * q + 1] = -F[nt][1];
+            }
+        }
+    }
+}
+
+struct Plan {
+    int TF, TE, TA, split, warps;
+    size_t smem;
+};
+
+bool make_plan(const DInt& I, bool want_jac, bool want_hess, Plan& pl) {
+    const int n = I.n, m = I.m, nc = I.n_carrier;
+    if (n % 8 != 0 || n > 64 || (n / 8 == 5) || (n / 8 == 7) || m > kMaxM || nc > kMaxC || I.Asw == nullptr) return false;
+    const int np = (I.order == 1 ? 2 * m : m) + 2, npairs = np * (np + 1) / 2;
+    if (1 + np > 8) return false;  // the first-order rows (and the adjoint set) must fit one tile
+    const int nvecF = want_hess ? 1 + np + npairs : (want_jac ? 1 + np : 1);
+    pl.TF = (nvecF + 7) / 8;
+    pl.TE = want_jac ? n / 8 : 0;
+    pl.TA = want_hess ? 1 : 0;
+    pl.split = 0;
+    pl.warps = pl.TF + pl.TE + pl.TA;
+    if (pl.warps > kMaxWarpsT) {
+        pl.split = 1;
+        pl.warps = std::max(pl.TF + pl.TA, pl.TE);
+        if (pl.warps > kMaxWarpsT) return false;
+    }
+    pl.warps = std::max(pl.warps, 4);  // idle warps still help assembling the generators
+    const size_t FR = (size_t)(n / 8) * 2 * 32, nbasis = 2 * m + nc;
+    const size_t doubles = 2 * (size_t)n * n + 4 * sizeof(Scal) / sizeof(double) + FR + n + 8 * n + nbasis * 8 * n + n + nbasis * n +
+                           (size_t)pl.warps * 2 * FR;
+    pl.smem = doubles * sizeof(double);
+    return pl.smem <= 226 * 1024;
+}
+
+template <int NT>
+void launch_nt(const DProb& P, int ii, const double* Z, const double* mu, double* g, double* jac, EvalFlags f, cudaStream_t st,
+               const Plan& pl) {
+    auto kern = tdb_dmma_kernel<NT>;
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        configured = true;
+    }
+    const DInt& I = P.in[ii];
+    dim3 grid((unsigned)(P.nI * P.batch), pl.split ? 2 : 1);
+    kern<<<grid, pl.warps * 32, pl.smem, st>>>(P, ii, Z, mu, f.want_g ? g : nullptr, jac, f.want_jac ? 1 : 0, f.want_hess ? 1 : 0, 8,
+                                               I.steps, pl.TF, pl.TE, pl.TA, pl.split);
+}
+
+}  // namespace
+
+bool tdb_dmma_supported(const DInt& I) {
+    Plan pl;
+    return make_plan(I, true, true, pl);
+}
+
+bool launch_tdb_dmma(const DProb& P, int ii, const double* Z, const double* mu, double* g, double* jac, EvalFlags f, cudaStream_t st,
+                     long long* launches) {
+    const DInt& I = P.in[ii];
+    if (P.nI <= 0) return true;
+    Plan pl;
+    if (!make_plan(I, f.want_jac, f.want_hess, pl)) return false;
+    switch (I.n / 8) {
+        case 1: launch_nt<1>(P, ii, Z, mu, g, jac, f, st, pl); break;
+        case 2: launch_nt<2>(P, ii, Z, mu, g, jac, f, st, pl); break;
+        case 3: launch_nt<3>(P, ii, Z, mu, g, jac, f, st, pl); break;
+        case 4: launch_nt<4>(P, ii, Z, mu, g, jac, f, st, pl); break;
+        case 6: launch_nt<6>(P, ii, Z, mu, g, jac, f, st, pl); break;
+        case 8: launch_nt<8>(P, ii, Z, mu, g, jac, f, st, pl); break;
+        default: return false;
+    }
+    ++*launches;
+    return true;
+}

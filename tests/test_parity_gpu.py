@@ -175,7 +175,8 @@ def test_unsupported_components_raise_at_construction():
 TDB_TOL = 1e-9  # fixed-order extrapolation integrator vs the oracle's rtol=1e-13 variational solve (DESIGN.md "TDBI parity")
 
 
-@pytest.mark.parametrize("order,n,m,carriers", [(1, 4, 2, 0), (0, 4, 2, 0), (1, 6, 1, 2), (1, 16, 2, 0)])
+@pytest.mark.parametrize("order,n,m,carriers", [(1, 4, 2, 0), (0, 4, 2, 0), (1, 6, 1, 2), (1, 16, 2, 0), (1, 8, 2, 1), (0, 24, 3, 0),
+                                                   (1, 32, 1, 2), (0, 8, 4, 1)])
 def test_tdbilinear_matches_exact_variational_solution(order, n, m, carriers):
     rng = np.random.default_rng(9)
     prob = pt.carrier_problem(N=5, state_dim=n, n_drives=m, spline_order=order, dt=0.2)
@@ -212,6 +213,26 @@ def test_tdbilinear_matches_exact_variational_solution(order, n, m, carriers):
         cross = (hr - 1) // z != (hc - 1) // z
         assert np.abs(Href[cross]).max() > 1e-6
     ev.close()
+
+
+def test_tdbilinear_variants_agree(monkeypatch):
+    """The tensor-core variant of K7 and the CUDA-core variant integrate the same equations with the same
+    extrapolation scheme: they must agree far below the parity tolerance (and the dispatch must pick them)."""
+    prob = pt.carrier_problem(N=6, state_dim=16, n_drives=2, spline_order=1, dt=0.2)
+    Z = prob.trajectory.datavec.copy()
+    outs = {}
+    for pin in ("", "generic"):
+        if pin:
+            monkeypatch.setenv("DTO_B200_KERNEL", pin)
+        ev = dto.Evaluator(prob)
+        assert ev.kernel_variant(0) == ("gbs" if pin else "gbs-dmma")
+        mu = np.random.default_rng(2).random(ev.n_constraints)
+        bufs = [np.empty(1), np.empty(ev.n_vars), np.empty(ev.n_constraints), np.empty(ev.nnz_jacobian), np.empty(ev.nnz_hessian)]
+        ev.eval_all(Z, 1.0, mu, *bufs)
+        outs[pin] = bufs
+        ev.close()
+    for a, b in zip(outs[""], outs["generic"]):
+        assert relerr(a, b) <= 1e-12
 
 
 def test_host_pipeline_matches_single_pass(monkeypatch):
