@@ -244,6 +244,11 @@ extern "C" int dto_create(const dto_problem_desc* d, dto_handle** out) {
                     I.Bsw = dev_upload(h, swizzled(s.B, s.u_dim).data(), nn * s.u_dim);
                 }
                 if (s.n_carrier > 0) I.Dsw = dev_upload(h, swizzled(s.D, s.n_carrier).data(), nn * s.n_carrier);
+                int sms = 148;
+                cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+                I.tdb_scratch_ctas = 2 * sms;
+                // [CTA][16 warps][accumulator, start][one tile in fragment order]
+                I.tdb_scratch = dev_upload<double>(h, nullptr, (size_t)I.tdb_scratch_ctas * 16 * 2 * (nd / 8) * 64);
             }
             const int np = (s.spline_order == 1 ? 2 * s.u_dim : s.u_dim) + 2;
             I.hs_stride = np * s.x_dim + np * np;

@@ -27,6 +27,8 @@ struct DInt {
     const double* Grm;  // bilinear: row-major copies of the same matrices
     const double *A, *B, *omega, *phi, *D, *omega_d, *phi_d;
     const double *Asw, *Bsw, *Dsw;  // tdbilinear, DMMA variant: swizzled row-major copies (Grm holds G0)
+    double* tdb_scratch;            // tdbilinear, DMMA variant: per-CTA extrapolation scratch
+    int tdb_scratch_ctas;           // CTAs the scratch was sized for (one per SM)
     double* hs;         // [batch][n_intervals][hs_stride]
     unsigned long long* wq;  // bilinear, persistent variant: three work-queue counters (FWD, EXP, ADJ)
 };

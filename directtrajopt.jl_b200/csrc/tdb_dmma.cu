@@ -61,83 +61,127 @@ __device__ void make_scal(const DInt& I, const double* zk, const double* zk1, in
 // ---- parameter couplings as linear combinations of table rows ------------------------------------------------
 // Tables (shared memory): T_0[v] = G Z_v (before the dt factor), T_{1+i}[v] = A_i Z_v, T_{1+m+i}[v] = B_i Z_v,
 // T_{1+2m+j}[v] = D_j Z_v.  Every coupling term of a row is  sum_t coef[t] * T_t[v'] ; the coefficients depend on
-// the node (tau) but not on the state index, so a lane builds them once per right-hand side and then streams
-// the table rows.  kMaxT = 1 + 2 kMaxM + kMaxC coefficient slots.
-constexpr int kMaxT = 1 + 2 * kMaxM + kMaxC;
-
-// coef += scale * (dG/dt applied to a vector) = scale * [sum_i u_i w_i (-s_i A_i + c_i B_i) - sum_j wd_j es_j D_j]
-__device__ __forceinline__ void add_Gt(double* coef, const Scal& S, const Ctx& C, double scale) {
-    for (int i = 0; i < C.m; ++i) {
-        coef[1 + i] += scale * S.u[i] * S.om[i] * (-S.s[i]);
-        coef[1 + C.m + i] += scale * S.u[i] * S.om[i] * S.c[i];
+// the node (tau) but not on the state index, so a lane builds them once per right-hand side (in registers:
+// fixed slots, statically indexed) and then streams the table rows.
+struct Coef {
+    double g, a[kMaxM], b[kMaxM], d[kMaxC];
+};
+__device__ __forceinline__ void coef_zero(Coef& c) {
+    c.g = 0.0;
+#pragma unroll
+    for (int i = 0; i < kMaxM; ++i) c.a[i] = c.b[i] = 0.0;
+#pragma unroll
+    for (int j = 0; j < kMaxC; ++j) c.d[j] = 0.0;
+}
+__device__ __forceinline__ void coef_scale(Coef& c, double f) {
+    c.g *= f;
+#pragma unroll
+    for (int i = 0; i < kMaxM; ++i) {
+        c.a[i] *= f;
+        c.b[i] *= f;
     }
-    for (int j = 0; j < C.nc; ++j) coef[1 + 2 * C.m + j] += scale * (-S.omd[j] * S.es[j]);
+#pragma unroll
+    for (int j = 0; j < kMaxC; ++j) c.d[j] *= f;
+}
+// coef += scale * dG/dt = scale * [sum_i u_i w_i (-s_i A_i + c_i B_i) - sum_j wd_j es_j D_j]
+__device__ __forceinline__ void add_Gt(Coef& c, const Scal& S, const Ctx& C, double scale) {
+#pragma unroll
+    for (int i = 0; i < kMaxM; ++i)
+        if (i < C.m) {
+            c.a[i] += scale * S.u[i] * S.om[i] * (-S.s[i]);
+            c.b[i] += scale * S.u[i] * S.om[i] * S.c[i];
+        }
+#pragma unroll
+    for (int j = 0; j < kMaxC; ++j)
+        if (j < C.nc) c.d[j] += scale * (-S.omd[j] * S.es[j]);
 }
 // coef += scale * d2G/dt2
-__device__ __forceinline__ void add_Gtt(double* coef, const Scal& S, const Ctx& C, double scale) {
-    for (int i = 0; i < C.m; ++i) {
-        const double f = -scale * S.u[i] * S.om[i] * S.om[i];
-        coef[1 + i] += f * S.c[i];
-        coef[1 + C.m + i] += f * S.s[i];
-    }
-    for (int j = 0; j < C.nc; ++j) coef[1 + 2 * C.m + j] += -scale * S.omd[j] * S.omd[j] * S.e[j];
+__device__ __forceinline__ void add_Gtt(Coef& c, const Scal& S, const Ctx& C, double scale) {
+#pragma unroll
+    for (int i = 0; i < kMaxM; ++i)
+        if (i < C.m) {
+            const double f = -scale * S.u[i] * S.om[i] * S.om[i];
+            c.a[i] += f * S.c[i];
+            c.b[i] += f * S.s[i];
+        }
+#pragma unroll
+    for (int j = 0; j < kMaxC; ++j)
+        if (j < C.nc) c.d[j] += -scale * S.omd[j] * S.omd[j] * S.e[j];
 }
 // coef += dM/dtheta_a, M = dt G(u(tau), t_k + tau dt), theta = [u_k (m), u_{k+1} (m, order 1), dt, t_k]
-__device__ __forceinline__ void add_Ma(double* coef, const Scal& S, const Ctx& C, int a) {
+__device__ __forceinline__ void add_Ma(Coef& c, const Scal& S, const Ctx& C, int a) {
     const int nu = C.np - 2;
     if (a < nu) {
-        const int i = a % C.m;
+        const int ia = a % C.m;
         const double w = S.dt * (a < C.m ? S.w0 : S.w1);
-        coef[1 + i] += w * S.c[i];
-        coef[1 + C.m + i] += w * S.s[i];
+#pragma unroll
+        for (int i = 0; i < kMaxM; ++i)
+            if (i == ia) {
+                c.a[i] += w * S.c[i];
+                c.b[i] += w * S.s[i];
+            }
     } else if (a == nu) {
-        coef[0] += 1.0;
-        add_Gt(coef, S, C, S.dt * S.tau);
+        c.g += 1.0;
+        add_Gt(c, S, C, S.dt * S.tau);
     } else {
-        add_Gt(coef, S, C, S.dt);
+        add_Gt(c, S, C, S.dt);
     }
 }
 // coef += d2M/(dtheta_a dtheta_b), a <= b
-__device__ __forceinline__ void add_Mab(double* coef, const Scal& S, const Ctx& C, int a, int b) {
+__device__ __forceinline__ void add_Mab(Coef& c, const Scal& S, const Ctx& C, int a, int b) {
     const int nu = C.np - 2;
     if (b < nu) return;  // u-u
     if (a < nu) {
-        const int i = a % C.m;
+        const int ia = a % C.m;
         const double w = a < C.m ? S.w0 : S.w1;
         // b == dt: w (C_i + dt tau C_i');  b == t: dt w C_i',  C_i = c A + s B, C_i' = om (-s A + c B)
         const double f0 = b == nu ? w : 0.0, f1 = b == nu ? w * S.dt * S.tau : S.dt * w;
-        coef[1 + i] += f0 * S.c[i] + f1 * S.om[i] * (-S.s[i]);
-        coef[1 + C.m + i] += f0 * S.s[i] + f1 * S.om[i] * S.c[i];
+#pragma unroll
+        for (int i = 0; i < kMaxM; ++i)
+            if (i == ia) {
+                c.a[i] += f0 * S.c[i] + f1 * S.om[i] * (-S.s[i]);
+                c.b[i] += f0 * S.s[i] + f1 * S.om[i] * S.c[i];
+            }
         return;
     }
     if (a == nu && b == nu) {
-        add_Gt(coef, S, C, 2.0 * S.tau);
-        add_Gtt(coef, S, C, S.dt * S.tau * S.tau);
+        add_Gt(c, S, C, 2.0 * S.tau);
+        add_Gtt(c, S, C, S.dt * S.tau * S.tau);
     } else if (a == nu) {
-        add_Gt(coef, S, C, 1.0);
-        add_Gtt(coef, S, C, S.dt * S.tau);
+        add_Gt(c, S, C, 1.0);
+        add_Gtt(c, S, C, S.dt * S.tau);
     } else {
-        add_Gtt(coef, S, C, S.dt);
+        add_Gtt(c, S, C, S.dt);
     }
 }
 
-// D += sum_t coef[t] * T_t[row]  (tables are [t][rows][n], this lane's states 8 nt + 2q + {0,1})
+// D += cf * row   (this lane's states 8 nt + 2q + {0,1})
 template <int NT>
-__device__ __forceinline__ void apply_terms(double (&D)[1][NT][2], const double* coef, int ntab, const double* tab, int rows, int row,
-                                            int q) {
-    constexpr int n = 8 * NT;
-#pragma unroll 1
-    for (int t = 0; t < ntab; ++t) {
-        const double cf = coef[t];
-        if (cf == 0.0) continue;
-        const double* src = tab + ((size_t)t * rows + row) * n + 2 * q;
+__device__ __forceinline__ void axpy_row(double (&D)[1][NT][2], double cf, const double* src) {
+    if (cf == 0.0) return;
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt) {
-            const double2 x = *reinterpret_cast<const double2*>(src + 8 * nt);
-            D[0][nt][0] = fma(cf, x.x, D[0][nt][0]);
-            D[0][nt][1] = fma(cf, x.y, D[0][nt][1]);
-        }
+    for (int nt = 0; nt < NT; ++nt) {
+        const double2 x = *reinterpret_cast<const double2*>(src + 8 * nt);
+        D[0][nt][0] = fma(cf, x.x, D[0][nt][0]);
+        D[0][nt][1] = fma(cf, x.y, D[0][nt][1]);
     }
+}
+// D += sum_t coef[t] * T_t[row]  (tables are [t][rows][n])
+template <int NT>
+__device__ __forceinline__ void apply_terms(double (&D)[1][NT][2], const Coef& c, const Ctx& C, const double* tab, int rows, int row, int q) {
+    constexpr int n = 8 * NT;
+    const double* base = tab + (size_t)row * n + 2 * q;
+    const size_t ts = (size_t)rows * n;
+    axpy_row<NT>(D, c.g, base);
+#pragma unroll
+    for (int i = 0; i < kMaxM; ++i)
+        if (i < C.m) {
+            axpy_row<NT>(D, c.a[i], base + (1 + i) * ts);
+            axpy_row<NT>(D, c.b[i], base + (1 + C.m + i) * ts);
+        }
+#pragma unroll
+    for (int j = 0; j < kMaxC; ++j)
+        if (j < C.nc) axpy_row<NT>(D, c.d[j], base + (1 + 2 * C.m + j) * ts);
 }
 
 enum { W_FWD = 0, W_EXP = 1, W_ADJ = 2, W_IDLE = 3 };
@@ -169,7 +213,7 @@ __device__ __forceinline__ void mma_tile(double (&out)[1][NT][2], const double (
 }
 
 // basis matrix b (0..2m+nc-1) of the swizzled row-major copies
-__device__ __forceinline__ const double* basis_ptr(const DInt& I, int b, int nn) {
+__device__ __forceinline__ const double* basis_global(const DInt& I, int b, int nn) {
     if (b < I.m) return I.Asw + (size_t)b * nn;
     if (b < 2 * I.m) return I.Bsw + (size_t)(b - I.m) * nn;
     return I.Dsw + (size_t)(b - 2 * I.m) * nn;
@@ -178,7 +222,8 @@ __device__ __forceinline__ const double* basis_ptr(const DInt& I, int b, int nn)
 template <int NT>
 __global__ void __launch_bounds__(kMaxWarpsT * 32, 1)
     tdb_dmma_kernel(DProb P, int ii, const double* __restrict__ Z, const double* __restrict__ mu, double* __restrict__ g,
-                    double* __restrict__ jac, int want_jac, int want_hess, int K, int steps, int TF, int TE, int TA, int split) {
+                    double* __restrict__ jac, int want_jac, int want_hess, int K, int steps, int TF, int TE, int TA, int split, int nbs,
+                    double* __restrict__ scratch) {
     extern __shared__ __align__(16) double sm[];
     constexpr int n = 8 * NT, nn = n * n, FR = NT * 2 * 32;  // FR: doubles of one tile in per-lane fragment order
     const DInt& I = P.in[ii];
@@ -187,10 +232,6 @@ __global__ void __launch_bounds__(kMaxWarpsT * 32, 1)
     const int np = C.np, npairs = np * (np + 1) / 2, nbasis = 2 * m + nc, nu = np - 2;
     const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q = lane & 3, row8 = lane >> 2;
-    const int b = blockIdx.x / P.nI, kl = blockIdx.x % P.nI;
-    const double* zk = Z + (long long)b * P.n_vars_local + (long long)kl * z;
-    const double* zk1 = zk + z;
-    if (P.halo != nullptr && kl + 1 == P.nK - 1) zk1 = P.halo;
     if (split) {  // two CTAs per interval: forward + adjoint tiles / propagator tiles
         if (blockIdx.y == 0) TE = 0;
         else TF = TA = 0;
@@ -215,21 +256,36 @@ __global__ void __launch_bounds__(kMaxWarpsT * 32, 1)
     double* Pb = PG + 8 * n;                                  // [nbasis][8][n]
     double* PGa = Pb + (size_t)nbasis * 8 * n;                // [n]       G' lambda
     double* PT = PGa + n;                                     // [nbasis][n] basis' lambda
-    double* AccS = PT + (size_t)nbasis * n + (size_t)warp * 2 * FR;  // this warp's extrapolation accumulator
-    double* Y0S = AccS + FR;                                  // this warp's macro-step start
-
-    const int ntab = 1 + nbasis;  // PG/Pb and PGa/PT are laid out back to back: table t of the forward set is PG + t*8n
-
-    // extrapolation weights w_k = prod_{l != k} n_k^2 / (n_k^2 - n_l^2), n_k = 2(k+1)
-    double wk[kMaxCols];
-#pragma unroll
-    for (int k = 0; k < kMaxCols; ++k) {
+    double* wk = PT + (size_t)nbasis * n;                     // [kMaxCols] extrapolation weights
+    double* Bs = wk + kMaxCols + (kMaxCols & 1);              // the first nbs basis matrices, cached for the CTA's lifetime
+    if (threadIdx.x < kMaxCols) {
+        // w_k = prod_{l != k} n_k^2 / (n_k^2 - n_l^2), n_k = 2(k+1)
+        const int k = threadIdx.x;
         double w = 1.0;
         const double nk2 = 4.0 * (k + 1) * (k + 1);
         for (int l = 0; l < K; ++l)
             if (l != k) w *= nk2 / (nk2 - 4.0 * (l + 1) * (l + 1));
         wk[k] = k < K ? w : 0.0;
     }
+    // extrapolation accumulator and macro-step start of this warp: touched only at sweep boundaries, kept in a
+    // per-CTA global scratch (L2-resident) so that shared memory can hold the basis matrices instead
+    double* AccS = scratch + (((size_t)blockIdx.y * gridDim.x + blockIdx.x) * kMaxWarpsT + warp) * 2 * FR;
+    double* Y0S = AccS + FR;
+    for (int i = threadIdx.x; i < nbs * nn; i += blockDim.x) {
+        const int bi = i / nn, p = i % nn;
+        Bs[i] = basis_global(I, bi, nn)[p];
+    }
+    auto basis_ptr = [&](int bi) -> const double* { return bi < nbs ? Bs + (size_t)bi * nn : basis_global(I, bi, nn); };
+
+    // PG/Pb and PGa/PT are laid out back to back: table t of the forward set is PG + t*8n, of the adjoint set PGa + t*n
+
+    const int n_items = P.nI * P.batch;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int b = item / P.nI, kl = item % P.nI;
+    const double* zk = Z + (long long)b * P.n_vars_local + (long long)kl * z;
+    const double* zk1 = zk + z;
+    if (P.halo != nullptr && kl + 1 == P.nK - 1) zk1 = P.halo;
+    __syncthreads();  // the previous item's tables and scalars are dead
     const long long mu_off = (long long)b * P.n_cons_local + I.row_off + (long long)kl * n;
 
     // ---- initial values (fragment element (nt, j): vector 8*tile + row8, state 8*nt + 2q + j) ------------
@@ -277,12 +333,12 @@ __global__ void __launch_bounds__(kMaxWarpsT * 32, 1)
                     const int p = sw<NT>(r, c);
                     double vf = I.Grm[p], va = vf;
                     for (int i = 0; i < m; ++i) {
-                        const double a = I.Asw[(size_t)i * nn + p], bb = I.Bsw[(size_t)i * nn + p];
+                        const double a = basis_ptr(i)[p], bb = basis_ptr(m + i)[p];
                         vf = fma(Sf.u[i], fma(Sf.c[i], a, Sf.s[i] * bb), vf);
                         va = fma(Sa.u[i], fma(Sa.c[i], a, Sa.s[i] * bb), va);
                     }
                     for (int j = 0; j < nc; ++j) {
-                        const double d = I.Dsw[(size_t)j * nn + p];
+                        const double d = basis_ptr(2 * m + j)[p];
                         vf = fma(Sf.e[j], d, vf);
                         va = fma(Sa.e[j], d, va);
                     }
@@ -318,7 +374,7 @@ __global__ void __launch_bounds__(kMaxWarpsT * 32, 1)
                     // basis' lambda on the FMA pipe, one output per thread, taken from the top of the CTA
                     for (int idx = (int)blockDim.x - 1 - (int)threadIdx.x; idx < nbasis * n; idx += blockDim.x) {
                         const int bi = idx / n, s = idx % n;
-                        const double* Mb = basis_ptr(I, bi, nn);
+                        const double* Mb = basis_ptr(bi);
                         double acc = 0.0;
 #pragma unroll 8
                         for (int kk = 0; kk < n; ++kk) acc = fma(Mb[sw<NT>(kk, s)], lam[kk], acc);
@@ -329,7 +385,7 @@ __global__ void __launch_bounds__(kMaxWarpsT * 32, 1)
                     // basis products of the leading forward tile, one per warp, starting at the propagator warps
                     for (int bi = 0; bi < nbasis; ++bi) {
                         if ((TF + bi) % nwarps != warp) continue;
-                        const double* Mb = basis_ptr(I, bi, nn);
+                        const double* Mb = basis_ptr(bi);
                         double* out = Pb + (size_t)bi * 8 * n + (size_t)row8 * n + 2 * q;
 #pragma unroll
                         for (int half = 0; half < 2; ++half) {
@@ -393,11 +449,11 @@ __global__ void __launch_bounds__(kMaxWarpsT * 32, 1)
                 if (role == W_FWD && couple) {
                     const int v = 8 * tile + row8;
                     if (v >= 1 && v < nvecF) {
-                        double coef[kMaxT];
+                        Coef cf;
+                        coef_zero(cf);
                         if (v <= np) {  // first-order row a: (dM/dtheta_a) x
-                            for (int t = 0; t < ntab; ++t) coef[t] = 0.0;
-                            add_Ma(coef, Sf, C, v - 1);
-                            apply_terms<NT>(D, coef, ntab, PG, 8, 0, q);
+                            add_Ma(cf, Sf, C, v - 1);
+                            apply_terms<NT>(D, cf, C, PG, 8, 0, q);
                         } else {  // pair (a, bb): M_a Z_bb + M_bb Z_a + M_ab x
                             int p = v - 1 - np, a = 0;
                             while (p >= np - a) {
@@ -405,29 +461,28 @@ __global__ void __launch_bounds__(kMaxWarpsT * 32, 1)
                                 ++a;
                             }
                             const int bb = a + p;
-                            for (int t = 0; t < ntab; ++t) coef[t] = 0.0;
-                            add_Ma(coef, Sf, C, a);
+                            add_Ma(cf, Sf, C, a);
                             if (a == bb) {
-                                for (int t = 0; t < ntab; ++t) coef[t] *= 2.0;
-                                apply_terms<NT>(D, coef, ntab, PG, 8, 1 + a, q);
+                                coef_scale(cf, 2.0);
+                                apply_terms<NT>(D, cf, C, PG, 8, 1 + a, q);
                             } else {
-                                apply_terms<NT>(D, coef, ntab, PG, 8, 1 + bb, q);
-                                for (int t = 0; t < ntab; ++t) coef[t] = 0.0;
-                                add_Ma(coef, Sf, C, bb);
-                                apply_terms<NT>(D, coef, ntab, PG, 8, 1 + a, q);
+                                apply_terms<NT>(D, cf, C, PG, 8, 1 + bb, q);
+                                coef_zero(cf);
+                                add_Ma(cf, Sf, C, bb);
+                                apply_terms<NT>(D, cf, C, PG, 8, 1 + a, q);
                             }
-                            for (int t = 0; t < ntab; ++t) coef[t] = 0.0;
-                            add_Mab(coef, Sf, C, a, bb);
-                            apply_terms<NT>(D, coef, ntab, PG, 8, 0, q);
+                            coef_zero(cf);
+                            add_Mab(cf, Sf, C, a, bb);
+                            apply_terms<NT>(D, cf, C, PG, 8, 0, q);
                         }
                     }
                 } else if (role == W_ADJ) {
                     const int v = row8;
                     if (v >= 1 && v <= np) {  // d lambda^a = M' lambda^a + (M^a)' lambda
-                        double coef[kMaxT];
-                        for (int t = 0; t < ntab; ++t) coef[t] = 0.0;
-                        add_Ma(coef, Sa, C, v - 1);
-                        apply_terms<NT>(D, coef, ntab, PGa, 1, 0, q);
+                        Coef cf;
+                        coef_zero(cf);
+                        add_Ma(cf, Sa, C, v - 1);
+                        apply_terms<NT>(D, cf, C, PGa, 1, 0, q);
                     }
                 }
                 if (role != W_IDLE) {
@@ -464,7 +519,7 @@ __global__ void __launch_bounds__(kMaxWarpsT * 32, 1)
     }
 
     // ---- outputs -----------------------------------------------------------------------------------------
-    if (role == W_IDLE) return;
+    if (role != W_IDLE) {
     double F[NT][2];
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
@@ -551,10 +606,12 @@ __global__ void __launch_bounds__(kMaxWarpsT * 32, 1)
             }
         }
     }
+    }  // role != W_IDLE
+    }  // items
 }
 
 struct Plan {
-    int TF, TE, TA, split, warps;
+    int TF, TE, TA, split, warps, nbs;
     size_t smem;
 };
 
@@ -576,10 +633,12 @@ bool make_plan(const DInt& I, bool want_jac, bool want_hess, Plan& pl) {
     }
     pl.warps = std::max(pl.warps, 4);  // idle warps still help assembling the generators
     const size_t FR = (size_t)(n / 8) * 2 * 32, nbasis = 2 * m + nc;
-    const size_t doubles = 2 * (size_t)n * n + 4 * sizeof(Scal) / sizeof(double) + FR + n + 8 * n + nbasis * 8 * n + n + nbasis * n +
-                           (size_t)pl.warps * 2 * FR;
-    pl.smem = doubles * sizeof(double);
-    return pl.smem <= 226 * 1024;
+    const size_t doubles = 2 * (size_t)n * n + 4 * sizeof(Scal) / sizeof(double) + FR + n + 8 * n + nbasis * 8 * n + n + nbasis * n + 12;
+    const size_t budget = 226 * 1024;
+    if (doubles * sizeof(double) > budget) return false;
+    pl.nbs = (int)std::min<size_t>(nbasis, (budget - doubles * sizeof(double)) / ((size_t)n * n * sizeof(double)));
+    pl.smem = (doubles + (size_t)pl.nbs * n * n) * sizeof(double);
+    return I.tdb_scratch != nullptr;
 }
 
 template <int NT>
@@ -592,9 +651,10 @@ void launch_nt(const DProb& P, int ii, const double* Z, const double* mu, double
         configured = true;
     }
     const DInt& I = P.in[ii];
-    dim3 grid((unsigned)(P.nI * P.batch), pl.split ? 2 : 1);
+    const int ctas = std::min(P.nI * P.batch, I.tdb_scratch_ctas / 2);  // persistent: one CTA per SM
+    dim3 grid((unsigned)ctas, pl.split ? 2 : 1);
     kern<<<grid, pl.warps * 32, pl.smem, st>>>(P, ii, Z, mu, f.want_g ? g : nullptr, jac, f.want_jac ? 1 : 0, f.want_hess ? 1 : 0, 8,
-                                               I.steps, pl.TF, pl.TE, pl.TA, pl.split);
+                                               I.steps, pl.TF, pl.TE, pl.TA, pl.split, pl.nbs, I.tdb_scratch);
 }
 
 }  // namespace
