@@ -331,6 +331,7 @@ __global__ void __launch_bounds__(kMaxWarpsT * 32, 1)
                     // on both the straight and the transposed store
                     const int r = (blk / NT) * 4 + (lane >> 3), c = (blk % NT) * 8 + (lane & 7);
                     const int p = sw<NT>(r, c);
+                    asm volatile("" ::: "memory");  // re-read the node scalars from shared memory: hoisting them spills the tiles
                     double vf = I.Grm[p], va = vf;
                     for (int i = 0; i < m; ++i) {
                         const double a = basis_ptr(i)[p], bb = basis_ptr(m + i)[p];
