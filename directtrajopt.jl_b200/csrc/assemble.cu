@@ -458,6 +458,70 @@ __global__ void jac_product_kernel(long long nnz, long long n_rows, long long n_
     }
 }
 
+// Matrix-free J w / J' w of the analytic parts: DerivativeIntegrator rows (one warp per interval) and the stored
+// knot-constraint entries (one thread per listed knot).  J w assigns its rows; J' w adds atomically (several
+// integrators and constraints touch the same variable).
+__global__ void analytic_product_kernel(DProb P, const double* __restrict__ Z, const double* __restrict__ w, double* __restrict__ y,
+                                        int transpose, long long total) {
+    const long long item = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (item >= total) return;
+    const int b = (int)(item / P.nI), kl = (int)(item % P.nI), z = P.z, lane = threadIdx.x & 31;
+    const double* zk = Z + (long long)b * P.n_vars_local + (long long)kl * z;
+    const double dt = zk[P.dt_off];
+    for (int ii = 0; ii < P.n_int; ++ii) {
+        const DInt& I = P.in[ii];
+        if (I.kind != DTO_INT_DERIVATIVE) continue;
+        const int d = I.n;
+        const long long row0 = (long long)b * P.n_cons_local + I.row_off + (long long)kl * d;
+        if (!transpose) {
+            const double* wk = w + (long long)b * P.n_vars_local + (long long)kl * z;
+            for (int a = lane; a < d; a += 32)
+                y[row0 + a] = wk[z + I.x_off + a] - wk[I.x_off + a] - dt * wk[I.u_off + a] - zk[I.u_off + a] * wk[P.dt_off];
+        } else {
+            double* yk = y + (long long)b * P.n_vars_local + (long long)kl * z;
+            double part = 0.0;
+            for (int a = lane; a < d; a += 32) {
+                const double wa = w[row0 + a];
+                atomicAdd(yk + I.x_off + a, -wa);
+                atomicAdd(yk + I.u_off + a, -dt * wa);
+                atomicAdd(yk + z + I.x_off + a, wa);
+                part = fma(zk[I.u_off + a], wa, part);
+            }
+            part = warp_sum(part);
+            if (lane == 0) atomicAdd(yk + P.dt_off, -part);
+        }
+    }
+}
+
+__global__ void constraint_product_kernel(DProb P, int ci, const double* __restrict__ Z, const double* __restrict__ w,
+                                          double* __restrict__ y, int transpose) {
+    const DCon& C = P.co[ci];
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)P.batch * C.nt_own) return;
+    const int b = (int)(t / C.nt_own), j = (int)(t % C.nt_own);
+    const int kl = C.own_knot[j];
+    const double* zk = Z + (long long)b * P.n_vars_local + (long long)kl * P.z;
+    const double* p = C.params + (long long)C.own_ti[j] * C.np;
+    const int nv = C.nv, gd = C.gd;
+    const long long row0 = (long long)b * P.n_cons_local + C.row_off + (long long)j * gd;
+    const long long col0 = (long long)b * P.n_vars_local + (long long)kl * P.z;
+    double acc[16];
+    for (int a = 0; a < gd; ++a) acc[a] = 0.0;
+    HDual out[16];
+    for (int i = 0; i < nv; ++i) {
+        knot_cfun<HDual>(C.fn, SeededVars{zk, C.var_offs, i, -1}, nv, p, out, gd);
+        double col = 0.0;
+        for (int a = 0; a < gd; ++a) {
+            if (C.jac_pos[((long long)j * gd + a) * nv + i] < 0) continue;  // never stored by the reference: not part of J
+            if (!transpose) acc[a] = fma(out[a].d1, w[col0 + C.var_offs[i]], acc[a]);
+            else col = fma(out[a].d1, w[row0 + a], col);
+        }
+        if (transpose) atomicAdd(y + col0 + C.var_offs[i], col);
+    }
+    if (!transpose)
+        for (int a = 0; a < gd; ++a) y[row0 + a] = acc[a];
+}
+
 }  // namespace
 
 void launch_analytic(const DProb& P, const double* Z, double* g, double* jac, EvalFlags f, cudaStream_t st, long long* launches) {
@@ -561,4 +625,21 @@ void launch_jac_product(const DProb& P, const double* jac, const long long* rows
     dim3 grid((unsigned)((P.nnz_jac_local + 255) / 256 > 2368 ? 2368 : (P.nnz_jac_local + 255) / 256), P.batch);
     jac_product_kernel<<<grid, 256, 0, st>>>(P.nnz_jac_local, n_rows, n_cols, jac, rows0, cols0, w, y, transpose ? 1 : 0);
     ++*launches;
+}
+
+void launch_analytic_product(const DProb& P, const double* Z, const double* w, double* y, bool transpose, cudaStream_t st,
+                             long long* launches) {
+    bool any_deriv = false;
+    for (int i = 0; i < P.n_int; ++i) any_deriv |= P.in[i].kind == DTO_INT_DERIVATIVE;
+    if (any_deriv && P.nI > 0) {
+        const long long total = (long long)P.nI * P.batch;
+        analytic_product_kernel<<<(unsigned)((total + 7) / 8), 256, 0, st>>>(P, Z, w, y, transpose ? 1 : 0, total);
+        ++*launches;
+    }
+    for (int ci = 0; ci < P.n_con; ++ci) {
+        const long long tot = (long long)P.batch * P.co[ci].nt_own;
+        if (tot == 0) continue;
+        constraint_product_kernel<<<(unsigned)((tot + 63) / 64), 64, 0, st>>>(P, ci, Z, w, y, transpose ? 1 : 0);
+        ++*launches;
+    }
 }

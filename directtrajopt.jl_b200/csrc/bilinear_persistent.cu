@@ -906,6 +906,293 @@ __global__ void __launch_bounds__(max_warps<NT>() * 32, 1)
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Matrix-free Jacobian products (evaluator.jl:406-456 materialises all Jacobian values first; here the products come
+// straight from the series).  J w: rows [x; w_x; d] with d the directional derivative of exp(dt G(u)) x along
+// (w_u, w_dt): one extra tile product with G_w = sum_i w_ui G_i per term.  J' w: the adjoint rows of role ADJ with
+// mu := w, contracted with x.  No propagator, no second-order rows.
+// ------------------------------------------------------------------------------------------------------------------
+template <int NT>
+__device__ __forceinline__ void product_forward(const Ctx<NT>& c, double* Gw, const double* __restrict__ w, double* __restrict__ y, int b,
+                                                int kk) {
+    constexpr int n = 8 * NT, nn = n * n;
+    const DProb& P = *c.P;
+    const DInt& I = *c.I;
+    const int m = I.m, z = P.z, lane = c.lane, q = lane & 3, row8 = lane >> 2;
+    const double* zk = c.Z + (long long)b * P.n_vars_local + (long long)kk * z;
+    const double* wk = w + (long long)b * P.n_vars_local + (long long)kk * z;
+    const double dt = zk[P.dt_off], wdt = wk[P.dt_off];
+    double uu[kMaxDrives], wu[kMaxDrives];
+#pragma unroll
+    for (int i = 0; i < kMaxDrives; ++i) {
+        uu[i] = i < m ? zk[I.u_off + i] : 0.0;
+        wu[i] = i < m ? wk[I.u_off + i] : 0.0;
+    }
+    const Series ser = choose_series(fabs(dt) * build_generator<NT>(c, uu, m));
+    for (int p = lane; p < nn; p += 32) {
+        double v = 0.0;
+#pragma unroll
+        for (int i = 0; i < kMaxDrives; ++i)
+            if (i < m) v = fma(wu[i], c.Gs[(1 + i) * nn + p], v);
+        Gw[p] = v;
+    }
+    __syncwarp();
+    double F[1][NT][2], term[1][NT][2];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int s = 8 * nt + 2 * q + j;
+            F[0][nt][j] = row8 == 0 ? zk[I.x_off + s] : (row8 == 1 ? wk[I.x_off + s] : 0.0);
+        }
+    for (int st = 0; st < ser.stages; ++st) {
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            term[0][nt][0] = F[0][nt][0];
+            term[0][nt][1] = F[0][nt][1];
+        }
+        for (int t = 1; t <= ser.terms; ++t) {
+            const double cf = dt * ser.inv_stages * kInv[t];
+            double nw[1][NT][2], tmp[1][NT][2];
+            frag_zero(nw);
+            frag_zero(tmp);
+            mma_apply<1, NT, 1>(nw, term, c.Gu, lane);
+            mma_apply<1, NT, 1>(tmp, term, Gw, lane);
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                const double v0 = __shfl_sync(0xffffffffu, tmp[0][nt][0], q);  // row 0 (x) feeds row 2 (d)
+                const double v1 = __shfl_sync(0xffffffffu, tmp[0][nt][1], q);
+                if (row8 == 2) {
+                    nw[0][nt][0] += v0;
+                    nw[0][nt][1] += v1;
+                }
+                term[0][nt][0] = cf * nw[0][nt][0];
+                term[0][nt][1] = cf * nw[0][nt][1];
+                F[0][nt][0] += term[0][nt][0];
+                F[0][nt][1] += term[0][nt][1];
+            }
+        }
+    }
+    double GF[1][NT][2];
+    frag_zero(GF);
+    mma_apply<1, NT, 1>(GF, F, c.Gu, lane);  // row 0: G E x
+    const double* wk1 = wk + z;
+    double* yp = y + (long long)b * P.n_cons_local + I.row_off + (long long)kk * n;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const double f1 = __shfl_sync(0xffffffffu, F[0][nt][j], 4 + q);
+            const double f2 = __shfl_sync(0xffffffffu, F[0][nt][j], 8 + q);
+            if (row8 == 0) {
+                const int s = 8 * nt + 2 * q + j;
+                yp[s] = wk1[I.x_off + s] - (f1 + f2 + wdt * GF[0][nt][j]);
+            }
+        }
+}
+
+template <int NT>
+__device__ __forceinline__ void product_adjoint(const Ctx<NT>& c, const double* __restrict__ w, double* __restrict__ y, int b, int kk) {
+    constexpr int n = 8 * NT, nn = n * n;
+    const DProb& P = *c.P;
+    const DInt& I = *c.I;
+    const int m = I.m, z = P.z, lane = c.lane, q = lane & 3, row8 = lane >> 2;
+    const double* zk = c.Z + (long long)b * P.n_vars_local + (long long)kk * z;
+    const double dt = zk[P.dt_off];
+    double uu[kMaxDrives];
+#pragma unroll
+    for (int i = 0; i < kMaxDrives; ++i) uu[i] = i < m ? zk[I.u_off + i] : 0.0;
+    double cmax = 0.0;
+    for (int k = lane; k < n; k += 32) {
+        double s1 = 0.0;
+        for (int s = 0; s < n; ++s) {
+            const int p = sw<NT>(s, k);
+            double v = c.Gs[p];
+#pragma unroll
+            for (int i = 0; i < kMaxDrives; ++i)
+                if (i < m) v = fma(uu[i], c.Gs[(1 + i) * nn + p], v);
+            s1 += fabs(v);
+        }
+        cmax = fmax(cmax, s1);
+    }
+    const Series ser = choose_series(fabs(dt) * warp_max(cmax));
+    for (int e = lane; e < nn; e += 32) {
+        const int r = e / n, col = e % n;
+        const int p = sw<NT>(r, col);
+        double v = c.Gs[p];
+#pragma unroll
+        for (int i = 0; i < kMaxDrives; ++i)
+            if (i < m) v = fma(uu[i], c.Gs[(1 + i) * nn + p], v);
+        c.Gu[sw<NT>(col, r)] = v;
+    }
+    __syncwarp();
+    const double* wr = w + (long long)b * P.n_cons_local + I.row_off + (long long)kk * n;
+    double* avec = c.vbuf;
+    double* ybuf = c.vbuf + n;
+    double F[1][NT][2], term[1][NT][2];
+    frag_zero(F);
+    if (row8 == 0) {
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            F[0][nt][0] = wr[8 * nt + 2 * q];
+            F[0][nt][1] = wr[8 * nt + 2 * q + 1];
+        }
+    }
+    for (int st = 0; st < ser.stages; ++st) {
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            term[0][nt][0] = F[0][nt][0];
+            term[0][nt][1] = F[0][nt][1];
+        }
+        for (int t = 1; t <= ser.terms; ++t) {
+            const double cf = dt * ser.inv_stages * kInv[t];
+            if (row8 == 0) {
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    avec[8 * nt + 2 * q] = term[0][nt][0];
+                    avec[8 * nt + 2 * q + 1] = term[0][nt][1];
+                }
+            }
+            __syncwarp();
+            for (int s = lane; s < n; s += 32) {
+                double yv[kMaxDrives] = {0.0, 0.0, 0.0, 0.0};
+                for (int k = 0; k < n; k += 2) {
+                    const double2 a2 = *reinterpret_cast<const double2*>(avec + k);
+                    const int p0 = sw<NT>(k, s), p1 = sw<NT>(k + 1, s);
+#pragma unroll
+                    for (int i = 0; i < kMaxDrives; ++i)
+                        if (i < m) {
+                            yv[i] = fma(c.Gs[(1 + i) * nn + p0], a2.x, yv[i]);
+                            yv[i] = fma(c.Gs[(1 + i) * nn + p1], a2.y, yv[i]);
+                        }
+                }
+#pragma unroll
+                for (int i = 0; i < kMaxDrives; ++i)
+                    if (i < m) ybuf[i * n + s] = yv[i];
+            }
+            double nw[1][NT][2];
+            frag_zero(nw);
+            mma_apply<1, NT, 1>(nw, term, c.Gu, lane);
+            __syncwarp();
+            if (row8 >= 1 && row8 <= m) {
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    nw[0][nt][0] += ybuf[(row8 - 1) * n + 8 * nt + 2 * q];
+                    nw[0][nt][1] += ybuf[(row8 - 1) * n + 8 * nt + 2 * q + 1];
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                term[0][nt][0] = cf * nw[0][nt][0];
+                term[0][nt][1] = cf * nw[0][nt][1];
+                F[0][nt][0] += term[0][nt][0];
+                F[0][nt][1] += term[0][nt][1];
+            }
+        }
+    }
+    double GY[1][NT][2];
+    frag_zero(GY);
+    mma_apply<1, NT, 1>(GY, F, c.Gu, lane);  // row 0: G' E' w
+    // x-columns of this knot: -E'w ; of the next knot: +w ; u_i: -x'(L_i' w) ; dt: -x'(G'E'w)
+    double* yk = y + (long long)b * P.n_vars_local + (long long)kk * z;
+    double dx = 0.0, dg = 0.0;  // x . F[row], x . GY[row 0]
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int s = 8 * nt + 2 * q + j;
+            const double xs = zk[I.x_off + s];
+            dx = fma(xs, F[0][nt][j], dx);
+            dg = fma(xs, GY[0][nt][j], dg);
+            if (row8 == 0) {
+                atomicAdd(yk + I.x_off + s, -F[0][nt][j]);
+                atomicAdd(yk + z + I.x_off + s, wr[s]);
+            }
+        }
+    dx = quad_sum(dx);
+    dg = quad_sum(dg);
+    if (q == 0 && row8 >= 1 && row8 <= m) atomicAdd(yk + I.u_off + (row8 - 1), -dx);
+    if (lane == 0) atomicAdd(yk + P.dt_off, -dg);
+}
+
+template <int NT>
+__global__ void __launch_bounds__(max_warps<NT>() * 32, 1)
+    bilinear_product_kernel(DProb P, int ii, const double* __restrict__ Z, const double* __restrict__ w, double* __restrict__ y,
+                            int transpose, unsigned long long* __restrict__ wq, int fetch) {
+    extern __shared__ __align__(16) double sm[];
+    constexpr int n = 8 * NT, nn = n * n;
+    const DInt& I = P.in[ii];
+    const int m = I.m;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int slot = 2 * nn + (1 + kMaxDrives) * n;
+    double* Gs = sm;
+    for (int e = threadIdx.x; e < (m + 1) * nn; e += blockDim.x) {
+        const int i = e / nn, r = e % nn;
+        Gs[i * nn + sw<NT>(r / n, r % n)] = I.Grm[e];
+    }
+    __syncthreads();
+    Ctx<NT> c;
+    c.P = &P;
+    c.I = &I;
+    c.Z = Z;
+    c.mu = nullptr;
+    c.g = nullptr;
+    c.jac = nullptr;
+    c.Gs = Gs;
+    c.Gu = Gs + (size_t)(m + 1) * nn + (size_t)warp * slot;
+    double* Gw = c.Gu + nn;
+    c.vbuf = Gw + nn;
+    c.M3 = c.S2 = nullptr;
+    c.lane = lane;
+    c.want_jac = c.want_hess = 0;
+    const unsigned long long nItems = (unsigned long long)P.batch * (unsigned long long)P.nI;
+    while (true) {
+        unsigned long long id0 = 0;
+        if (lane == 0) id0 = atomicAdd(&wq[0], (unsigned long long)fetch);
+        id0 = __shfl_sync(0xffffffffu, id0, 0);
+        if (id0 >= nItems) break;
+        for (unsigned long long id = id0; id < id0 + fetch && id < nItems; ++id) {
+            const int b = (int)(id / (unsigned long long)P.nI), kk = (int)(id % (unsigned long long)P.nI);
+            __syncwarp();
+            if (transpose) product_adjoint<NT>(c, w, y, b, kk);
+            else product_forward<NT>(c, Gw, w, y, b, kk);
+            __syncwarp();
+        }
+    }
+}
+
+template <int NT>
+bool launch_product_nt(const DProb& P, int ii, const double* Z, const double* w, double* y, bool transpose, cudaStream_t st,
+                       long long* launches) {
+    const DInt& I = P.in[ii];
+    constexpr int n = 8 * NT;
+    const size_t mat = sizeof(double) * (size_t)n * n;
+    const size_t slot = 2 * mat + sizeof(double) * (1 + kMaxDrives) * n;
+    const size_t shared_part = (size_t)(I.m + 1) * mat;
+    const size_t budget = 227 * 1024 - 1024;
+    if (shared_part + slot > budget) return false;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int W = (int)std::min<size_t>(max_warps<NT>(), (budget - shared_part) / slot);
+    const size_t smem = shared_part + (size_t)W * slot;
+    auto kern = bilinear_product_kernel<NT>;
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return false;
+        configured = true;
+    }
+    const long long items = (long long)P.batch * P.nI;
+    const int grid = (int)std::max<long long>(1, std::min<long long>(sms, (items + W - 1) / W));
+    const long long per_warp = items / ((long long)grid * W);
+    const int fetch = (NT <= 2) ? (int)std::max<long long>(1, std::min<long long>(8, per_warp / 8)) : 1;
+    if (cudaMemsetAsync(I.wq, 0, 3 * sizeof(unsigned long long), st) != cudaSuccess) return false;
+    kern<<<grid, W * 32, smem, st>>>(P, ii, Z, w, y, transpose ? 1 : 0, I.wq, fetch);
+    ++*launches;
+    return true;
+}
+
 template <int NT, int MT>
 bool launch_variant(const DProb& P, int ii, const double* Z, const double* mu, double* g, double* jac, EvalFlags f, cudaStream_t st,
                     long long* launches) {
@@ -988,5 +1275,22 @@ bool launch_bilinear_persistent(const DProb& P, int ii, const double* Z, const d
         DTO_DISPATCH(8)
     }
 #undef DTO_DISPATCH
+    return false;
+}
+
+// y (+)= the rows / columns of integrator ii in J w (transpose = false: rows are assigned) or J' w (atomically added)
+bool launch_bilinear_product(const DProb& P, int ii, const double* Z, const double* w, double* y, bool transpose, cudaStream_t st,
+                             long long* launches) {
+    const DInt& I = P.in[ii];
+    if (P.nI <= 0) return true;
+    if (!bilinear_persistent_supported(I.n, I.m) || I.G_stride != 0 || I.wq == nullptr || P.halo != nullptr) return false;
+    switch (I.n / 8) {
+        case 1: return launch_product_nt<1>(P, ii, Z, w, y, transpose, st, launches);
+        case 2: return launch_product_nt<2>(P, ii, Z, w, y, transpose, st, launches);
+        case 3: return launch_product_nt<3>(P, ii, Z, w, y, transpose, st, launches);
+        case 4: return launch_product_nt<4>(P, ii, Z, w, y, transpose, st, launches);
+        case 6: return launch_product_nt<6>(P, ii, Z, w, y, transpose, st, launches);
+        case 8: return launch_product_nt<8>(P, ii, Z, w, y, transpose, st, launches);
+    }
     return false;
 }

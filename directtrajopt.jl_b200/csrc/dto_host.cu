@@ -886,27 +886,32 @@ extern "C" int dto_eval_hessian(dto_handle* h, const double* Z, double sigma, co
     return dto_eval_all(h, Z, sigma, mu, nullptr, nullptr, nullptr, nullptr, vals);
 }
 
+// Products straight from the series for problems made of persistent-variant bilinear integrators, derivative
+// integrators and knot constraints; anything else materialises the Jacobian values first, as the reference does
+// (evaluator.jl:406-456).  DTO_B200_JVP=materialize forces the latter.
+static bool matrix_free_capable(const dto_handle* h) {
+    const DProb& P = h->P;
+    if (h->sharded) return false;
+    const char* env = getenv("DTO_B200_JVP");
+    if (env && strcmp(env, "materialize") == 0) return false;
+    for (int i = 0; i < P.n_int; ++i)
+        if (P.in[i].kind != DTO_INT_DERIVATIVE && !(P.in[i].kind == DTO_INT_BILINEAR && P.in[i].variant == DTO_VAR_PERSISTENT)) return false;
+    return true;
+}
+
 static int jac_product(dto_handle* h, const double* Z, const double* w, double* y, bool transpose) {
     if (!h || !Z || !w || !y) return DTO_ERR_INVALID;
     const DProb& P = h->P;
     const size_t B = (size_t)P.batch;
     CUDA_TRY(h, cudaSetDevice(h->device));
-    if (!h->d_rows0) {
-        std::vector<int64_t> r((size_t)P.nnz_jac_local), c((size_t)P.nnz_jac_local);
-        int rc = dto_jac_structure(h, r.data(), c.data());
-        if (rc != DTO_OK) return rc;
-        // local 0-based rows/cols: a whole-problem handle has local == global numbering
-        if (h->sharded) {
-            h->err = "Jacobian products are not available on knot-range shards";
-            return DTO_ERR_UNSUPPORTED;
-        }
-        for (auto& v : r) v -= 1;
-        for (auto& v : c) v -= 1;
-        h->d_rows0 = (long long*)dev_upload(h, (const long long*)r.data(), r.size());
-        h->d_cols0 = (long long*)dev_upload(h, (const long long*)c.data(), c.size());
+    if (h->sharded) {
+        h->err = "Jacobian products are not available on knot-range shards";
+        return DTO_ERR_UNSUPPORTED;
+    }
+    if (!h->dw) {
         h->dw = dev_upload<double>(h, nullptr, B * (size_t)std::max(P.n_vars_local, P.n_cons_local));
         h->dy = dev_upload<double>(h, nullptr, B * (size_t)std::max(P.n_vars_local, P.n_cons_local));
-        if (!h->d_rows0 || !h->d_cols0 || !h->dw || !h->dy) {
+        if (!h->dw || !h->dy) {
             h->err = "device allocation failed (Jacobian product)";
             return DTO_ERR_ALLOC;
         }
@@ -915,9 +920,33 @@ static int jac_product(dto_handle* h, const double* Z, const double* w, double* 
     const size_t ny = transpose ? (size_t)P.n_vars_local : (size_t)P.n_cons_local;
     CUDA_TRY(h, cudaMemcpyAsync(h->dZ, Z, sizeof(double) * B * P.n_vars_local, cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(h, cudaMemcpyAsync(h->dw, w, sizeof(double) * B * nw, cudaMemcpyHostToDevice, h->stream));
-    int rc = run_eval(h, h->dZ, 0.0, nullptr, nullptr, nullptr, nullptr, h->djac, nullptr);
-    if (rc != DTO_OK) return rc;
-    launch_jac_product(P, h->djac, h->d_rows0, h->d_cols0, h->dw, h->dy, transpose, h->stream, &h->launches);
+    bool done = false;
+    if (matrix_free_capable(h)) {
+        CUDA_TRY(h, cudaMemsetAsync(h->dy, 0, sizeof(double) * B * ny, h->stream));
+        done = true;
+        for (int i = 0; i < P.n_int && done; ++i)
+            if (P.in[i].kind == DTO_INT_BILINEAR) done = launch_bilinear_product(P, i, h->dZ, h->dw, h->dy, transpose, h->stream, &h->launches);
+        if (done) launch_analytic_product(P, h->dZ, h->dw, h->dy, transpose, h->stream, &h->launches);
+    }
+    if (!done) {
+        if (!h->d_rows0) {
+            std::vector<int64_t> r((size_t)P.nnz_jac_local), c((size_t)P.nnz_jac_local);
+            int rc = dto_jac_structure(h, r.data(), c.data());
+            if (rc != DTO_OK) return rc;
+            for (auto& v : r) v -= 1;  // a whole-problem handle has local == global numbering
+            for (auto& v : c) v -= 1;
+            h->d_rows0 = (long long*)dev_upload(h, (const long long*)r.data(), r.size());
+            h->d_cols0 = (long long*)dev_upload(h, (const long long*)c.data(), c.size());
+            if (!h->d_rows0 || !h->d_cols0) {
+                h->err = "device allocation failed (Jacobian product)";
+                return DTO_ERR_ALLOC;
+            }
+        }
+        int rc = run_eval(h, h->dZ, 0.0, nullptr, nullptr, nullptr, nullptr, h->djac, nullptr);
+        if (rc != DTO_OK) return rc;
+        launch_jac_product(P, h->djac, h->d_rows0, h->d_cols0, h->dw, h->dy, transpose, h->stream, &h->launches);
+    }
+    CUDA_TRY(h, cudaGetLastError());
     CUDA_TRY(h, cudaMemcpyAsync(y, h->dy, sizeof(double) * B * ny, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     return DTO_OK;

@@ -113,6 +113,10 @@ bool bilinear_dmma_supported(int n, int m);
 bool launch_bilinear_persistent(const DProb& P, int ii, const double* Z, const double* mu, double* g, double* jac, EvalFlags f,
                                 cudaStream_t st, long long* launches);
 bool bilinear_persistent_supported(int n, int m);
+bool launch_bilinear_product(const DProb& P, int ii, const double* Z, const double* w, double* y, bool transpose, cudaStream_t st,
+                             long long* launches);
+void launch_analytic_product(const DProb& P, const double* Z, const double* w, double* y, bool transpose, cudaStream_t st,
+                             long long* launches);
 bool tdb_available();
 bool tdb_dmma_supported(const DInt& I);
 bool launch_tdb_dmma(const DProb& P, int ii, const double* Z, const double* mu, double* g, double* jac, EvalFlags f, cudaStream_t st,

@@ -150,6 +150,33 @@ def test_jacobian_products(case):
     assert np.allclose(y, Jd.T @ w, atol=1e-10 * max(1, np.abs(Jd.T @ w).max()))
 
 
+def test_matrix_free_products_match_materialised(monkeypatch):
+    """Jacobian-vector products straight from the series (no Jacobian values formed) against the reference's
+    materialise-then-multiply path (evaluator.jl:406-456), on a problem with two integrator kinds and knot
+    constraints with never-stored entries."""
+    big = pt.scaled_problem(N=40, state_dim=16, n_controls=2, generator_scale=0.6)
+    for pr in (big, pt.quantum_gate_problem(N=9, levels=16, n_drives=4)):
+        Z = pr.trajectory.datavec.copy()
+        res = {}
+        for mode in ("", "materialize"):
+            if mode:
+                monkeypatch.setenv("DTO_B200_JVP", mode)
+            else:
+                monkeypatch.delenv("DTO_B200_JVP", raising=False)
+            ev = dto.Evaluator(pr)
+            rng = np.random.default_rng(11)
+            w1, w2 = rng.standard_normal(ev.n_vars), rng.standard_normal(ev.n_constraints)
+            y1, y2 = np.empty(ev.n_constraints), np.empty(ev.n_vars)
+            l0 = ev.launch_count
+            ev.eval_constraint_jacobian_product(y1, Z, w1)
+            ev.eval_constraint_jacobian_transpose_product(y2, Z, w2)
+            res[mode] = (y1, y2, ev.launch_count - l0)
+            ev.close()
+        for a, b in zip(res[""][:2], res["materialize"][:2]):
+            assert relerr(a, b) <= 1e-12
+    monkeypatch.delenv("DTO_B200_JVP", raising=False)
+
+
 def test_features_and_bounds():
     prob = pt.standard_problem(N=6)
     ev = dto.Evaluator(prob, eval_hessian=False)
