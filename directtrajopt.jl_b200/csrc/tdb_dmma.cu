@@ -18,6 +18,8 @@
 // basis products A_i, B_i, D_j times the leading forward tile (needed by the parameter couplings) are spread
 // over the lightly loaded warps, the transposed basis products of lambda run on the FP64 FMA pipe, (3) the
 // couplings are added from the shared tables.  Two block barriers per right-hand side.
+#include <stdlib.h>
+
 #include "dmma_tiles.cuh"
 #include "dto_internal.h"
 
@@ -219,8 +221,58 @@ __device__ __forceinline__ const double* basis_global(const DInt& I, int b, int 
     return I.Dsw + (size_t)(b - 2 * I.m) * nn;
 }
 
-template <int NT>
-__global__ void __launch_bounds__(kMaxWarpsT * 32, 1)
+// G(tau) -> Gf and G(1 - tau)' -> Ga from the drift entries already sitting in Gf (cp.async) and the basis matrices.
+// A 4 x 8 block of the matrix per warp pass: few bank conflicts on both the straight and the transposed store.
+// CACHED: every basis matrix is in the shared cache Bs (plain offset arithmetic in the inner loop).  The node's
+// coefficients u_i cos, u_i sin, carrier cos are lifted into registers first (MM drives, CC carriers at most):
+// the stores to Gf/Ga would otherwise force the compiler to re-read them from shared memory per element.
+template <int NT, bool CACHED, int MM, int CC>
+__device__ __forceinline__ void assemble_generators(double* Gf, double* Ga, const double* Bs, const DInt& I, const Scal& Sf, const Scal& Sa,
+                                                    int m, int nc, bool want_adj, int warp, int nwarps, int lane) {
+    constexpr int n = 8 * NT, nn = n * n;
+    const double* gA = I.Asw;
+    const double* gB = I.Bsw;
+    const double* gD = I.Dsw;
+    double fc[MM], fs[MM], ac[MM], as[MM], fe[CC > 0 ? CC : 1], ae[CC > 0 ? CC : 1];
+#pragma unroll
+    for (int i = 0; i < MM; ++i) {
+        fc[i] = i < m ? Sf.u[i] * Sf.c[i] : 0.0;
+        fs[i] = i < m ? Sf.u[i] * Sf.s[i] : 0.0;
+        ac[i] = i < m ? Sa.u[i] * Sa.c[i] : 0.0;
+        as[i] = i < m ? Sa.u[i] * Sa.s[i] : 0.0;
+    }
+#pragma unroll
+    for (int j = 0; j < CC; ++j) {
+        fe[j] = j < nc ? Sf.e[j] : 0.0;
+        ae[j] = j < nc ? Sa.e[j] : 0.0;
+    }
+    for (int blk = warp; blk < nn / 32; blk += nwarps) {
+        const int r = (blk / NT) * 4 + (lane >> 3), c = (blk % NT) * 8 + (lane & 7);
+        const int p = sw<NT>(r, c);
+        double vf = Gf[p], va = vf;  // the drift entry, prefetched by this very thread
+#pragma unroll
+        for (int i = 0; i < MM; ++i)
+            if (i < m) {
+                const double a = CACHED ? Bs[i * nn + p] : gA[(size_t)i * nn + p];
+                const double bb = CACHED ? Bs[(m + i) * nn + p] : gB[(size_t)i * nn + p];
+                vf = fma(fc[i], a, fma(fs[i], bb, vf));
+                va = fma(ac[i], a, fma(as[i], bb, va));
+            }
+#pragma unroll
+        for (int j = 0; j < CC; ++j)
+            if (j < nc) {
+                const double d = CACHED ? Bs[(2 * m + j) * nn + p] : gD[(size_t)j * nn + p];
+                vf = fma(fe[j], d, vf);
+                va = fma(ae[j], d, va);
+            }
+        Gf[p] = vf;
+        if (want_adj) Ga[sw<NT>(c, r)] = va;
+    }
+}
+
+// MAXW = 8: up to 255 registers per thread (no spills at n = 64); MAXW = 16: 128 registers
+template <int NT, int MAXW>
+__global__ void __launch_bounds__(MAXW * 32, 1)
     tdb_dmma_kernel(DProb P, int ii, const double* __restrict__ Z, const double* __restrict__ mu, double* __restrict__ g,
                     double* __restrict__ jac, int want_jac, int want_hess, int K, int steps, int TF, int TE, int TA, int split, int nbs,
                     double* __restrict__ scratch) {
@@ -276,6 +328,16 @@ __global__ void __launch_bounds__(kMaxWarpsT * 32, 1)
         Bs[i] = basis_global(I, bi, nn)[p];
     }
     auto basis_ptr = [&](int bi) -> const double* { return bi < nbs ? Bs + (size_t)bi * nn : basis_global(I, bi, nn); };
+    // The drift matrix does not fit beside the basis cache: every thread copies the entries it will assemble
+    // from L2 straight into their place in Gf, asynchronously, while the previous right-hand side finishes.
+    auto prefetch_drift = [&]() {
+        for (int blk = warp; blk < nn / 32; blk += nwarps) {
+            const int p = sw<NT>((blk / NT) * 4 + (lane >> 3), (blk % NT) * 8 + (lane & 7));
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(Gf + p);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(I.Grm + p) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
 
     // PG/Pb and PGa/PT are laid out back to back: table t of the forward set is PG + t*8n, of the adjoint set PGa + t*n
 
@@ -304,6 +366,7 @@ __global__ void __launch_bounds__(kMaxWarpsT * 32, 1)
             }
     }
     if (warp == scal_warp && lane < 2) make_scal(I, zk, zk1, P.dt_off, lane == 0 ? 0.0 : 1.0, scal[lane]);
+    prefetch_drift();
     __syncthreads();
 
     double Zp[1][NT][2], Zc[1][NT][2], D[1][NT][2];
@@ -326,26 +389,10 @@ __global__ void __launch_bounds__(kMaxWarpsT * 32, 1)
                 const Scal& Sf = scal[(e & 1) * 2];
                 const Scal& Sa = scal[(e & 1) * 2 + 1];
                 // ---- phase 1: generators of this node, published operands --------------------------------
-                for (int blk = warp; blk < nn / 32; blk += nwarps) {
-                    // a 4 x 8 block of the matrix per warp pass: 64-byte global segments, few bank conflicts
-                    // on both the straight and the transposed store
-                    const int r = (blk / NT) * 4 + (lane >> 3), c = (blk % NT) * 8 + (lane & 7);
-                    const int p = sw<NT>(r, c);
-                    asm volatile("" ::: "memory");  // re-read the node scalars from shared memory: hoisting them spills the tiles
-                    double vf = I.Grm[p], va = vf;
-                    for (int i = 0; i < m; ++i) {
-                        const double a = basis_ptr(i)[p], bb = basis_ptr(m + i)[p];
-                        vf = fma(Sf.u[i], fma(Sf.c[i], a, Sf.s[i] * bb), vf);
-                        va = fma(Sa.u[i], fma(Sa.c[i], a, Sa.s[i] * bb), va);
-                    }
-                    for (int j = 0; j < nc; ++j) {
-                        const double d = basis_ptr(2 * m + j)[p];
-                        vf = fma(Sf.e[j], d, vf);
-                        va = fma(Sa.e[j], d, va);
-                    }
-                    Gf[p] = vf;
-                    if (TA > 0) Ga[sw<NT>(c, r)] = va;
-                }
+                asm volatile("cp.async.wait_all;" ::: "memory");
+                if (nbs == nbasis && m <= 2 && nc == 0) assemble_generators<NT, true, 2, 0>(Gf, Ga, Bs, I, Sf, Sa, m, nc, TA > 0, warp, nwarps, lane);
+                else if (nbs == nbasis) assemble_generators<NT, true, kMaxM, kMaxC>(Gf, Ga, Bs, I, Sf, Sa, m, nc, TA > 0, warp, nwarps, lane);
+                else assemble_generators<NT, false, kMaxM, kMaxC>(Gf, Ga, Bs, I, Sf, Sa, m, nc, TA > 0, warp, nwarps, lane);
                 if (role == W_FWD && tile == 0 && couple) {
 #pragma unroll
                     for (int nt = 0; nt < NT; ++nt) {
@@ -446,6 +493,7 @@ __global__ void __launch_bounds__(kMaxWarpsT * 32, 1)
                     }
                 }
                 __syncthreads();
+                prefetch_drift();  // Gf is free again: fetch the drift entries of the next node
                 // ---- phase 3: parameter couplings, midpoint update ---------------------------------------
                 if (role == W_FWD && couple) {
                     const int v = 8 * tile + row8;
@@ -625,12 +673,23 @@ bool make_plan(const DInt& I, bool want_jac, bool want_hess, Plan& pl) {
     pl.TF = (nvecF + 7) / 8;
     pl.TE = want_jac ? n / 8 : 0;
     pl.TA = want_hess ? 1 : 0;
+    // one CTA per interval if its tiles fit 8 warps (255 registers each); else two CTAs per interval (forward +
+    // adjoint tiles / propagator tiles) if each half fits 8 warps: both assemble the generators, neither spills;
+    // else 16 warps at 128 registers
     pl.split = 0;
     pl.warps = pl.TF + pl.TE + pl.TA;
-    if (pl.warps > kMaxWarpsT) {
-        pl.split = 1;
-        pl.warps = std::max(pl.TF + pl.TA, pl.TE);
-        if (pl.warps > kMaxWarpsT) return false;
+    if (pl.warps > 8) {
+        const int half = std::max(pl.TF + pl.TA, pl.TE);
+        const char* env = getenv("DTO_B200_TDB_SPLIT");  // A/B switch: 0 = one 16-warp CTA (128 registers) instead of two 8-warp CTAs (255 registers)
+        const bool allow_split = !(env && env[0] == '0');
+        if (half <= 8 && pl.TE > 0 && (allow_split || pl.warps > kMaxWarpsT)) {
+            pl.split = 1;
+            pl.warps = half;
+        } else if (pl.warps > kMaxWarpsT) {
+            pl.split = 1;
+            pl.warps = half;
+            if (pl.warps > kMaxWarpsT) return false;
+        }
     }
     pl.warps = std::max(pl.warps, 4);  // idle warps still help assembling the generators
     const size_t FR = (size_t)(n / 8) * 2 * 32, nbasis = 2 * m + nc;
@@ -642,10 +701,10 @@ bool make_plan(const DInt& I, bool want_jac, bool want_hess, Plan& pl) {
     return I.tdb_scratch != nullptr;
 }
 
-template <int NT>
-void launch_nt(const DProb& P, int ii, const double* Z, const double* mu, double* g, double* jac, EvalFlags f, cudaStream_t st,
-               const Plan& pl) {
-    auto kern = tdb_dmma_kernel<NT>;
+template <int NT, int MAXW>
+void launch_nt_w(const DProb& P, int ii, const double* Z, const double* mu, double* g, double* jac, EvalFlags f, cudaStream_t st,
+                 const Plan& pl) {
+    auto kern = tdb_dmma_kernel<NT, MAXW>;
     static bool configured = false;
     if (!configured) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -656,6 +715,13 @@ void launch_nt(const DProb& P, int ii, const double* Z, const double* mu, double
     dim3 grid((unsigned)ctas, pl.split ? 2 : 1);
     kern<<<grid, pl.warps * 32, pl.smem, st>>>(P, ii, Z, mu, f.want_g ? g : nullptr, jac, f.want_jac ? 1 : 0, f.want_hess ? 1 : 0, 8,
                                                I.steps, pl.TF, pl.TE, pl.TA, pl.split, pl.nbs, I.tdb_scratch);
+}
+
+template <int NT>
+void launch_nt(const DProb& P, int ii, const double* Z, const double* mu, double* g, double* jac, EvalFlags f, cudaStream_t st,
+               const Plan& pl) {
+    if (pl.warps <= 8) launch_nt_w<NT, 8>(P, ii, Z, mu, g, jac, f, st, pl);
+    else launch_nt_w<NT, 16>(P, ii, Z, mu, g, jac, f, st, pl);
 }
 
 }  // namespace
