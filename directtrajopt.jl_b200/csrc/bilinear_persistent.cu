@@ -209,6 +209,60 @@ __device__ __forceinline__ double build_generator(const Ctx<NT>& c, const double
     return warp_max(cmax);
 }
 
+// y_i = G_i' a for every drive on the FP64 FMA pipe (one vector times m matrices would waste 7/8 of a DMMA tile).
+// Lane s reads column s of G_i, i.e. consecutive elements of row k of the row-major matrix: conflict-free.
+// For n < 32 the contraction index is split over the 32/n lane groups and reduced with shuffles, so that all
+// lanes (not n of 32) carry FMAs.
+template <int NT>
+__device__ __forceinline__ void adjoint_drive_products(const double* __restrict__ Gs, const double* __restrict__ avec,
+                                                       double* __restrict__ ybuf, int m, int lane) {
+    constexpr int n = 8 * NT, nn = n * n;
+    if constexpr (n >= 32) {
+        for (int s = lane; s < n; s += 32) {
+            double y[kMaxDrives] = {0.0, 0.0, 0.0, 0.0};
+            for (int k = 0; k < n; k += 2) {
+                const double2 a2 = *reinterpret_cast<const double2*>(avec + k);
+                const int p0 = sw<NT>(k, s), p1 = sw<NT>(k + 1, s);
+#pragma unroll
+                for (int i = 0; i < kMaxDrives; ++i)
+                    if (i < m) {
+                        y[i] = fma(Gs[(1 + i) * nn + p0], a2.x, y[i]);
+                        y[i] = fma(Gs[(1 + i) * nn + p1], a2.y, y[i]);
+                    }
+            }
+#pragma unroll
+            for (int i = 0; i < kMaxDrives; ++i)
+                if (i < m) ybuf[i * n + s] = y[i];
+        }
+    } else {
+        constexpr int KS = 32 / n;       // lane groups (n = 8: 4, n = 16: 2, n = 24: 1)
+        constexpr int KL = n / KS;       // contraction indices per group
+        const int s = lane % n, part = lane / n;
+        double y[kMaxDrives] = {0.0, 0.0, 0.0, 0.0};
+        if (part < KS) {
+#pragma unroll
+            for (int kk = 0; kk < KL; kk += 2) {
+                const int k = part * KL + kk;
+                const double2 a2 = *reinterpret_cast<const double2*>(avec + k);
+                const int p0 = sw<NT>(k, s), p1 = sw<NT>(k + 1, s);
+#pragma unroll
+                for (int i = 0; i < kMaxDrives; ++i)
+                    if (i < m) {
+                        y[i] = fma(Gs[(1 + i) * nn + p0], a2.x, y[i]);
+                        y[i] = fma(Gs[(1 + i) * nn + p1], a2.y, y[i]);
+                    }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < kMaxDrives; ++i)
+            if (i < m) {
+#pragma unroll
+                for (int off = n; off < 32 && off < n * KS; off <<= 1) y[i] += __shfl_xor_sync(0xffffffffu, y[i], off);
+                if (lane < n) ybuf[i * n + s] = y[i];
+            }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // FWD
 // ------------------------------------------------------------------------------------------------------------------
@@ -731,22 +785,7 @@ __device__ __forceinline__ void role_adjoint(const Ctx<NT>& c, int b, int kk) {
                 }
             }
             __syncwarp();
-            for (int s = lane; s < n; s += 32) {
-                double y[kMaxDrives] = {0.0, 0.0, 0.0, 0.0};
-                for (int k = 0; k < n; k += 2) {
-                    const double2 a2 = *reinterpret_cast<const double2*>(avec + k);
-                    const int p0 = sw<NT>(k, s), p1 = sw<NT>(k + 1, s);
-#pragma unroll
-                    for (int i = 0; i < kMaxDrives; ++i)
-                        if (i < m) {
-                            y[i] = fma(c.Gs[(1 + i) * nn + p0], a2.x, y[i]);
-                            y[i] = fma(c.Gs[(1 + i) * nn + p1], a2.y, y[i]);
-                        }
-                }
-#pragma unroll
-                for (int i = 0; i < kMaxDrives; ++i)
-                    if (i < m) ybuf[i * n + s] = y[i];
-            }
+            adjoint_drive_products<NT>(c.Gs, avec, ybuf, m, lane);
             double nw[1][NT][2];
             frag_zero(nw);
             mma_apply<1, NT, 1>(nw, term, c.Gu, lane);
@@ -1054,22 +1093,7 @@ __device__ __forceinline__ void product_adjoint(const Ctx<NT>& c, const double* 
                 }
             }
             __syncwarp();
-            for (int s = lane; s < n; s += 32) {
-                double yv[kMaxDrives] = {0.0, 0.0, 0.0, 0.0};
-                for (int k = 0; k < n; k += 2) {
-                    const double2 a2 = *reinterpret_cast<const double2*>(avec + k);
-                    const int p0 = sw<NT>(k, s), p1 = sw<NT>(k + 1, s);
-#pragma unroll
-                    for (int i = 0; i < kMaxDrives; ++i)
-                        if (i < m) {
-                            yv[i] = fma(c.Gs[(1 + i) * nn + p0], a2.x, yv[i]);
-                            yv[i] = fma(c.Gs[(1 + i) * nn + p1], a2.y, yv[i]);
-                        }
-                }
-#pragma unroll
-                for (int i = 0; i < kMaxDrives; ++i)
-                    if (i < m) ybuf[i * n + s] = yv[i];
-            }
+            adjoint_drive_products<NT>(c.Gs, avec, ybuf, m, lane);
             double nw[1][NT][2];
             frag_zero(nw);
             mma_apply<1, NT, 1>(nw, term, c.Gu, lane);
