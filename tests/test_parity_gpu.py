@@ -42,6 +42,16 @@ def catalogue_problem(N=7, seed=3):
     return dto.DirectTrajOptProblem(traj, J, integrators, constraints=cons)
 
 
+def zero_drive_problem(n=16, N=4):
+    """A drive whose matrix is identically zero (all u-derivatives vanish but the columns stay in the structure)."""
+    rng = np.random.default_rng(3)
+    G0 = rng.standard_normal((n, n)) / n
+    traj = dto.NamedTrajectory({"x": rng.standard_normal((n, N)), "u": rng.standard_normal((1, N)), "dt": np.full(N, 0.1)},
+                               timestep="dt", controls=("u",))
+    return dto.DirectTrajOptProblem(traj, dto.QuadraticRegularizer("u", traj, 1.0),
+                                    dto.BilinearIntegrator(lambda u: G0 + u[0] * np.zeros((n, n)), "x", "u", traj))
+
+
 PROBLEMS = {
     "readme_c1": lambda: pt.readme_problem(N=50),
     "catalogue": catalogue_problem,
@@ -59,6 +69,15 @@ PROBLEMS = {
     "gate_n6": lambda: pt.quantum_gate_problem(N=7, levels=3, n_drives=2),
     "gate_n64": lambda: pt.quantum_gate_problem(N=5, levels=32, n_drives=2),
     "linreg": lambda: pt.linear_regularizer_problem(N=8),
+    # edge cases: the shortest trajectory, all drives and Hessian rows at n = 48/64 (series-mode propagator),
+    # scaling-and-squaring (theta = 3) and multi-stage series (theta = 12), a zero drive matrix
+    "N2_n8": lambda: pt.scaled_problem(N=2, state_dim=8, n_controls=2),
+    "N2_readme": lambda: pt.readme_problem(N=2),
+    "n64_m4": lambda: pt.scaled_problem(N=3, state_dim=64, n_controls=4, generator_scale=0.4),
+    "n48_m4": lambda: pt.scaled_problem(N=3, state_dim=48, n_controls=4, generator_scale=0.4),
+    "n32_theta3": lambda: pt.scaled_problem(N=4, state_dim=32, n_controls=3, generator_scale=3.0),
+    "n16_theta12": lambda: pt.scaled_problem(N=4, state_dim=16, n_controls=2, generator_scale=12.0),
+    "zero_drive_n16": zero_drive_problem,
 }
 
 
