@@ -79,6 +79,26 @@ def build_problem(workload, seed):
     return dto.problem_templates.scaled_problem(seed=seed, **kw)
 
 
+def workload_config(workload, prob, mode):
+    """The `config` both arms print (identical strings: the driver pairs the two lines by it).  Sizes are the
+    closed-form counts of SURVEY.md section 8a (the bench workloads have no knot constraints)."""
+    t = prob.trajectory
+    n, m, z, N = t.dims["x"], t.dims["u"], t.dim, t.N
+    dsum = sum(i.x_dim for i in prob.integrators)
+    rows, jac = (N - 1) * dsum, (N - 1) * dsum * 2 * z
+    hess = N * z * (z + 1) // 2 + (N - 1) * z * z
+    batch = WORKLOADS[workload].get("batch")
+    return {
+        "workload": f"{workload}: " + ("bilinear quantum gate" if mode == "replicas" else "random dense bilinear (make_scaled_problem)") +
+                    f", state dim {n}, {m} drives, N={N}" + (f", batch {batch}" if batch else "") +
+                    f" (z={z}; per problem: {N * z} vars, {rows} rows, {jac} Jac nnz, {hess} Hess nnz)",
+        "per_rank": {"replicas": "one independent problem per GPU (problem-parallel, no collective)",
+                     "knot_shards": "contiguous knot range of ONE trajectory per GPU; one-knot halo read through a CUDA-IPC peer pointer (NVLink) inside the kernels; NCCL all-reduce of 2 scalars (objective, violation) per step",
+                     "batch_split": "contiguous block of the problem batch per GPU (no collective)"}[mode],
+        "step": "objective+gradient+constraint+Jacobian+Hessian of one iterate",
+    }
+
+
 class ClockSampler(threading.Thread):
     """Samples nvidia-smi SM clocks and throttle reasons while the timed region runs."""
 
@@ -136,7 +156,7 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "full NLP evals/sec (constraint+Jacobian+Hessian)", "value": v, "unit": "evals/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / v, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: bilinear quantum gate, state dim {t.dims['x']}, {t.dims['u']} drives, N={t.N}, free dt + MinimumTime"},
+        "config": workload_config(args.workload, prob, {"c2": "replicas", "c4": "knot_shards", "c5": "batch_split"}[args.workload]),
         "cpu_baseline": {"value": v, "unit": "evals/s", "cores": info["threads"], "kind": "port", "sample": info["sample"]},
         "e2e": {"value": v, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "reference is Julia (absent here and on the GPU box); this arm times oracle/dto_oracle.c, a C restatement of the reference's ForwardDiff-through-expv algorithm, POSIX threads over knot intervals, all host cores",
@@ -311,18 +331,11 @@ def main():
             "metric": "full NLP evals/sec (constraint+Jacobian+Hessian)", "value": value, "unit": "evals/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak" if mode == "replicas" else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {
-                "workload": f"{args.workload}: " + ("bilinear quantum gate" if mode == "replicas" else "random dense bilinear (make_scaled_problem)") +
-                            f", state dim {n}, {m} drives, N={t.N}" + (f", batch {WORKLOADS[args.workload]['batch']}" if mode == "batch_split" else "") +
-                            f" (z={t.dim}; rank 0: {ev.n_vars} vars, {ev.n_constraints} rows, {ev.nnz_jacobian} Jac nnz, {ev.nnz_hessian} Hess nnz per problem)",
-                "per_rank": {"replicas": "one independent problem per GPU (problem-parallel, no collective)",
-                             "knot_shards": "contiguous knot range of ONE trajectory per GPU; one-knot halo read through a CUDA-IPC peer pointer (NVLink) inside the kernels; NCCL all-reduce of 2 scalars (objective, violation) per step",
-                             "batch_split": "contiguous block of the problem batch per GPU (no collective)"}[mode],
-                "l2": "256 MB memset between timed steps (outside the per-step CUDA events)",
-                "step": "objective+gradient+constraint+Jacobian+Hessian of one iterate, outputs left in HBM",
-                "kernel_variant": ev.kernel_variant(0),
-                "e2e_path": "dto_eval_all with pinned host buffers; knot-range pipeline (D2H of finished ranges overlaps the next range) unless DTO_B200_PIPELINE=0",
-            },
+            "config": dict(workload_config(args.workload, prob, mode),
+                           l2="256 MB memset between timed steps (outside the per-step CUDA events)",
+                           outputs="value: outputs left in HBM (dto_eval_all_dev); e2e: dto_eval_all with pinned host buffers, knot-range pipeline "
+                                   "(D2H of finished ranges overlaps the next range) unless DTO_B200_PIPELINE=0",
+                           kernel_variant=ev.kernel_variant(0)),
             "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_s_max / args.steps * 1e3, "matches_device_path": same},
             "gpu_launches": int(launches),
