@@ -352,7 +352,7 @@ def main():
             },
             "wall_s_timed_region": t_wall,
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:  # the CPU baseline is timed on rank 0 of the single-GPU run only
             try:
                 threads = os.cpu_count() or 1
                 rate, info = cpu_port_rate(prob, args.cpu_sample, threads)

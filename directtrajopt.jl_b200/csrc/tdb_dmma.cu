@@ -246,27 +246,37 @@ __device__ __forceinline__ void assemble_generators(double* Gf, double* Ga, cons
         fe[j] = j < nc ? Sf.e[j] : 0.0;
         ae[j] = j < nc ? Sa.e[j] : 0.0;
     }
-    for (int blk = warp; blk < nn / 32; blk += nwarps) {
-        const int r = (blk / NT) * 4 + (lane >> 3), c = (blk % NT) * 8 + (lane & 7);
+    // two adjacent columns per thread (16-byte loads and stores; a swizzled pair stays adjacent): an 8 x 8 block of
+    // the matrix per warp pass
+    for (int blk = warp; blk < nn / 64; blk += nwarps) {
+        const int r = (blk / NT) * 8 + (lane >> 2), c = (blk % NT) * 8 + 2 * (lane & 3);
         const int p = sw<NT>(r, c);
-        double vf = Gf[p], va = vf;  // the drift entry, prefetched by this very thread
+        const double2 g0 = *reinterpret_cast<const double2*>(Gf + p);  // the drift entries, prefetched by this very thread
+        double vf0 = g0.x, vf1 = g0.y, va0 = g0.x, va1 = g0.y;
 #pragma unroll
         for (int i = 0; i < MM; ++i)
             if (i < m) {
-                const double a = CACHED ? Bs[i * nn + p] : gA[(size_t)i * nn + p];
-                const double bb = CACHED ? Bs[(m + i) * nn + p] : gB[(size_t)i * nn + p];
-                vf = fma(fc[i], a, fma(fs[i], bb, vf));
-                va = fma(ac[i], a, fma(as[i], bb, va));
+                const double2 a = *reinterpret_cast<const double2*>((CACHED ? Bs + i * nn : gA + (size_t)i * nn) + p);
+                const double2 bb = *reinterpret_cast<const double2*>((CACHED ? Bs + (m + i) * nn : gB + (size_t)i * nn) + p);
+                vf0 = fma(fc[i], a.x, fma(fs[i], bb.x, vf0));
+                vf1 = fma(fc[i], a.y, fma(fs[i], bb.y, vf1));
+                va0 = fma(ac[i], a.x, fma(as[i], bb.x, va0));
+                va1 = fma(ac[i], a.y, fma(as[i], bb.y, va1));
             }
 #pragma unroll
         for (int j = 0; j < CC; ++j)
             if (j < nc) {
-                const double d = CACHED ? Bs[(2 * m + j) * nn + p] : gD[(size_t)j * nn + p];
-                vf = fma(fe[j], d, vf);
-                va = fma(ae[j], d, va);
+                const double2 d = *reinterpret_cast<const double2*>((CACHED ? Bs + (2 * m + j) * nn : gD + (size_t)j * nn) + p);
+                vf0 = fma(fe[j], d.x, vf0);
+                vf1 = fma(fe[j], d.y, vf1);
+                va0 = fma(ae[j], d.x, va0);
+                va1 = fma(ae[j], d.y, va1);
             }
-        Gf[p] = vf;
-        if (want_adj) Ga[sw<NT>(c, r)] = va;
+        *reinterpret_cast<double2*>(Gf + p) = make_double2(vf0, vf1);
+        if (want_adj) {
+            Ga[sw<NT>(c, r)] = va0;
+            Ga[sw<NT>(c + 1, r)] = va1;
+        }
     }
 }
 
@@ -331,10 +341,10 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
     // The drift matrix does not fit beside the basis cache: every thread copies the entries it will assemble
     // from L2 straight into their place in Gf, asynchronously, while the previous right-hand side finishes.
     auto prefetch_drift = [&]() {
-        for (int blk = warp; blk < nn / 32; blk += nwarps) {
-            const int p = sw<NT>((blk / NT) * 4 + (lane >> 3), (blk % NT) * 8 + (lane & 7));
+        for (int blk = warp; blk < nn / 64; blk += nwarps) {
+            const int p = sw<NT>((blk / NT) * 8 + (lane >> 2), (blk % NT) * 8 + 2 * (lane & 3));
             const unsigned dst = (unsigned)__cvta_generic_to_shared(Gf + p);
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(I.Grm + p) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(I.Grm + p) : "memory");
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
