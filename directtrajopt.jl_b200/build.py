@@ -17,7 +17,8 @@ OBJDIR = os.path.join(HERE, "lib", "obj")
 LIB = os.path.join(LIBDIR, "libdto_b200.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
-NVCC_FLAGS = [
+# DTO_EXTRA_NVCC_FLAGS: extra flags for debug builds (e.g. -DDTO_TDB_PROFILE); part of the rebuild key
+NVCC_FLAGS = os.environ.get("DTO_EXTRA_NVCC_FLAGS", "").split() + [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC",

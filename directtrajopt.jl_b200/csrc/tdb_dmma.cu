@@ -168,12 +168,12 @@ __device__ __forceinline__ void axpy_row(double (&D)[1][NT][2], double cf, const
         D[0][nt][1] = fma(cf, x.y, D[0][nt][1]);
     }
 }
-// D += sum_t coef[t] * T_t[row]  (tables are [t][rows][n])
+// D += sum_t coef[t] * T_t[row]  (tables are [t][rows][stride])
 template <int NT>
-__device__ __forceinline__ void apply_terms(double (&D)[1][NT][2], const Coef& c, const Ctx& C, const double* tab, int rows, int row, int q) {
-    constexpr int n = 8 * NT;
-    const double* base = tab + (size_t)row * n + 2 * q;
-    const size_t ts = (size_t)rows * n;
+__device__ __forceinline__ void apply_terms(double (&D)[1][NT][2], const Coef& c, const Ctx& C, const double* tab, int rows, int stride,
+                                            int row, int q) {
+    const double* base = tab + (size_t)row * stride + 2 * q;
+    const size_t ts = (size_t)rows * stride;
     axpy_row<NT>(D, c.g, base);
 #pragma unroll
     for (int i = 0; i < kMaxM; ++i)
@@ -187,6 +187,11 @@ __device__ __forceinline__ void apply_terms(double (&D)[1][NT][2], const Coef& c
 }
 
 enum { W_FWD = 0, W_EXP = 1, W_ADJ = 2, W_IDLE = 3 };
+
+#ifdef DTO_TDB_PROFILE
+// debug build only (DTO_EXTRA_NVCC_FLAGS=-DDTO_TDB_PROFILE): cycles of CTA x = 0 per warp and segment of a right-hand side
+__device__ unsigned long long g_tdb_prof[2][16][8];
+#endif
 
 // out += V * M' for one tile, the output n-tiles in two halves (half the B fragments live at a time)
 template <int NT>
@@ -314,9 +319,12 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
     Scal* scal = reinterpret_cast<Scal*>(Ga + nn);            // [2 buffers][forward, adjoint]
     double* pub0 = reinterpret_cast<double*>(scal + 4);       // leading forward tile in fragment order
     double* lam = pub0 + FR;                                  // lambda (n)
-    double* PG = lam + n;                                     // [8][n]    G Z_v (before the dt factor)
-    double* Pb = PG + 8 * n;                                  // [nbasis][8][n]
-    double* PGa = Pb + (size_t)nbasis * 8 * n;                // [n]       G' lambda
+    // table rows are n + 2 doubles apart: the couplings read a different row per lane group, and this stride
+    // spreads the 32 16-byte reads of one LDS.128 evenly over the banks
+    constexpr int TS = n + 2;
+    double* PG = lam + n;                                     // [8][TS]   G Z_v (before the dt factor)
+    double* Pb = PG + 8 * TS;                                 // [nbasis][8][TS]
+    double* PGa = Pb + (size_t)nbasis * 8 * TS;               // [n]       G' lambda
     double* PT = PGa + n;                                     // [nbasis][n] basis' lambda
     double* wk = PT + (size_t)nbasis * n;                     // [kMaxCols] extrapolation weights
     double* Bs = wk + kMaxCols + (kMaxCols & 1);              // the first nbs basis matrices, cached for the CTA's lifetime
@@ -399,7 +407,13 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
                 const Scal& Sf = scal[(e & 1) * 2];
                 const Scal& Sa = scal[(e & 1) * 2 + 1];
                 // ---- phase 1: generators of this node, published operands --------------------------------
+#ifdef DTO_TDB_PROFILE
+                long long tp0 = clock64();
+#endif
                 asm volatile("cp.async.wait_all;" ::: "memory");
+#ifdef DTO_TDB_PROFILE
+                long long tp1 = clock64();
+#endif
                 if (nbs == nbasis && m <= 2 && nc == 0) assemble_generators<NT, true, 2, 0>(Gf, Ga, Bs, I, Sf, Sa, m, nc, TA > 0, warp, nwarps, lane);
                 else if (nbs == nbasis) assemble_generators<NT, true, kMaxM, kMaxC>(Gf, Ga, Bs, I, Sf, Sa, m, nc, TA > 0, warp, nwarps, lane);
                 else assemble_generators<NT, false, kMaxM, kMaxC>(Gf, Ga, Bs, I, Sf, Sa, m, nc, TA > 0, warp, nwarps, lane);
@@ -417,7 +431,13 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
                         lam[8 * nt + 2 * q + 1] = Zc[0][nt][1];
                     }
                 }
+#ifdef DTO_TDB_PROFILE
+                long long tp2 = clock64();
+#endif
                 __syncthreads();
+#ifdef DTO_TDB_PROFILE
+                long long tp3 = clock64();
+#endif
                 // ---- phase 2: products ------------------------------------------------------------------
                 if (warp == scal_warp && lane < 2) {  // scalars of the next node, into the other buffer
                     bool has_next = true;
@@ -444,7 +464,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
                     for (int bi = 0; bi < nbasis; ++bi) {
                         if ((TF + bi) % nwarps != warp) continue;
                         const double* Mb = basis_ptr(bi);
-                        double* out = Pb + (size_t)bi * 8 * n + (size_t)row8 * n + 2 * q;
+                        double* out = Pb + (size_t)bi * 8 * TS + (size_t)row8 * TS + 2 * q;
 #pragma unroll
                         for (int half = 0; half < 2; ++half) {
                             constexpr int NH = (NT + 1) / 2;
@@ -457,15 +477,16 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
                             for (int t = 0; t < NT; ++t) {
                                 const double a0 = pub0[(t * 2) * 32 + lane], a1 = pub0[(t * 2 + 1) * 32 + lane];
                                 const int off = 8 * t + ((t & 1) ? -dsw : dsw);
+                                double2 bf[NH];
 #pragma unroll
-                                for (int x = 0; x < NH; ++x) {
-                                    const int nt = half * NH + x;
-                                    if (nt < NT) {
-                                        const double2 bf = *reinterpret_cast<const double2*>(base + 8 * nt * n + off);
-                                        dmma(acc[x][0], acc[x][1], a0, bf.x);
-                                        dmma(acc[x][0], acc[x][1], a1, bf.y);
-                                    }
-                                }
+                                for (int x = 0; x < NH; ++x)
+                                    if (half * NH + x < NT) bf[x] = *reinterpret_cast<const double2*>(base + 8 * (half * NH + x) * n + off);
+#pragma unroll
+                                for (int x = 0; x < NH; ++x)
+                                    if (half * NH + x < NT) dmma(acc[x][0], acc[x][1], a0, bf[x].x);
+#pragma unroll
+                                for (int x = 0; x < NH; ++x)
+                                    if (half * NH + x < NT) dmma(acc[x][0], acc[x][1], a1, bf[x].y);
                             }
 #pragma unroll
                             for (int x = 0; x < NH; ++x) {
@@ -484,8 +505,8 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
                     if (role == W_FWD && tile == 0 && couple) {
 #pragma unroll
                         for (int nt = 0; nt < NT; ++nt) {
-                            PG[row8 * n + 8 * nt + 2 * q] = D[0][nt][0];
-                            PG[row8 * n + 8 * nt + 2 * q + 1] = D[0][nt][1];
+                            PG[row8 * TS + 8 * nt + 2 * q] = D[0][nt][0];
+                            PG[row8 * TS + 8 * nt + 2 * q + 1] = D[0][nt][1];
                         }
                     }
                     if (role == W_ADJ && row8 == 0) {
@@ -502,7 +523,13 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
                         D[0][nt][1] *= dts;
                     }
                 }
+#ifdef DTO_TDB_PROFILE
+                long long tp4 = clock64();
+#endif
                 __syncthreads();
+#ifdef DTO_TDB_PROFILE
+                long long tp5 = clock64();
+#endif
                 prefetch_drift();  // Gf is free again: fetch the drift entries of the next node
                 // ---- phase 3: parameter couplings, midpoint update ---------------------------------------
                 if (role == W_FWD && couple) {
@@ -512,7 +539,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
                         coef_zero(cf);
                         if (v <= np) {  // first-order row a: (dM/dtheta_a) x
                             add_Ma(cf, Sf, C, v - 1);
-                            apply_terms<NT>(D, cf, C, PG, 8, 0, q);
+                            apply_terms<NT>(D, cf, C, PG, 8, TS, 0, q);
                         } else {  // pair (a, bb): M_a Z_bb + M_bb Z_a + M_ab x
                             int p = v - 1 - np, a = 0;
                             while (p >= np - a) {
@@ -523,16 +550,16 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
                             add_Ma(cf, Sf, C, a);
                             if (a == bb) {
                                 coef_scale(cf, 2.0);
-                                apply_terms<NT>(D, cf, C, PG, 8, 1 + a, q);
+                                apply_terms<NT>(D, cf, C, PG, 8, TS, 1 + a, q);
                             } else {
-                                apply_terms<NT>(D, cf, C, PG, 8, 1 + bb, q);
+                                apply_terms<NT>(D, cf, C, PG, 8, TS, 1 + bb, q);
                                 coef_zero(cf);
                                 add_Ma(cf, Sf, C, bb);
-                                apply_terms<NT>(D, cf, C, PG, 8, 1 + a, q);
+                                apply_terms<NT>(D, cf, C, PG, 8, TS, 1 + a, q);
                             }
                             coef_zero(cf);
                             add_Mab(cf, Sf, C, a, bb);
-                            apply_terms<NT>(D, cf, C, PG, 8, 0, q);
+                            apply_terms<NT>(D, cf, C, PG, 8, TS, 0, q);
                         }
                     }
                 } else if (role == W_ADJ) {
@@ -541,7 +568,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
                         Coef cf;
                         coef_zero(cf);
                         add_Ma(cf, Sa, C, v - 1);
-                        apply_terms<NT>(D, cf, C, PGa, 1, 0, q);
+                        apply_terms<NT>(D, cf, C, PGa, 1, n, 0, q);
                     }
                 }
                 if (role != W_IDLE) {
@@ -570,6 +597,13 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
                                 AccS[(nt * 2 + j) * 32 + lane] += wk[k] * 0.5 * (Zc[0][nt][j] + Zp[0][nt][j] + h * D[0][nt][j]);
                     }
                 }
+#ifdef DTO_TDB_PROFILE
+                if (lane == 0 && blockIdx.x == 0) {
+                    long long tp6 = clock64();
+                    unsigned long long* pr = &g_tdb_prof[blockIdx.y][warp][0];
+                    pr[0] += tp1 - tp0; pr[1] += tp2 - tp1; pr[2] += tp3 - tp2; pr[3] += tp4 - tp3; pr[4] += tp5 - tp4; pr[5] += tp6 - tp5; pr[6] += 1;
+                }
+#endif
             }
         }
         if (role != W_IDLE)
@@ -703,7 +737,7 @@ bool make_plan(const DInt& I, bool want_jac, bool want_hess, Plan& pl) {
     }
     pl.warps = std::max(pl.warps, 4);  // idle warps still help assembling the generators
     const size_t FR = (size_t)(n / 8) * 2 * 32, nbasis = 2 * m + nc;
-    const size_t doubles = 2 * (size_t)n * n + 4 * sizeof(Scal) / sizeof(double) + FR + n + 8 * n + nbasis * 8 * n + n + nbasis * n + 12;
+    const size_t doubles = 2 * (size_t)n * n + 4 * sizeof(Scal) / sizeof(double) + FR + n + 8 * (n + 2) + nbasis * 8 * (n + 2) + n + nbasis * n + 12;
     const size_t budget = 226 * 1024;
     if (doubles * sizeof(double) > budget) return false;
     pl.nbs = (int)std::min<size_t>(nbasis, (budget - doubles * sizeof(double)) / ((size_t)n * n * sizeof(double)));
@@ -759,3 +793,14 @@ bool launch_tdb_dmma(const DProb& P, int ii, const double* Z, const double* mu, 
     ++*launches;
     return true;
 }
+
+#ifdef DTO_TDB_PROFILE
+extern "C" void dto_debug_tdb_profile(unsigned long long* out /* [2][16][8] */, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, g_tdb_prof, sizeof(unsigned long long) * 2 * 16 * 8);
+    if (reset) {
+        unsigned long long z[2 * 16 * 8] = {0};
+        cudaMemcpyToSymbol(g_tdb_prof, z, sizeof(z));
+    }
+}
+#endif
