@@ -138,13 +138,25 @@ __device__ __forceinline__ int int_nparam(const DInt& I) {
     return I.kind == DTO_INT_BILINEAR ? I.m + 1 : (I.order == 1 ? 2 * I.m : I.m) + 2;
 }
 
-// One WARP per (problem, owned knot); several knots per CTA, each with its own z x z tile(s) in shared memory.
+// One group of GS lanes per (problem, owned knot) -- a whole warp for wide knots, 16 or 8 lanes for narrow ones
+// (z <= 24 / z <= 16: a warp would idle most of its lanes and the kernel is latency-bound); several knots per
+// CTA, each with its own z x z tile(s) in shared memory.
+template <int GS>
+__device__ __forceinline__ double group_sum(double v, unsigned gmask) {
+#pragma unroll
+    for (int o = GS / 2; o > 0; o >>= 1) v += __shfl_xor_sync(gmask, v, o);
+    return v;
+}
+
+template <int GS>
 __global__ void hessian_assemble_kernel(DProb P, const double* __restrict__ Z, double sigma, const double* __restrict__ mu,
                                         double* __restrict__ hess, int warps_per_cta, long long total) {
     extern __shared__ double sm[];
-    const int z = P.z, tid = threadIdx.x & 31, nt = 32;
-    const int warp = threadIdx.x >> 5;
-    const long long item = (long long)blockIdx.x * warps_per_cta + warp;
+    constexpr int GPW = 32 / GS;  // groups per warp
+    const int z = P.z, lane = threadIdx.x & 31, tid = lane % GS, nt = GS;
+    const int warp = (threadIdx.x >> 5) * GPW + lane / GS;  // group index inside the CTA
+    const unsigned gmask = GS == 32 ? 0xffffffffu : (((1u << GS) - 1u) << ((lane / GS) * GS));
+    const long long item = (long long)blockIdx.x * warps_per_cta * GPW + warp;
     if (item >= total) return;
     const int nKc = min(P.kc1, P.nOwn) - P.kc0;  // owned knots of the active range
     const int b = (int)(item / nKc), kl = P.kc0 + (int)(item % nKc);
@@ -155,7 +167,7 @@ __global__ void hessian_assemble_kernel(DProb P, const double* __restrict__ Z, d
     const double* mub = mu + (long long)b * P.n_cons_local;
     const bool has_cross = hess_knot_has_cross(P, kl);
     for (int e = tid; e < tiles * z * z; e += nt) diag[e] = 0.0;
-    __syncwarp();
+    __syncwarp(gmask);
 
     for (int ii = 0; ii < P.n_int; ++ii) {
         const DInt& I = P.in[ii];
@@ -164,7 +176,7 @@ __global__ void hessian_assemble_kernel(DProb P, const double* __restrict__ Z, d
                 const double* mup = mub + I.row_off + (long long)kl * I.n;
                 for (int a = tid; a < I.n; a += nt) sym_add(diag, z, I.u_off + a, P.dt_off, -mup[a]);
             }
-            __syncwarp();
+            __syncwarp(gmask);
             continue;
         }
         const int np = int_nparam(I), n = I.n;
@@ -177,7 +189,7 @@ __global__ void hessian_assemble_kernel(DProb P, const double* __restrict__ Z, d
                 int_param(I, P.dt_off, p, nx, comp);
                 if (!nx) sym_add(diag, z, I.x_off + a, comp, hs[e]);
             }
-            __syncwarp();
+            __syncwarp(gmask);
             for (int e = tid; e < np * np; e += nt) {
                 const int p = e / np, q = e % np;
                 if (p > q) continue;
@@ -186,7 +198,7 @@ __global__ void hessian_assemble_kernel(DProb P, const double* __restrict__ Z, d
                 int_param(I, P.dt_off, q, nxq, cq);
                 if (!nxp && !nxq) sym_add(diag, z, cp, cq, hpp[e]);
             }
-            __syncwarp();
+            __syncwarp(gmask);
         }
         if (I.kind == DTO_INT_TDBILINEAR && I.order == 1 && kl >= 1) {
             // previous interval: (next,next) -> this knot's diagonal block; (own,next) -> cross block
@@ -198,7 +210,7 @@ __global__ void hessian_assemble_kernel(DProb P, const double* __restrict__ Z, d
                 int_param(I, P.dt_off, p, nx, comp);
                 if (nx) cross[(I.x_off + a) * z + comp] += hs[e];
             }
-            __syncwarp();
+            __syncwarp(gmask);
             for (int e = tid; e < np * np; e += nt) {
                 const int p = e / np, q = e % np;
                 int nxp, cp, nxq, cq;
@@ -210,7 +222,7 @@ __global__ void hessian_assemble_kernel(DProb P, const double* __restrict__ Z, d
                     cross[cp * z + cq] += hpp[e];
                 }
             }
-            __syncwarp();
+            __syncwarp(gmask);
         }
     }
 
@@ -232,7 +244,7 @@ __global__ void hessian_assemble_kernel(DProb P, const double* __restrict__ Z, d
                 sym_add(diag, z, C.var_offs[a], C.var_offs[c], s);
             }
         }
-        __syncwarp();
+        __syncwarp(gmask);
     }
 
     // objective: sigma * sum_i w_i Hess J_i   (skipped entirely when sigma == 0, evaluator.jl:626)
@@ -253,11 +265,11 @@ __global__ void hessian_assemble_kernel(DProb P, const double* __restrict__ Z, d
                         if (va <= P.dt_off && va != P.dt_off) diag[va * z + P.dt_off] += sw * 2.0 * dt * O.R[a] * dv;
                         part += O.R[a] * dv * dv;
                     }
-                    const double q = warp_sum(part);
-                    __syncwarp();
+                    const double q = group_sum<GS>(part, gmask);
+                    __syncwarp(gmask);
                     if (tid == 0) diag[P.dt_off * z + P.dt_off] += sw * q;
                 }
-                __syncwarp();
+                __syncwarp(gmask);
             }
             if (O.kind == DTO_OBJ_LINREG) {
                 // d2J/(dv ddt) = R, written at (row v, col dt) only (regularizers.jl:287-313): kept iff v precedes dt
@@ -266,7 +278,7 @@ __global__ void hessian_assemble_kernel(DProb P, const double* __restrict__ Z, d
                         const int va = O.var_offs[a];
                         if (va < P.dt_off) diag[va * z + P.dt_off] += sigma * O.weight * O.R[a];
                     }
-                __syncwarp();
+                __syncwarp(gmask);
             }
             // knot objectives are added by knot_objective_hessian_kernel (one thread per hyper-dual pair)
         }
@@ -278,18 +290,18 @@ __global__ void hessian_assemble_kernel(DProb P, const double* __restrict__ Z, d
     const int ncross = has_cross ? z : 0;
     const int region = ncross * z + z * (z + 1) / 2;
     {
-        // lane-private (column l, row-in-column i) cursor advanced by 32 entries per iteration
+        // lane-private (column l, row-in-column i) cursor advanced by GS entries per iteration
         int l = 0, i = tid;
         while (l < z && i >= ncross + l + 1) {
             i -= ncross + l + 1;
             ++l;
         }
-        for (int e = tid; e < region; e += 32) {
+        for (int e = tid; e < region; e += GS) {
             double v;
             if (i < ncross) v = P.any_cross ? cross[i * z + l] : 0.0;
             else v = diag[(i - ncross) * z + l];
             hp[e] = v;
-            i += 32;
+            i += GS;
             while (l < z && i >= ncross + l + 1) {
                 i -= ncross + l + 1;
                 ++l;
@@ -562,17 +574,23 @@ void launch_hessian_assemble(const DProb& P, const double* Z, double sigma, cons
                              long long* launches) {
     const int nKc = std::min(P.kc1, P.nOwn) - P.kc0;
     if (nKc <= 0) return;
-    const size_t per_warp = sizeof(double) * (size_t)P.z * P.z * (P.any_cross ? 2 : 1);
+    const size_t per_group = sizeof(double) * (size_t)P.z * P.z * (P.any_cross ? 2 : 1);
+    const int GS = P.z <= 16 ? 8 : (P.z <= 24 ? 16 : 32), GPW = 32 / GS;
     int W = 8;
-    while (W > 1 && W * per_warp > 64 * 1024) W >>= 1;
-    const size_t smem = W * per_warp;
+    while (W > 1 && W * GPW * per_group > 64 * 1024) W >>= 1;
+    const size_t smem = W * GPW * per_group;
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
-        cudaFuncSetAttribute(hessian_assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(hessian_assemble_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(hessian_assemble_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(hessian_assemble_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         configured = 227 * 1024;
     }
     const long long total = (long long)nKc * P.batch;
-    hessian_assemble_kernel<<<(unsigned)((total + W - 1) / W), W * 32, smem, st>>>(P, Z, sigma, mu, hess, W, total);
+    const unsigned grid = (unsigned)((total + (long long)W * GPW - 1) / ((long long)W * GPW));
+    if (GS == 8) hessian_assemble_kernel<8><<<grid, W * 32, smem, st>>>(P, Z, sigma, mu, hess, W, total);
+    else if (GS == 16) hessian_assemble_kernel<16><<<grid, W * 32, smem, st>>>(P, Z, sigma, mu, hess, W, total);
+    else hessian_assemble_kernel<32><<<grid, W * 32, smem, st>>>(P, Z, sigma, mu, hess, W, total);
     ++*launches;
     if (sigma != 0.0)
         for (int oi = 0; oi < P.n_obj; ++oi) {
