@@ -35,13 +35,14 @@ __device__ double block_sum(double v, double* red) {
 // ------------------------------------------------------------------------------------------------
 // K2: DerivativeIntegrator  f = x+ - x - dt*xdot : residual and full d x 2z block (zeros included)
 // ------------------------------------------------------------------------------------------------
+template <int GS>
 __global__ void analytic_kernel(DProb P, const double* __restrict__ Z, double* __restrict__ g, double* __restrict__ jac,
                                 long long total) {
-    // one warp per (problem, interval)
-    const long long item = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    // one group of GS lanes per (problem, interval)
+    const long long item = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / GS;
     if (item >= total) return;
     const int nIc = min(P.kc1, P.nI) - P.kc0;  // intervals of the active range
-    const int b = (int)(item / nIc), kl = P.kc0 + (int)(item % nIc), z = P.z, lane = threadIdx.x & 31;
+    const int b = (int)(item / nIc), kl = P.kc0 + (int)(item % nIc), z = P.z, lane = threadIdx.x % GS;
     const double* zk = Z + (long long)b * P.n_vars_local + (long long)kl * z;
     const double* zk1 = zk + z;
     if (P.halo != nullptr && kl + 1 == P.nK - 1) zk1 = P.halo;
@@ -52,13 +53,13 @@ __global__ void analytic_kernel(DProb P, const double* __restrict__ Z, double* _
         const int d = I.n;
         if (g != nullptr) {
             double* gp = g + (long long)b * P.n_cons_local + I.row_off + (long long)kl * d;
-            for (int a = lane; a < d; a += 32) gp[a] = zk1[I.x_off + a] - zk[I.x_off + a] - dt * zk[I.u_off + a];
+            for (int a = lane; a < d; a += GS) gp[a] = zk1[I.x_off + a] - zk[I.x_off + a] - dt * zk[I.u_off + a];
         }
         if (jac != nullptr) {
             double* jp = jac + (long long)b * P.nnz_jac_local;
             const long long own_off = jac_own_off(P, kl, I.doff, d);
             const long long prev_off = jac_prev_off(P, kl + 1, I.doff);
-            for (int e = lane; e < 2 * z * d; e += 32) {
+            for (int e = lane; e < 2 * z * d; e += GS) {
                 const int l = e / d, a = e % d;
                 double v = 0.0;
                 long long pos;
@@ -349,18 +350,22 @@ __global__ void knot_objective_hessian_kernel(DProb P, int oi, const double* __r
 // K6: objective value + gradient, one WARP per (problem, owned knot); partial sums reduced in a
 // second, deterministic pass.
 // ------------------------------------------------------------------------------------------------
+template <int GS>
 __global__ void objective_kernel(DProb P, const double* __restrict__ Z, double* __restrict__ grad, double* __restrict__ partials,
                                  int warps_per_cta, long long total) {
     extern __shared__ double sm[];
-    const int z = P.z, tid = threadIdx.x & 31, nt = 32, warp = threadIdx.x >> 5;
-    const long long item = (long long)blockIdx.x * warps_per_cta + warp;
+    constexpr int GPW = 32 / GS;
+    const int z = P.z, lane = threadIdx.x & 31, tid = lane % GS, nt = GS;
+    const int warp = (threadIdx.x >> 5) * GPW + lane / GS;  // group index inside the CTA
+    const unsigned gmask = GS == 32 ? 0xffffffffu : (((1u << GS) - 1u) << ((lane / GS) * GS));
+    const long long item = (long long)blockIdx.x * warps_per_cta * GPW + warp;
     if (item >= total) return;
     const int b = (int)(item / P.nOwn), kl = (int)(item % P.nOwn);
     double* gz = sm + (size_t)warp * z;
     const double* zk = Z + (long long)b * P.n_vars_local + (long long)kl * z;
     const long long kg = (long long)P.kb - 1 + kl;  // global 0-based knot
     for (int e = tid; e < z; e += nt) gz[e] = 0.0;
-    __syncwarp();
+    __syncwarp(gmask);
     double Jk = 0.0;  // meaningful in lane 0 only
     for (int oi = 0; oi < P.n_obj; ++oi) {
         const DObj& O = P.ob[oi];
@@ -373,14 +378,14 @@ __global__ void objective_kernel(DProb P, const double* __restrict__ Z, double* 
                     gz[O.var_offs[a]] += O.weight * dt * dt * O.R[a] * dv;
                     part += O.R[a] * dv * dv;
                 }
-                const double q = warp_sum(part);
-                __syncwarp();
+                const double q = group_sum<GS>(part, gmask);
+                __syncwarp(gmask);
                 if (tid == 0) {
                     Jk += O.weight * 0.5 * dt * dt * q;
                     gz[P.dt_off] += O.weight * q * dt;
                 }
             }
-            __syncwarp();
+            __syncwarp(gmask);
         } else if (O.kind == DTO_OBJ_LINREG) {
             // J = sum_t dt_t R'v_t (regularizers.jl:241-270)
             if (O.knot_to_own[kl] >= 0) {
@@ -390,20 +395,20 @@ __global__ void objective_kernel(DProb P, const double* __restrict__ Z, double* 
                     gz[O.var_offs[a]] += O.weight * dt * O.R[a];
                     part += O.R[a] * zk[O.var_offs[a]];
                 }
-                const double q = warp_sum(part);
-                __syncwarp();
+                const double q = group_sum<GS>(part, gmask);
+                __syncwarp(gmask);
                 if (tid == 0) {
                     Jk += O.weight * dt * q;
                     gz[P.dt_off] += O.weight * q;
                 }
             }
-            __syncwarp();
+            __syncwarp(gmask);
         } else if (O.kind == DTO_OBJ_MINTIME) {
             if (tid == 0 && kg < P.N - 1) {
                 Jk += O.weight * O.D * zk[P.dt_off];
                 gz[P.dt_off] += O.weight * O.D;
             }
-            __syncwarp();
+            __syncwarp(gmask);
         } else if (O.kind == DTO_OBJ_KNOT) {
             const int j = O.knot_to_own[kl];
             if (j >= 0) {
@@ -416,7 +421,7 @@ __global__ void objective_kernel(DProb P, const double* __restrict__ Z, double* 
                     if (a == 0) Jk += w * r.v;  // a == 0 is handled by lane 0
                 }
             }
-            __syncwarp();
+            __syncwarp(gmask);
         }
     }
     if (grad != nullptr)
@@ -542,7 +547,13 @@ void launch_analytic(const DProb& P, const double* Z, double* g, double* jac, Ev
     const int nIc = std::min(P.kc1, P.nI) - P.kc0;
     if (any_deriv && nIc > 0) {
         const long long total = (long long)nIc * P.batch;
-        analytic_kernel<<<(unsigned)((total + 7) / 8), 256, 0, st>>>(P, Z, f.want_g ? g : nullptr, f.want_jac ? jac : nullptr, total);
+        int dmax = 0;
+        for (int i = 0; i < P.n_int; ++i)
+            if (P.in[i].kind == DTO_INT_DERIVATIVE) dmax = std::max(dmax, P.in[i].n);
+        if (2 * P.z * dmax <= 64)  // a handful of entries per interval: 8 lanes each
+            analytic_kernel<8><<<(unsigned)((total + 31) / 32), 256, 0, st>>>(P, Z, f.want_g ? g : nullptr, f.want_jac ? jac : nullptr, total);
+        else
+            analytic_kernel<32><<<(unsigned)((total + 7) / 8), 256, 0, st>>>(P, Z, f.want_g ? g : nullptr, f.want_jac ? jac : nullptr, total);
         ++*launches;
     }
 }
@@ -607,9 +618,13 @@ void launch_objective(const DProb& P, const double* Z, double* J, double* grad, 
                       long long* launches) {
     if (P.nOwn <= 0) return;
     const int W = 8;
-    const size_t smem = sizeof(double) * (size_t)P.z * W;
+    const int GS = P.z <= 16 ? 8 : (P.z <= 24 ? 16 : 32), GPW = 32 / GS;
+    const size_t smem = sizeof(double) * (size_t)P.z * W * GPW;
     const long long total = (long long)P.nOwn * P.batch;
-    objective_kernel<<<(unsigned)((total + W - 1) / W), W * 32, smem, st>>>(P, Z, grad, J ? partials : nullptr, W, total);
+    const unsigned grid = (unsigned)((total + (long long)W * GPW - 1) / ((long long)W * GPW));
+    if (GS == 8) objective_kernel<8><<<grid, W * 32, smem, st>>>(P, Z, grad, J ? partials : nullptr, W, total);
+    else if (GS == 16) objective_kernel<16><<<grid, W * 32, smem, st>>>(P, Z, grad, J ? partials : nullptr, W, total);
+    else objective_kernel<32><<<grid, W * 32, smem, st>>>(P, Z, grad, J ? partials : nullptr, W, total);
     ++*launches;
     if (J) {
         // partials layout: [batch][nOwn] followed by [batch][nchunks] of scratch
