@@ -67,10 +67,10 @@ __global__ void analytic_kernel(DProb P, const double* __restrict__ Z, double* _
                     if (l == I.x_off + a) v += -1.0;
                     if (l == I.u_off + a) v += -dt;
                     if (l == P.dt_off) v += -zk[I.u_off + a];
-                    pos = P.jac_colptr[(long long)kl * z + l] + own_off + a;
+                    pos = jac_col(P, kl, l) + own_off + a;
                 } else {
                     if (l - z == I.x_off + a) v = 1.0;
-                    pos = P.jac_colptr[(long long)(kl + 1) * z + (l - z)] + prev_off + a;
+                    pos = jac_col(P, (kl + 1), (l - z)) + prev_off + a;
                 }
                 jp[pos] = v;
             }

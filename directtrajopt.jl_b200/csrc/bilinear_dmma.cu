@@ -261,14 +261,14 @@ __global__ void __launch_bounds__(128) bilinear_dmma_kernel(DProb P, int ii, con
                 const int l = e / n, a = e % n;
                 if (l < z) {
                     if ((l >= I.x_off && l < I.x_off + n) || (l >= I.u_off && l < I.u_off + m) || l == P.dt_off) continue;
-                    jp[P.jac_colptr[(long long)kk * z + l] + own_off + a] = 0.0;
+                    jp[jac_col(P, kk, l) + own_off + a] = 0.0;
                 } else {
-                    jp[P.jac_colptr[(long long)(kk + 1) * z + (l - z)] + prev_off + a] = (l - z - I.x_off == a) ? 1.0 : 0.0;
+                    jp[jac_col(P, (kk + 1), (l - z)) + prev_off + a] = (l - z - I.x_off == a) ? 1.0 : 0.0;
                 }
             }
             // d/du_i columns from rows 1+i of tile 0, d/ddt column from row 0 of GF
             if (row8 >= 1 && row8 <= m) {
-                double* col = jp + P.jac_colptr[(long long)kk * z + I.u_off + (row8 - 1)] + own_off;
+                double* col = jp + jac_col(P, kk, I.u_off + (row8 - 1)) + own_off;
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt) {
                     col[8 * nt + 2 * q] = -F[0][nt][0];
@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(128) bilinear_dmma_kernel(DProb P, int ii, con
                 }
             }
             if (row8 == 0) {
-                double* col = jp + P.jac_colptr[(long long)kk * z + P.dt_off] + own_off;
+                double* col = jp + jac_col(P, kk, P.dt_off) + own_off;
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt) {
                     col[8 * nt + 2 * q] = -GF[0][nt][0];
@@ -386,7 +386,7 @@ __global__ void __launch_bounds__(128) bilinear_dmma_kernel(DProb P, int ii, con
             for (int mt = 0; mt < MT; ++mt) {
                 const int c = c0 + mt * 8 + row8;
                 if (c < n) {
-                    double* col = jp + P.jac_colptr[(long long)kk * z + I.x_off + c] + own_off;
+                    double* col = jp + jac_col(P, kk, I.x_off + c) + own_off;
 #pragma unroll
                     for (int nt = 0; nt < NT; ++nt) {
                         col[8 * nt + 2 * q] = -F[mt][nt][0];

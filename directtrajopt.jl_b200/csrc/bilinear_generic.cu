@@ -182,11 +182,11 @@ __global__ void __launch_bounds__(32) bilinear_generic_kernel(DProb P, int ii, c
                 if (l >= I.x_off && l < I.x_off + n) v = -V[(colE + (l - I.x_off)) * n + a];
                 else if (l >= I.u_off && l < I.u_off + m) v = -V[(1 + (l - I.u_off)) * n + a];
                 else if (l == P.dt_off) v = -gF[a];
-                pos = P.jac_colptr[(long long)kl * z + l] + own_off + a;
+                pos = jac_col(P, kl, l) + own_off + a;
             } else {
                 const int lp = l - z;
                 if (lp - I.x_off == a) v = 1.0;
-                pos = P.jac_colptr[(long long)(kl + 1) * z + lp] + prev_off + a;
+                pos = jac_col(P, (kl + 1), lp) + prev_off + a;
             }
             jp[pos] = v;
         }

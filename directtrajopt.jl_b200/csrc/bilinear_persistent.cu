@@ -356,14 +356,14 @@ __device__ __forceinline__ void role_forward(const Ctx<NT>& c, int b, int kk, co
             const int l = e / n, a = e % n;
             if (l < z) {
                 if ((l >= I.x_off && l < I.x_off + n) || (l >= I.u_off && l < I.u_off + m) || l == P.dt_off) continue;
-                jp[P.jac_colptr[(long long)kk * z + l] + own_off + a] = 0.0;
+                jp[jac_col(P, kk, l) + own_off + a] = 0.0;
             } else {
-                jp[P.jac_colptr[(long long)(kk + 1) * z + (l - z)] + prev_off + a] = (l - z - I.x_off == a) ? 1.0 : 0.0;
+                jp[jac_col(P, (kk + 1), (l - z)) + prev_off + a] = (l - z - I.x_off == a) ? 1.0 : 0.0;
             }
         }
         // d/du_i columns from rows 1+i of tile 0, d/ddt column from row 0 of GF
         if (row8 >= 1 && row8 <= m) {
-            double* col = jp + P.jac_colptr[(long long)kk * z + I.u_off + (row8 - 1)] + own_off;
+            double* col = jp + jac_col(P, kk, I.u_off + (row8 - 1)) + own_off;
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt) {
                 col[8 * nt + 2 * q] = -F[0][nt][0];
@@ -371,7 +371,7 @@ __device__ __forceinline__ void role_forward(const Ctx<NT>& c, int b, int kk, co
             }
         }
         if (row8 == 0) {
-            double* col = jp + P.jac_colptr[(long long)kk * z + P.dt_off] + own_off;
+            double* col = jp + jac_col(P, kk, P.dt_off) + own_off;
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt) {
                 col[8 * nt + 2 * q] = -GF[0][nt][0];
@@ -496,7 +496,7 @@ __device__ __forceinline__ void role_exp_series(const Ctx<NT>& c, int b, int kk)
         for (int mt = 0; mt < MT; ++mt) {
             const int col = c0 + mt * 8 + row8;
             if (col < n) {
-                double* cp = jp + P.jac_colptr[(long long)kk * z + I.x_off + col] + own_off;
+                double* cp = jp + jac_col(P, kk, I.x_off + col) + own_off;
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt) {
                     cp[8 * nt + 2 * q] = -F[mt][nt][0];
@@ -647,7 +647,7 @@ __device__ __forceinline__ void role_exp_ps(const Ctx<NT>& c, int b, int kk) {
 #pragma unroll
             for (int mt = 0; mt < ME; ++mt) {
                 const int col = 8 * (cb * ME + mt) + row8;
-                double* cp = jp + P.jac_colptr[(long long)kk * z + I.x_off + col] + own_off;
+                double* cp = jp + jac_col(P, kk, I.x_off + col) + own_off;
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt) {
                     cp[8 * nt + 2 * q] = -Pm[mt][nt][0];
@@ -697,7 +697,7 @@ __device__ __forceinline__ void role_exp_ps(const Ctx<NT>& c, int b, int kk) {
 #pragma unroll
                 for (int mt = 0; mt < ME; ++mt) {
                     const int col = 8 * (cb * ME + mt) + row8;
-                    double* cp = jp + P.jac_colptr[(long long)kk * z + I.x_off + col] + own_off;
+                    double* cp = jp + jac_col(P, kk, I.x_off + col) + own_off;
 #pragma unroll
                     for (int nt = 0; nt < NT; ++nt) {
                         cp[8 * nt + 2 * q] = -O[mt][nt][0];

@@ -444,6 +444,7 @@ extern "C" int dto_create(const dto_problem_desc* d, dto_handle** out) {
     }
     P.nnz_jac_local = h->jac_colptr.back();
     P.jac_colptr = dev_upload(h, h->jac_colptr.data(), h->jac_colptr.size());
+    P.jac_closed = h->con_entries.empty() && d->n_constraints == 0 ? 1 : 0;
     {
         std::vector<long long> fill((size_t)P.nK * z, 0);
         for (int i = 0; i < d->n_constraints; ++i) {

@@ -76,6 +76,7 @@ struct DProb {
     long long n_vars_local;   // nK * z  (stride of one problem in the local Z buffer)
     long long n_cons_local, nnz_jac_local, nnz_hess_local;
     const long long* jac_colptr;  // [nK*z + 1] local
+    int jac_closed;               // no knot-constraint entries: column starts follow in closed form (no loads in the kernels)
     const double* halo;           // if non-null: knot nK-1 is read from here (peer memory) instead of local Z
     DInt in[DTO_MAX_INT];
     DObj ob[DTO_MAX_OBJ];
@@ -89,6 +90,15 @@ __host__ __device__ inline long long jac_own_off(const DProb& P, int kl, int dof
 }
 __host__ __device__ inline long long jac_prev_off(const DProb& P, int kl, int doff) {
     return (kl < P.nI) ? 2LL * doff : doff;
+}
+// start of local column (knot kl, component l)
+__host__ __device__ inline long long jac_col(const DProb& P, long long kl, int l) {
+    if (P.jac_closed) {  // every column of a knot holds Dsum rows per adjacent interval
+        const long long D = P.Dsum;
+        const long long start = kl == 0 ? 0 : (long long)P.z * D * (2 * kl - 1);
+        return start + (long long)l * D * ((kl >= 1 ? 1 : 0) + (kl < P.nI ? 1 : 0));
+    }
+    return P.jac_colptr[kl * P.z + l];
 }
 // Hessian: start of local knot kl's region and of column l inside it
 __host__ __device__ inline long long hess_knot_base(const DProb& P, int kl) {

@@ -340,12 +340,12 @@ __global__ void __launch_bounds__(kThreads) tdb_kernel(DProb P, int ii, const do
                     if (l >= I.u_off && l < I.u_off + m) v = -F[(size_t)(1 + (l - I.u_off)) * n + a];
                     else if (l == P.dt_off) v = -F[(size_t)(1 + nu) * n + a];
                     else if (l == I.t_off) v = -F[(size_t)(2 + nu) * n + a];
-                    pos = P.jac_colptr[(long long)kl * z + l] + own_off + a;
+                    pos = jac_col(P, kl, l) + own_off + a;
                 } else {
                     const int lp = l - z;
                     if (lp - I.x_off == a) v = 1.0;
                     if (I.order == 1 && lp >= I.u_off && lp < I.u_off + m) v = -F[(size_t)(1 + m + (lp - I.u_off)) * n + a];
-                    pos = P.jac_colptr[(long long)(kl + 1) * z + lp] + prev_off + a;
+                    pos = jac_col(P, (kl + 1), lp) + prev_off + a;
                 }
                 jp[pos] = v;
             }
@@ -374,7 +374,7 @@ __global__ void __launch_bounds__(kThreads) tdb_kernel(DProb P, int ii, const do
         const long long own_off = jac_own_off(P, kl, I.doff, n);
         for (int e = tid; e < n * n; e += nt) {
             const int c = e / n, a = e % n;  // column c of Phi = vector c
-            jp[P.jac_colptr[(long long)kl * z + I.x_off + c] + own_off + a] = -F[(size_t)c * n + a];
+            jp[jac_col(P, kl, I.x_off + c) + own_off + a] = -F[(size_t)c * n + a];
         }
     } else {
         double* hx = I.hs + ((long long)b * P.nI + kl) * I.hs_stride;

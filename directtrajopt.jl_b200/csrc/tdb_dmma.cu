@@ -635,10 +635,10 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
             if (v >= 1 && v <= np) {  // first-order rows are Jacobian columns
                 const int a = v - 1;
                 double* col;
-                if (a < m) col = jp + P.jac_colptr[(long long)kl * z + I.u_off + a] + own_off;
-                else if (a < nu) col = jp + P.jac_colptr[(long long)(kl + 1) * z + I.u_off + (a - m)] + prev_off;
-                else if (a == nu) col = jp + P.jac_colptr[(long long)kl * z + P.dt_off] + own_off;
-                else col = jp + P.jac_colptr[(long long)kl * z + I.t_off] + own_off;
+                if (a < m) col = jp + jac_col(P, kl, I.u_off + a) + own_off;
+                else if (a < nu) col = jp + jac_col(P, (kl + 1), I.u_off + (a - m)) + prev_off;
+                else if (a == nu) col = jp + jac_col(P, kl, P.dt_off) + own_off;
+                else col = jp + jac_col(P, kl, I.t_off) + own_off;
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt) {
                     col[8 * nt + 2 * q] = -F[nt][0];
@@ -650,11 +650,11 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
                     const int l = e2 / n, a = e2 % n;
                     if (l < z) {
                         if ((l >= I.x_off && l < I.x_off + n) || (l >= I.u_off && l < I.u_off + m) || l == P.dt_off || l == I.t_off) continue;
-                        jp[P.jac_colptr[(long long)kl * z + l] + own_off + a] = 0.0;
+                        jp[jac_col(P, kl, l) + own_off + a] = 0.0;
                     } else {
                         const int lp = l - z;
                         if (I.order == 1 && lp >= I.u_off && lp < I.u_off + m) continue;
-                        jp[P.jac_colptr[(long long)(kl + 1) * z + lp] + prev_off + a] = (lp - I.x_off == a) ? 1.0 : 0.0;
+                        jp[jac_col(P, (kl + 1), lp) + prev_off + a] = (lp - I.x_off == a) ? 1.0 : 0.0;
                     }
                 }
             }
@@ -682,7 +682,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
         double* jp = jac + (long long)b * P.nnz_jac_local;
         const long long own_off = jac_own_off(P, kl, I.doff, n);
         const int col = 8 * tile + row8;
-        double* cp = jp + P.jac_colptr[(long long)kl * z + I.x_off + col] + own_off;
+        double* cp = jp + jac_col(P, kl, I.x_off + col) + own_off;
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) {
             cp[8 * nt + 2 * q] = -F[nt][0];
