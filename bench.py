@@ -117,7 +117,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append([c.strip() for c in out.split(",")])
             except Exception:
                 pass
-            self.stop_flag.wait(0.1)
+            self.stop_flag.wait(0.02)
 
     def summary(self):
         if not self.rows:

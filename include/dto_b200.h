@@ -26,9 +26,10 @@
  *     (column-major findnz of the Jacobian; upper triangle, column-major, of the Hessian).
  *   - Z is the solver's primal vector [vec(data[z x N]); (no globals in scope)], knot-major.
  *   - every output buffer is owned and pre-allocated by the caller and is fully overwritten.
- *   - host-pointer entry points copy through pinned staging owned by the handle; `_dev` entry points
- *     take device pointers valid on the handle's device and enqueue on the handle's stream
- *     (dto_stream) without synchronising.
+ *   - host-pointer entry points copy between the caller's buffers and device buffers owned by the handle and
+ *     return after the stream has drained; with page-locked caller buffers the device->host copies of
+ *     finished knot ranges overlap the remaining computation.  `_dev` entry points take device pointers
+ *     valid on the handle's device and enqueue on the handle's stream (dto_stream) without synchronising.
  *   - return value: 0 on success, negative dto_status otherwise; no exception crosses the boundary.
  *     dto_last_error() gives the message.  A handle is not thread-safe (matches the reference, whose
  *     callbacks mutate a shared cached trajectory: src/solvers/evaluator.jl:474-482).
