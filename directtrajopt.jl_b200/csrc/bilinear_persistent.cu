@@ -22,6 +22,8 @@
 // states of tile t: the matching B fragments are one 16-byte LDS from the row-major matrix.  Matrices are
 // stored unpadded; when n is a multiple of 16 the 8-double blocks of odd rows are swapped pairwise
 // (XOR swizzle) so that the 8 rows x 64 bytes of one LDS.128 phase fall into distinct banks.
+#include <stdlib.h>
+
 #include "dto_internal.h"
 
 namespace {
@@ -1251,6 +1253,7 @@ bool launch_variant(const DProb& P, int ii, const double* Z, const double* mu, d
         }
         W = bestW;
         nE = bestE;
+        if (const char* env = getenv("DTO_B200_K1_NE")) nE = std::max(0, std::min(nE, atoi(env)));  // experiments
     }
     const size_t smem = shared_part + (size_t)W * slot + (size_t)nE * 2 * mat;
     auto kern = bilinear_persistent_kernel<NT, MT>;
