@@ -312,6 +312,19 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
     else if (warp < TF + TE) { role = W_EXP; tile = warp - TF; }
     else if (warp < TF + TE + TA) { role = W_ADJ; tile = 0; }
     const int scal_warp = nwarps - 1;
+    int pair_a = 0, pair_b = 0;  // forward rows beyond 1 + np: the parameter pair (a <= b) of this lane's row
+    if (role == W_FWD) {
+        int p = 8 * tile + row8 - 1 - np;
+        if (p >= 0) {
+            int a = 0;
+            while (a < np && p >= np - a) {
+                p -= np - a;
+                ++a;
+            }
+            pair_a = a;
+            pair_b = a + p;
+        }
+    }
 
     // ---- shared memory -----------------------------------------------------------------------------------
     double* Gf = sm;                                          // G(tau), swizzled row-major
@@ -348,8 +361,17 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
     auto basis_ptr = [&](int bi) -> const double* { return bi < nbs ? Bs + (size_t)bi * nn : basis_global(I, bi, nn); };
     // The drift matrix does not fit beside the basis cache: every thread copies the entries it will assemble
     // from L2 straight into their place in Gf, asynchronously, while the previous right-hand side finishes.
+    // Who assembles G: all warps, except that forward-tile warps with parameter couplings are exempt when at least
+    // three other warps exist -- their coupling phase is the long one, and the assembly of node q+1 by the others
+    // then overlaps it.  (aw, na) = this warp's index among the assemblers and their number; aw < 0: not one.
+    int aw = warp, na = nwarps;
+    if (TF > 0 && (want_hess || want_jac) && nwarps - TF >= 3) {
+        aw = warp >= TF ? warp - TF : -1;
+        na = nwarps - TF;
+    }
     auto prefetch_drift = [&]() {
-        for (int blk = warp; blk < nn / 64; blk += nwarps) {
+        if (aw < 0) return;
+        for (int blk = aw; blk < nn / 64; blk += na) {
             const int p = sw<NT>((blk / NT) * 8 + (lane >> 2), (blk % NT) * 8 + 2 * (lane & 3));
             const unsigned dst = (unsigned)__cvta_generic_to_shared(Gf + p);
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(I.Grm + p) : "memory");
@@ -414,9 +436,10 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
 #ifdef DTO_TDB_PROFILE
                 long long tp1 = clock64();
 #endif
-                if (nbs == nbasis && m <= 2 && nc == 0) assemble_generators<NT, true, 2, 0>(Gf, Ga, Bs, I, Sf, Sa, m, nc, TA > 0, warp, nwarps, lane);
-                else if (nbs == nbasis) assemble_generators<NT, true, kMaxM, kMaxC>(Gf, Ga, Bs, I, Sf, Sa, m, nc, TA > 0, warp, nwarps, lane);
-                else assemble_generators<NT, false, kMaxM, kMaxC>(Gf, Ga, Bs, I, Sf, Sa, m, nc, TA > 0, warp, nwarps, lane);
+                if (aw < 0) {
+                } else if (nbs == nbasis && m <= 2 && nc == 0) assemble_generators<NT, true, 2, 0>(Gf, Ga, Bs, I, Sf, Sa, m, nc, TA > 0, aw, na, lane);
+                else if (nbs == nbasis) assemble_generators<NT, true, kMaxM, kMaxC>(Gf, Ga, Bs, I, Sf, Sa, m, nc, TA > 0, aw, na, lane);
+                else assemble_generators<NT, false, kMaxM, kMaxC>(Gf, Ga, Bs, I, Sf, Sa, m, nc, TA > 0, aw, na, lane);
                 if (role == W_FWD && tile == 0 && couple) {
 #pragma unroll
                     for (int nt = 0; nt < NT; ++nt) {
@@ -535,39 +558,36 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
                 if (role == W_FWD && couple) {
                     const int v = 8 * tile + row8;
                     if (v >= 1 && v < nvecF) {
+                        const Scal S = Sf;  // node scalars into registers: the coefficient algebra below is then load-free
                         Coef cf;
                         coef_zero(cf);
                         if (v <= np) {  // first-order row a: (dM/dtheta_a) x
-                            add_Ma(cf, Sf, C, v - 1);
+                            add_Ma(cf, S, C, v - 1);
                             apply_terms<NT>(D, cf, C, PG, 8, TS, 0, q);
                         } else {  // pair (a, bb): M_a Z_bb + M_bb Z_a + M_ab x
-                            int p = v - 1 - np, a = 0;
-                            while (p >= np - a) {
-                                p -= np - a;
-                                ++a;
-                            }
-                            const int bb = a + p;
-                            add_Ma(cf, Sf, C, a);
+                            const int a = pair_a, bb = pair_b;
+                            add_Ma(cf, S, C, a);
                             if (a == bb) {
                                 coef_scale(cf, 2.0);
                                 apply_terms<NT>(D, cf, C, PG, 8, TS, 1 + a, q);
                             } else {
                                 apply_terms<NT>(D, cf, C, PG, 8, TS, 1 + bb, q);
                                 coef_zero(cf);
-                                add_Ma(cf, Sf, C, bb);
+                                add_Ma(cf, S, C, bb);
                                 apply_terms<NT>(D, cf, C, PG, 8, TS, 1 + a, q);
                             }
                             coef_zero(cf);
-                            add_Mab(cf, Sf, C, a, bb);
+                            add_Mab(cf, S, C, a, bb);
                             apply_terms<NT>(D, cf, C, PG, 8, TS, 0, q);
                         }
                     }
                 } else if (role == W_ADJ) {
                     const int v = row8;
                     if (v >= 1 && v <= np) {  // d lambda^a = M' lambda^a + (M^a)' lambda
+                        const Scal S = Sa;
                         Coef cf;
                         coef_zero(cf);
-                        add_Ma(cf, Sa, C, v - 1);
+                        add_Ma(cf, S, C, v - 1);
                         apply_terms<NT>(D, cf, C, PGa, 1, n, 0, q);
                     }
                 }
