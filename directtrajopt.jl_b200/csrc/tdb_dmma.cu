@@ -723,6 +723,186 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
     }  // items
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Propagator-only CTA (the second half of a split interval): the columns of the identity need no couplings, tables or
+// adjoint generator, so G(tau) is double-buffered -- while the warps multiply their tiles by G(node q) they also
+// assemble G(node q+1) into the other buffer (drift entries prefetched with cp.async one node earlier, node scalars
+// computed two nodes ahead by one warp): ONE block barrier per right-hand side and assembly overlapped with DMMAs.
+// ------------------------------------------------------------------------------------------------------------------
+struct NodeIter {
+    int ms, k, qq, steps, K;
+    __device__ bool valid() const { return ms < steps; }
+    __device__ double time() const {
+        const double H = 1.0 / steps, s0 = ms * H;
+        const int nk = 2 * (k + 1);
+        return qq == nk ? s0 + H : s0 + qq * (H / nk);
+    }
+    __device__ void next() {
+        if (qq < 2 * (k + 1)) ++qq;
+        else {
+            qq = 0;
+            if (++k == K) {
+                k = 0;
+                ++ms;
+            }
+        }
+    }
+};
+
+template <int NT>
+__global__ void __launch_bounds__(8 * 32, 1)
+    tdb_exp_kernel(DProb P, int ii, const double* __restrict__ Z, double* __restrict__ jac, int K, int steps, int TE, int nbs,
+                   double* __restrict__ scratch) {
+    extern __shared__ __align__(16) double sm[];
+    constexpr int n = 8 * NT, nn = n * n, FR = NT * 2 * 32;
+    const DInt& I = P.in[ii];
+    const int m = I.m, nc = I.n_carrier, z = P.z, nbasis = 2 * m + nc;
+    const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q = lane & 3, row8 = lane >> 2;
+    const bool active = warp < TE;
+    const int tile = warp;
+    double* G0b = sm;                                          // G of even nodes
+    double* G1b = G0b + nn;                                    // G of odd nodes
+    Scal* scal = reinterpret_cast<Scal*>(G1b + nn);            // [node parity]
+    double* wk = reinterpret_cast<double*>(scal + 2);          // [kMaxCols] extrapolation weights
+    double* Bs = wk + kMaxCols + (kMaxCols & 1);               // cached basis matrices
+    double* AccS = scratch + ((size_t)(gridDim.x + blockIdx.x) * kMaxWarpsT + warp) * 2 * FR;  // second half of the scratch
+    double* Y0S = AccS + FR;
+    if (threadIdx.x < kMaxCols) {
+        const int k = threadIdx.x;
+        double w = 1.0;
+        const double nk2 = 4.0 * (k + 1) * (k + 1);
+        for (int l = 0; l < K; ++l)
+            if (l != k) w *= nk2 / (nk2 - 4.0 * (l + 1) * (l + 1));
+        wk[k] = k < K ? w : 0.0;
+    }
+    for (int i = threadIdx.x; i < nbs * nn; i += blockDim.x) Bs[i] = basis_global(I, i / nn, nn)[i % nn];
+    auto prefetch_drift = [&](double* Gd) {
+        for (int blk = warp; blk < nn / 64; blk += nwarps) {
+            const int p = sw<NT>((blk / NT) * 8 + (lane >> 2), (blk % NT) * 8 + 2 * (lane & 3));
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(Gd + p);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(I.Grm + p) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto assemble = [&](double* Gd, const Scal& S) {
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        if (nbs == nbasis && m <= 2 && nc == 0) assemble_generators<NT, true, 2, 0>(Gd, nullptr, Bs, I, S, S, m, nc, false, warp, nwarps, lane);
+        else if (nbs == nbasis) assemble_generators<NT, true, kMaxM, kMaxC>(Gd, nullptr, Bs, I, S, S, m, nc, false, warp, nwarps, lane);
+        else assemble_generators<NT, false, kMaxM, kMaxC>(Gd, nullptr, Bs, I, S, S, m, nc, false, warp, nwarps, lane);
+    };
+
+    const int n_items = P.nI * P.batch;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int b = item / P.nI, kl = item % P.nI;
+        const double* zk = Z + (long long)b * P.n_vars_local + (long long)kl * z;
+        const double* zk1 = zk + z;
+        if (P.halo != nullptr && kl + 1 == P.nK - 1) zk1 = P.halo;
+        const double dts = zk[P.dt_off];
+        __syncthreads();  // previous item done with both generators and the scalars
+        if (active) {
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) Y0S[(nt * 2 + j) * 32 + lane] = (8 * tile + row8 == 8 * nt + 2 * q + j) ? 1.0 : 0.0;
+        }
+        // scalars of nodes 0 and 1, G(node 0), drift of node 1
+        NodeIter ahead{0, 0, 0, steps, K};
+        if (warp == nwarps - 1 && lane == 0) {
+            NodeIter it = ahead;
+            make_scal(I, zk, zk1, P.dt_off, it.time(), scal[0]);
+            it.next();
+            if (it.valid()) make_scal(I, zk, zk1, P.dt_off, it.time(), scal[1]);
+        }
+        ahead.next();
+        ahead.next();  // the node whose scalars are computed during right-hand side 0
+        prefetch_drift(G0b);
+        __syncthreads();
+        assemble(G0b, scal[0]);
+        prefetch_drift(G1b);
+        __syncthreads();
+
+        double Zp[1][NT][2], Zc[1][NT][2], D[1][NT][2];
+        int e = 0;
+        for (int ms = 0; ms < steps; ++ms) {
+            const double H = 1.0 / steps;
+            if (active)
+                for (int i = lane; i < FR; i += 32) AccS[i] = 0.0;
+            for (int k = 0; k < K; ++k) {
+                const int nk = 2 * (k + 1);
+                const double h = H / nk;
+                if (active) {
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt) {
+                        Zc[0][nt][0] = Y0S[(nt * 2) * 32 + lane];
+                        Zc[0][nt][1] = Y0S[(nt * 2 + 1) * 32 + lane];
+                    }
+                }
+                for (int qq = 0; qq <= nk; ++qq, ++e) {
+                    double* Gcur = (e & 1) ? G1b : G0b;
+                    double* Gnext = (e & 1) ? G0b : G1b;
+                    const bool last = (ms == steps - 1 && k == K - 1 && qq == nk);
+                    // the two warps of a scheduler take the two jobs in opposite order, so that one assembles
+                    // (shared-memory loads, few FMAs) while the other keeps the FP64 pipe busy with its products
+                    const bool asm_first = (warp & 4) != 0;
+                    if (asm_first && !last) assemble(Gnext, scal[(e + 1) & 1]);
+                    if (active) {
+                        frag_zero(D);
+                        mma_tile<NT>(D, Zc, Gcur, lane);
+#pragma unroll
+                        for (int nt = 0; nt < NT; ++nt) {
+                            D[0][nt][0] *= dts;
+                            D[0][nt][1] *= dts;
+                        }
+                        if (qq == 0) {
+#pragma unroll
+                            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                                for (int j = 0; j < 2; ++j) {
+                                    Zp[0][nt][j] = Zc[0][nt][j];
+                                    Zc[0][nt][j] = fma(h, D[0][nt][j], Zc[0][nt][j]);
+                                }
+                        } else if (qq < nk) {
+#pragma unroll
+                            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                                for (int j = 0; j < 2; ++j) {
+                                    const double znew = fma(2.0 * h, D[0][nt][j], Zp[0][nt][j]);
+                                    Zp[0][nt][j] = Zc[0][nt][j];
+                                    Zc[0][nt][j] = znew;
+                                }
+                        } else {
+#pragma unroll
+                            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                                for (int j = 0; j < 2; ++j)
+                                    AccS[(nt * 2 + j) * 32 + lane] += wk[k] * 0.5 * (Zc[0][nt][j] + Zp[0][nt][j] + h * D[0][nt][j]);
+                        }
+                    }
+                    if (!asm_first && !last) assemble(Gnext, scal[(e + 1) & 1]);  // G of the next node, behind this node's products
+                    if (warp == nwarps - 1 && lane == 0 && ahead.valid()) make_scal(I, zk, zk1, P.dt_off, ahead.time(), scal[e & 1]);
+                    ahead.next();
+                    __syncthreads();
+                    if (!last) prefetch_drift(Gcur);  // free now: drift entries of the node after next
+                }
+            }
+            if (active)
+                for (int i = lane; i < FR; i += 32) Y0S[i] = AccS[i];
+            __syncwarp();
+        }
+        if (active) {
+            double* jp = jac + (long long)b * P.nnz_jac_local;
+            const long long own_off = jac_own_off(P, kl, I.doff, n);
+            double* cp = jp + jac_col(P, kl, I.x_off + 8 * tile + row8) + own_off;
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                cp[8 * nt + 2 * q] = -Y0S[(nt * 2) * 32 + lane];
+                cp[8 * nt + 2 * q + 1] = -Y0S[(nt * 2 + 1) * 32 + lane];
+            }
+        }
+    }
+}
+
 struct Plan {
     int TF, TE, TA, split, warps, nbs;
     size_t smem;
@@ -772,13 +952,24 @@ void launch_nt_w(const DProb& P, int ii, const double* Z, const double* mu, doub
     static bool configured = false;
     if (!configured) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(tdb_exp_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         configured = true;
     }
     const DInt& I = P.in[ii];
     const int ctas = std::min(P.nI * P.batch, I.tdb_scratch_ctas / 2);  // persistent: one CTA per SM
-    dim3 grid((unsigned)ctas, pl.split ? 2 : 1);
-    kern<<<grid, pl.warps * 32, pl.smem, st>>>(P, ii, Z, mu, f.want_g ? g : nullptr, jac, f.want_jac ? 1 : 0, f.want_hess ? 1 : 0, 8,
-                                               I.steps, pl.TF, pl.TE, pl.TA, pl.split, pl.nbs, I.tdb_scratch);
+    if (!pl.split) {
+        kern<<<ctas, pl.warps * 32, pl.smem, st>>>(P, ii, Z, mu, f.want_g ? g : nullptr, jac, f.want_jac ? 1 : 0, f.want_hess ? 1 : 0, 8,
+                                                   I.steps, pl.TF, pl.TE, pl.TA, 0, pl.nbs, I.tdb_scratch);
+        return;
+    }
+    // split interval: forward + adjoint tiles in one kernel, the propagator tiles in the double-buffered one
+    kern<<<ctas, std::min(MAXW, std::max(pl.TF + pl.TA + 3, 4)) * 32, pl.smem, st>>>(P, ii, Z, mu, f.want_g ? g : nullptr, jac, f.want_jac ? 1 : 0,
+                                                                    f.want_hess ? 1 : 0, 8, I.steps, pl.TF, 0, pl.TA, 0, pl.nbs, I.tdb_scratch);
+    const int n = I.n, nbasis = 2 * I.m + I.n_carrier;
+    const size_t fixed = (2 * (size_t)n * n + 2 * sizeof(Scal) / sizeof(double) + 12) * sizeof(double);
+    const int nbs = (int)std::min<size_t>(nbasis, (226 * 1024 - fixed) / ((size_t)n * n * sizeof(double)));
+    tdb_exp_kernel<NT><<<ctas, std::max(pl.TE, 4) * 32, fixed + (size_t)nbs * n * n * sizeof(double), st>>>(P, ii, Z, jac, 8, I.steps, pl.TE, nbs,
+                                                                                                       I.tdb_scratch);
 }
 
 template <int NT>
