@@ -471,17 +471,24 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
                     else { has_next = false; sn = 0.0; }
                     if (has_next) make_scal(I, zk, zk1, P.dt_off, lane == 0 ? sn : 1.0 - sn, scal[((e + 1) & 1) * 2 + lane]);
                 }
-                if (TA > 0) {
-                    // basis' lambda on the FMA pipe, one output per thread, taken from the top of the CTA
+                // basis' lambda on the FMA pipe, one output per thread, taken from the top of the CTA.  It is a chain of
+                // dependent FMAs fed from shared memory (latency-bound): the two warps of a scheduler run it at
+                // opposite ends of the phase so that it hides behind the other warp's DMMAs.
+                auto adjoint_basis_products = [&]() {
                     for (int idx = (int)blockDim.x - 1 - (int)threadIdx.x; idx < nbasis * n; idx += blockDim.x) {
                         const int bi = idx / n, s = idx % n;
                         const double* Mb = basis_ptr(bi);
-                        double acc = 0.0;
+                        double acc0 = 0.0, acc1 = 0.0;
 #pragma unroll 8
-                        for (int kk = 0; kk < n; ++kk) acc = fma(Mb[sw<NT>(kk, s)], lam[kk], acc);
-                        PT[(size_t)bi * n + s] = acc;
+                        for (int kk = 0; kk < n; kk += 2) {
+                            acc0 = fma(Mb[sw<NT>(kk, s)], lam[kk], acc0);
+                            acc1 = fma(Mb[sw<NT>(kk + 1, s)], lam[kk + 1], acc1);
+                        }
+                        PT[(size_t)bi * n + s] = acc0 + acc1;
                     }
-                }
+                };
+                const bool matvec_first = (warp & 4) == 0;
+                if (TA > 0 && matvec_first) adjoint_basis_products();
                 if (couple) {
                     // basis products of the leading forward tile, one per warp, starting at the propagator warps
                     for (int bi = 0; bi < nbasis; ++bi) {
@@ -546,6 +553,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
                         D[0][nt][1] *= dts;
                     }
                 }
+                if (TA > 0 && !matvec_first) adjoint_basis_products();
 #ifdef DTO_TDB_PROFILE
                 long long tp4 = clock64();
 #endif
@@ -555,6 +563,9 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
 #endif
                 prefetch_drift();  // Gf is free again: fetch the drift entries of the next node
                 // ---- phase 3: parameter couplings, midpoint update ---------------------------------------
+#ifdef DTO_TDB_PROFILE
+                long long tc0 = clock64();
+#endif
                 if (role == W_FWD && couple) {
                     const int v = 8 * tile + row8;
                     if (v >= 1 && v < nvecF) {
@@ -591,6 +602,9 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
                         apply_terms<NT>(D, cf, C, PGa, 1, n, 0, q);
                     }
                 }
+#ifdef DTO_TDB_PROFILE
+                if (lane == 0 && blockIdx.x == 0) g_tdb_prof[blockIdx.y][warp][7] += (unsigned long long)(D[0][0][0] != 12345.678 ? clock64() - tc0 : 0);
+#endif
                 if (role != W_IDLE) {
                     if (qq == 0) {
 #pragma unroll

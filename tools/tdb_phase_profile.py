@@ -21,4 +21,4 @@ for y in range(2):
     for w in range(16):
         n = a[y, w, 6]
         if n == 0: continue
-        print(f"group {y} warp {w:2d}: " + "  ".join(f"{nm} {a[y, w, i] / n:7.0f}" for i, nm in enumerate(names)) + f"   total {a[y, w, :6].sum() / n:7.0f}  (rhs {int(n)})")
+        print(f"group {y} warp {w:2d}: " + "  ".join(f"{nm} {a[y, w, i] / n:7.0f}" for i, nm in enumerate(names)) + f"   total {a[y, w, :6].sum() / n:7.0f}  coupling-only {a[y, w, 7] / n:7.0f}  (rhs {int(n)})")
