@@ -590,12 +590,11 @@ void launch_hessian_assemble(const DProb& P, const double* Z, double sigma, cons
     int W = 8;
     while (W > 1 && W * GPW * per_group > 64 * 1024) W >>= 1;
     const size_t smem = W * GPW * per_group;
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
+    static PerDeviceOnce configured;
+    if (smem > 48 * 1024 && configured.first()) {
         cudaFuncSetAttribute(hessian_assemble_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         cudaFuncSetAttribute(hessian_assemble_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         cudaFuncSetAttribute(hessian_assemble_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        configured = 227 * 1024;
     }
     const long long total = (long long)nKc * P.batch;
     const unsigned grid = (unsigned)((total + (long long)W * GPW - 1) / ((long long)W * GPW));

@@ -496,10 +496,9 @@ bool launch_variant(const DProb& P, int ii, const double* Z, const double* mu, d
     const size_t smem = shared_part + W * per_warp;
     if (smem > 227 * 1024) return false;
     auto kern = bilinear_dmma_kernel<NT, MT>;
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configured;
+    if (configured.first()) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return false;
-        configured = true;
     }
     const int cpp = (P.nI + W - 1) / W;
     dim3 grid((unsigned)(cpp * P.batch), 1 + (f.want_jac ? 1 : 0) + (f.want_hess ? 1 : 0));

@@ -248,10 +248,9 @@ void launch_bilinear_generic(const DProb& P, int ii, const double* Z, const doub
     const DInt& I = P.in[ii];
     if (P.nI <= 0) return;
     size_t smem = generic_smem_bytes(I.n, I.m, f.want_jac, f.want_hess);
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
+    static PerDeviceOnce configured;
+    if (smem > 48 * 1024 && configured.first()) {
         cudaFuncSetAttribute(bilinear_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        configured = 227 * 1024;
     }
     bilinear_generic_kernel<<<P.nI * P.batch, 32, smem, st>>>(P, ii, Z, mu, f.want_g ? g : nullptr, jac, f.want_jac ? 1 : 0,
                                                                f.want_hess ? 1 : 0);

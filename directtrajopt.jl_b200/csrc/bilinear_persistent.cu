@@ -1204,10 +1204,9 @@ bool launch_product_nt(const DProb& P, int ii, const double* Z, const double* w,
     const int W = (int)std::min<size_t>(max_warps<NT>(), (budget - shared_part) / slot);
     const size_t smem = shared_part + (size_t)W * slot;
     auto kern = bilinear_product_kernel<NT>;
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configured;
+    if (configured.first()) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return false;
-        configured = true;
     }
     const long long items = (long long)P.batch * P.nI;
     const int grid = (int)std::max<long long>(1, std::min<long long>(sms, (items + W - 1) / W));
@@ -1257,10 +1256,9 @@ bool launch_variant(const DProb& P, int ii, const double* Z, const double* mu, d
     }
     const size_t smem = shared_part + (size_t)W * slot + (size_t)nE * 2 * mat;
     auto kern = bilinear_persistent_kernel<NT, MT>;
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configured;
+    if (configured.first()) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return false;
-        configured = true;
     }
     const long long items = (long long)P.batch * (std::min(P.kc1, P.nI) - P.kc0);
     const long long roles = 1 + (f.want_jac ? 1 : 0) + (f.want_hess ? 1 : 0);

@@ -111,6 +111,18 @@ __host__ __device__ inline bool hess_knot_has_cross(const DProb& P, int kl) { re
 // variants of the bilinear kernel
 enum { DTO_VAR_GENERIC = 0, DTO_VAR_DMMA = 1, DTO_VAR_PERSISTENT = 2 };
 
+// cudaFuncSetAttribute is per device: a launcher opts a kernel into large dynamic shared memory once per device
+struct PerDeviceOnce {
+    bool done[64] = {};
+    bool first() {
+        int d = 0;
+        if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return true;
+        if (done[d]) return false;
+        done[d] = true;
+        return true;
+    }
+};
+
 // ---- kernel launchers (defined in the .cu files) ------------------------------------------------
 struct EvalFlags {
     bool want_g, want_jac, want_hess;

@@ -405,10 +405,9 @@ void launch_tdb(const DProb& P, int ii, const double* Z, const double* mu, doubl
     const DInt& I = P.in[ii];
     if (P.nI <= 0) return;
     const size_t smem = tdb_smem_bytes(I, f.want_jac, f.want_hess);
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configured;
+    if (configured.first()) {
         cudaFuncSetAttribute(tdb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        configured = true;
     }
     const int K = 8;
     dim3 grid((unsigned)(P.nI * P.batch), 1 + (f.want_jac ? 1 : 0) + (f.want_hess ? 1 : 0));

@@ -963,11 +963,10 @@ template <int NT, int MAXW>
 void launch_nt_w(const DProb& P, int ii, const double* Z, const double* mu, double* g, double* jac, EvalFlags f, cudaStream_t st,
                  const Plan& pl) {
     auto kern = tdb_dmma_kernel<NT, MAXW>;
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configured;
+    if (configured.first()) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         cudaFuncSetAttribute(tdb_exp_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        configured = true;
     }
     const DInt& I = P.in[ii];
     const int ctas = std::min(P.nI * P.batch, I.tdb_scratch_ctas / 2);  // persistent: one CTA per SM
