@@ -13,7 +13,9 @@ from .components import (AbstractIntegrator, AbstractNonlinearConstraint, Abstra
                          CarrierGenerator, CompositeObjective, DerivativeIntegrator, IsoInfidelity, KnotFunction,
                          KnotPointObjective, LinearCost, LinearMap, LinearRegularizer, MinimumTimeObjective, NonlinearKnotPointConstraint,
                          NormMinus, NormSqMinus, NormSqPlus, NullObjective, QuadraticRegularizer, SqDist, SqDistMinus,
-                         TerminalObjective, TimeDependentBilinearIntegrator, UnsupportedComponent)
+                         TerminalObjective, TimeDependentBilinearIntegrator, UnsupportedComponent,
+                         GlobalObjective, GlobalKnotPointObjective, NonlinearGlobalConstraint, NonlinearGlobalKnotPointConstraint,
+                         NormProduct, SplitSqDist, KnotHVP, ConstantLowRankHVP, CustomKnotHVP, knot_hvp)
 from .evaluator import DirectTrajOptProblem, Evaluator
 from .trajectory import KnotPoint, NamedTrajectory
 from . import problem_templates

@@ -73,6 +73,18 @@ def LinearCost(c):
     return KnotFunction("linear", c)
 
 
+def SplitSqDist():
+    """l(v) = norm(v[:h] - v[h:])^2, h = len(v)/2: e.g. a state against a goal held in a global variable
+    (global_objectives.jl:364-369)"""
+    return KnotFunction("split_sqdist", [0.0])
+
+
+def NormProduct(n1, c1=1.0, c2=1.0):
+    """g(v) = [norm(v1) - c1; norm(v1) norm(v2) - c2] with v = [v1 (n1 entries); v2]: the reference's test function
+    for knot + global variables (global_knot_point_constraint.jl:267-270)"""
+    return KnotFunction("norm_product", [c1, c2, float(n1)], g_dim=2)
+
+
 def IsoInfidelity(goal):
     """l(psi_iso) = 1 - |<goal|psi>|^2 for iso-vectors [re; im]"""
     return KnotFunction("iso_infidelity", goal)
@@ -291,14 +303,91 @@ class KnotPointObjective(AbstractObjective):
         if self.Qs.shape != (len(self.times),):
             raise ValueError("Qs must have the same length as times")
         self.params = l.param_table(len(self.times))
+        self.knot_hvp = None  # optional KnotHVP carrier (knot_hvp.jl)
 
     def to_spec(self, traj):
         return {"kind": "knot", "fn": self.l.name, "names": self.var_names, "times": self.times, "params": self.params, "Qs": self.Qs}
 
 
-def TerminalObjective(l, names, traj, Q=1.0):
-    """``TerminalObjective(l, name(s), traj; Q)`` = KnotPointObjective at ``times=[N]`` (knot_point_objectives.jl:120-157)."""
+def _global_offsets(traj, global_names):
+    if global_names is None:  # auto-detect (global_objectives.jl:167-170)
+        global_names = list(traj.global_names)
+    if isinstance(global_names, str):
+        global_names = [global_names]
+    offs = []
+    for n in global_names:
+        offs += list(traj.global_components[n])
+    return list(global_names), np.asarray(offs, dtype=np.int32)
+
+
+class GlobalKnotPointObjective(AbstractObjective):
+    """``GlobalKnotPointObjective(l, names, global_names, traj; times, Qs)``:
+    J = sum_i Q_i l([knot vars at times[i]; global vars], params_i)  (global_objectives.jl:139-341).
+    ``global_names=None`` takes every global component of the trajectory."""
+
+    def __init__(self, l, names, global_names, traj, times=None, Qs=None):
+        if not isinstance(l, KnotFunction) or l.name not in _lib.L_FUNCS:
+            raise UnsupportedComponent("GlobalKnotPointObjective: l must be a KnotFunction from the device objective catalogue")
+        self.l = l
+        self.var_names, self.var_offs = _offsets(traj, names) if names else ([], np.zeros(0, np.int32))
+        self.global_names, self.gvar_offs = _global_offsets(traj, global_names)
+        self.times = list(range(1, traj.N + 1)) if times is None else [int(t) for t in times]
+        self.Qs = np.ones(len(self.times)) if Qs is None else np.asarray(Qs, float)
+        if self.Qs.shape != (len(self.times),):
+            raise ValueError("Qs must have the same length as times")
+        self.params = l.param_table(len(self.times))
+        self.knot_hvp = None
+
+    def to_spec(self, traj):
+        return {"kind": "global_knot", "fn": self.l.name, "names": self.var_names, "global_names": self.global_names,
+                "times": self.times, "params": self.params, "Qs": self.Qs}
+
+
+class GlobalObjective(GlobalKnotPointObjective):
+    """``GlobalObjective(l, global_names, traj; Q)``: J = Q l(global vars)  (global_objectives.jl:35-130).  Lowered to
+    a global-knot term without knot variables, listed once."""
+
+    def __init__(self, l, global_names, traj, Q=1.0):
+        super().__init__(l, [], global_names, traj, times=[1], Qs=[Q])
+        self.Q = float(Q)
+
+
+def TerminalObjective(l, names, traj, global_names=None, Q=1.0):
+    """``TerminalObjective(l, name(s), traj; Q)`` = KnotPointObjective at ``times=[N]`` (knot_point_objectives.jl:120-157);
+    with ``global_names`` the GlobalKnotPointObjective form (global_objectives.jl:347-389)."""
+    if global_names is not None:
+        return GlobalKnotPointObjective(l, names, global_names, traj, times=[traj.N], Qs=[Q])
     return KnotPointObjective(l, names, traj, times=[traj.N], Qs=[Q])
+
+
+# ---- KnotHVP: declarable per-knot Hessian-vector-product capability (knot_hvp.jl:45-148) -------
+# The reference defines only the carriers and the trait; the apply-math belongs to the consumer.
+class KnotHVP:
+    pass
+
+
+class ConstantLowRankHVP(KnotHVP):
+    """``ConstantLowRankHVP(A, core)``: per-knot Hessian H = A' G A with constant A (knot_hvp.jl:84-87)."""
+
+    def __init__(self, A, core):
+        self.A = np.asarray(A, float)
+        if self.A.ndim != 2:
+            raise ValueError("A must be a matrix")
+        self.core = str(core)
+
+
+class CustomKnotHVP(KnotHVP):
+    """``CustomKnotHVP(apply!, on_device)`` (knot_hvp.jl:122-125)."""
+
+    def __init__(self, apply, on_device):
+        self.apply = apply
+        self.on_device = bool(on_device)
+
+
+def knot_hvp(obj, traj):
+    """Trait: the declared per-knot HVP capability of ``obj``, or ``None`` (knot_hvp.jl:148 and the
+    KnotPointObjective method below it)."""
+    return getattr(obj, "knot_hvp", None)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -327,3 +416,35 @@ class NonlinearKnotPointConstraint(AbstractNonlinearConstraint):
     def to_spec(self, traj):
         return {"kind": "knot", "fn": self.g.name, "names": self.var_names, "times": self.times, "params": self.params,
                 "equality": self.equality}
+
+
+class NonlinearGlobalKnotPointConstraint(AbstractNonlinearConstraint):
+    """``NonlinearGlobalKnotPointConstraint(g, names, global_names, traj; times, equality)``: g([knot vars; global vars])
+    at every listed time (global_knot_point_constraint.jl:30-256)."""
+
+    def __init__(self, g, names, global_names, traj, times=None, equality=True):
+        if not isinstance(g, KnotFunction) or g.name not in _lib.G_FUNCS:
+            raise UnsupportedComponent("NonlinearGlobalKnotPointConstraint: g must be a KnotFunction from the device constraint catalogue")
+        self.g = g
+        self.var_names, self.var_offs = _offsets(traj, names) if names else ([], np.zeros(0, np.int32))
+        self.global_names, self.gvar_offs = _global_offsets(traj, global_names)
+        self.equality = bool(equality)
+        self.times = list(range(1, traj.N + 1)) if times is None else [int(t) for t in times]
+        self.params = g.param_table(len(self.times))
+        self.g_dim = g.g_dim
+        self.var_dim = len(self.var_offs)
+        self.global_dim = len(self.gvar_offs)
+        self.combined_dim = self.var_dim + self.global_dim
+        self.dim = self.g_dim * len(self.times)
+
+    def to_spec(self, traj):
+        return {"kind": "global_knot", "fn": self.g.name, "names": self.var_names, "global_names": self.global_names,
+                "times": self.times, "params": self.params, "equality": self.equality}
+
+
+class NonlinearGlobalConstraint(NonlinearGlobalKnotPointConstraint):
+    """``NonlinearGlobalConstraint(g, global_names, traj; equality)``: g(global vars) (global_constraint.jl:24-159).
+    Lowered to a global-knot constraint without knot variables, listed once (rows = g_dim)."""
+
+    def __init__(self, g, global_names, traj, equality=True):
+        super().__init__(g, [], global_names, traj, times=[1], equality=equality)

@@ -89,18 +89,19 @@ __global__ void constraint_kernel(DProb P, int ci, const double* __restrict__ Z,
     const int b = (int)(t / C.nt_own), j = (int)(t % C.nt_own);
     const int kl = C.own_knot[j];
     const double* zk = Z + (long long)b * P.n_vars_local + (long long)kl * P.z;
+    const double* gp = Z + (long long)b * P.n_vars_local + (long long)P.nK * P.z;  // global variables
     const double* p = C.params + (long long)C.own_ti[j] * C.np;
     const int nv = C.nv, gd = C.gd;
     if (g != nullptr) {
         double out[16];
-        knot_cfun<double>(C.fn, ValueVars{zk, C.var_offs}, nv, p, out, gd);
+        knot_cfun<double>(C.fn, ValueVars{zk, gp, C.var_offs, C.nvk}, nv, p, out, gd);
         double* gp = g + (long long)b * P.n_cons_local + C.row_off + (long long)j * gd;
         for (int a = 0; a < gd; ++a) gp[a] = out[a];
     }
     if (jac != nullptr || dense_probe != nullptr) {
         HDual out[16];
         for (int i = 0; i < nv; ++i) {
-            knot_cfun<HDual>(C.fn, SeededVars{zk, C.var_offs, i, -1}, nv, p, out, gd);
+            knot_cfun<HDual>(C.fn, SeededVars{zk, gp, C.var_offs, C.nvk, i, -1}, nv, p, out, gd);
             for (int a = 0; a < gd; ++a) {
                 const long long e = ((long long)j * gd + a) * nv + i;
                 if (dense_probe != nullptr) {
@@ -165,6 +166,7 @@ __global__ void hessian_assemble_kernel(DProb P, const double* __restrict__ Z, d
     double* diag = sm + (size_t)warp * tiles * z * z;  // z*z, entries (i<=l) used
     double* cross = diag + z * z;                      // z*z if any_cross: cross[i*z + l] = H[knot kl-1 comp i][knot kl comp l]
     const double* zk = Z + (long long)b * P.n_vars_local + (long long)kl * z;
+    const double* gpz = Z + (long long)b * P.n_vars_local + (long long)P.nK * z;  // global variables
     const double* mub = mu + (long long)b * P.n_cons_local;
     const bool has_cross = hess_knot_has_cross(P, kl);
     for (int e = tid; e < tiles * z * z; e += nt) diag[e] = 0.0;
@@ -232,14 +234,14 @@ __global__ void hessian_assemble_kernel(DProb P, const double* __restrict__ Z, d
         const DCon& C = P.co[ci];
         const int j = C.knot_to_own[kl];
         if (j >= 0) {
-            const int nv = C.nv, gd = C.gd;
+            const int nv = C.nv, nvk = C.nvk, gd = C.gd;  // (knot, global) and (global, global) entries: launch_global_hessian
             const double* p = C.params + (long long)C.own_ti[j] * C.np;
             const double* mup = mub + C.row_off + (long long)j * gd;
-            for (int e = tid; e < nv * nv; e += nt) {
-                const int a = e / nv, c = e % nv;
+            for (int e = tid; e < nvk * nvk; e += nt) {
+                const int a = e / nvk, c = e % nvk;
                 if (a > c) continue;
                 HDual out[16];
-                knot_cfun<HDual>(C.fn, SeededVars{zk, C.var_offs, a, c}, nv, p, out, gd);
+                knot_cfun<HDual>(C.fn, SeededVars{zk, gpz, C.var_offs, nvk, a, c}, nv, p, out, gd);
                 double s = 0.0;
                 for (int q = 0; q < gd; ++q) s = fma(mup[q], out[q].d12, s);
                 sym_add(diag, z, C.var_offs[a], C.var_offs[c], s);
@@ -319,7 +321,7 @@ __global__ void knot_objective_hessian_kernel(DProb P, int oi, const double* __r
     const DObj& O = P.ob[oi];
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= total) return;
-    const int nv = O.nv, npairs = nv * (nv + 1) / 2, z = P.z;
+    const int nv = O.nvk, npairs = nv * (nv + 1) / 2, z = P.z;  // pairs of knot variables
     const int pair = (int)(t % npairs);
     const long long r = t / npairs;
     const int j = (int)(r % O.nt_own), b = (int)(r / O.nt_own);
@@ -333,7 +335,8 @@ __global__ void knot_objective_hessian_kernel(DProb P, int oi, const double* __r
     if (kl < P.kc0 || kl >= P.kc1) return;  // assembled (and added to) by another launch of the pipeline
     const double* zk = Z + (long long)b * P.n_vars_local + (long long)kl * z;
     const double* prm = O.params + (long long)O.own_ti[j] * O.np;
-    const HDual res = knot_lfun<HDual>(O.fn, SeededVars{zk, O.var_offs, a, c}, nv, prm);
+    const double* gp = Z + (long long)b * P.n_vars_local + (long long)P.nK * z;
+    const HDual res = knot_lfun<HDual>(O.fn, SeededVars{zk, gp, O.var_offs, nv, a, c}, O.nv, prm);
     const double v = sigma * O.weight * O.Qs[O.own_ti[j]] * res.d12;
     int i = O.var_offs[a], l = O.var_offs[c];
     if (i > l) {
@@ -363,6 +366,7 @@ __global__ void objective_kernel(DProb P, const double* __restrict__ Z, double* 
     const int b = (int)(item / P.nOwn), kl = (int)(item % P.nOwn);
     double* gz = sm + (size_t)warp * z;
     const double* zk = Z + (long long)b * P.n_vars_local + (long long)kl * z;
+    const double* gp = Z + (long long)b * P.n_vars_local + (long long)P.nK * z;  // global variables
     const long long kg = (long long)P.kb - 1 + kl;  // global 0-based knot
     for (int e = tid; e < z; e += nt) gz[e] = 0.0;
     __syncwarp(gmask);
@@ -409,23 +413,25 @@ __global__ void objective_kernel(DProb P, const double* __restrict__ Z, double* 
                 gz[P.dt_off] += O.weight * O.D;
             }
             __syncwarp(gmask);
-        } else if (O.kind == DTO_OBJ_KNOT) {
+        } else if (O.kind == DTO_OBJ_KNOT || O.kind == DTO_OBJ_GLOBAL_KNOT) {
+            // knot part of the gradient; the global part is launch_global_gradient's
             const int j = O.knot_to_own[kl];
             if (j >= 0) {
-                const int nv = O.nv;
+                const int nv = O.nv, nvk = O.nvk;
                 const double* p = O.params + (long long)O.own_ti[j] * O.np;
                 const double w = O.weight * O.Qs[O.own_ti[j]];
-                for (int a = tid; a < nv; a += nt) {
-                    const HDual r = knot_lfun<HDual>(O.fn, SeededVars{zk, O.var_offs, a, -1}, nv, p);
-                    gz[O.var_offs[a]] += w * r.d1;
-                    if (a == 0) Jk += w * r.v;  // a == 0 is handled by lane 0
-                }
+                if (tid == 0) Jk += w * knot_lfun<double>(O.fn, ValueVars{zk, gp, O.var_offs, nvk}, nv, p);
+                if (grad != nullptr)
+                    for (int a = tid; a < nvk; a += nt) {
+                        const HDual r = knot_lfun<HDual>(O.fn, SeededVars{zk, gp, O.var_offs, nvk, a, -1}, nv, p);
+                        gz[O.var_offs[a]] += w * r.d1;
+                    }
             }
             __syncwarp(gmask);
         }
     }
     if (grad != nullptr)
-        for (int e = tid; e < z; e += nt) grad[((long long)b * P.nOwn + kl) * z + e] = gz[e];
+        for (int e = tid; e < z; e += nt) grad[(long long)b * P.n_grad_local + (long long)kl * z + e] = gz[e];
     if (tid == 0 && partials != nullptr) partials[(long long)b * P.nOwn + kl] = Jk;
 }
 
@@ -518,22 +524,24 @@ __global__ void constraint_product_kernel(DProb P, int ci, const double* __restr
     const int b = (int)(t / C.nt_own), j = (int)(t % C.nt_own);
     const int kl = C.own_knot[j];
     const double* zk = Z + (long long)b * P.n_vars_local + (long long)kl * P.z;
+    const double* gp = Z + (long long)b * P.n_vars_local + (long long)P.nK * P.z;
     const double* p = C.params + (long long)C.own_ti[j] * C.np;
     const int nv = C.nv, gd = C.gd;
     const long long row0 = (long long)b * P.n_cons_local + C.row_off + (long long)j * gd;
     const long long col0 = (long long)b * P.n_vars_local + (long long)kl * P.z;
+    const long long gcol0 = (long long)b * P.n_vars_local + (long long)P.nK * P.z;
     double acc[16];
     for (int a = 0; a < gd; ++a) acc[a] = 0.0;
     HDual out[16];
     for (int i = 0; i < nv; ++i) {
-        knot_cfun<HDual>(C.fn, SeededVars{zk, C.var_offs, i, -1}, nv, p, out, gd);
+        knot_cfun<HDual>(C.fn, SeededVars{zk, gp, C.var_offs, C.nvk, i, -1}, nv, p, out, gd);
         double col = 0.0;
         for (int a = 0; a < gd; ++a) {
             if (C.jac_pos[((long long)j * gd + a) * nv + i] < 0) continue;  // never stored by the reference: not part of J
-            if (!transpose) acc[a] = fma(out[a].d1, w[col0 + C.var_offs[i]], acc[a]);
+            if (!transpose) acc[a] = fma(out[a].d1, w[(i < C.nvk ? col0 : gcol0) + C.var_offs[i]], acc[a]);
             else col = fma(out[a].d1, w[row0 + a], col);
         }
-        if (transpose) atomicAdd(y + col0 + C.var_offs[i], col);
+        if (transpose) atomicAdd(y + (i < C.nvk ? col0 : gcol0) + C.var_offs[i], col);
     }
     if (!transpose)
         for (int a = 0; a < gd; ++a) y[row0 + a] = acc[a];
@@ -605,9 +613,9 @@ void launch_hessian_assemble(const DProb& P, const double* Z, double sigma, cons
     if (sigma != 0.0)
         for (int oi = 0; oi < P.n_obj; ++oi) {
             const DObj& O = P.ob[oi];
-            if (O.kind != DTO_OBJ_KNOT || O.nt_own == 0) continue;
+            if ((O.kind != DTO_OBJ_KNOT && O.kind != DTO_OBJ_GLOBAL_KNOT) || O.nt_own == 0 || O.nvk == 0) continue;
             if (O.own_kmax < P.kc0 || O.own_kmin >= P.kc1) continue;  // no listed knot in the active range
-            const long long tot = (long long)P.batch * O.nt_own * (O.nv * (O.nv + 1) / 2);
+            const long long tot = (long long)P.batch * O.nt_own * (O.nvk * (O.nvk + 1) / 2);
             knot_objective_hessian_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(P, oi, Z, sigma, hess, tot);
             ++*launches;
         }

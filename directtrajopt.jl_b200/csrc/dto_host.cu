@@ -46,6 +46,8 @@ struct dto_handle {
     std::vector<ConEntry> con_entries;         // stored constraint Jacobian entries (owned), sorted by (col, row)
     std::vector<std::vector<unsigned char>> con_stored_all;  // per constraint: stored mask over ALL times [ti][a][i]
     std::vector<int> row_is_eq;
+    int G = 0;                                             // traj.global_dim
+    std::vector<std::pair<long long, long long>> hess_tail;  // (global column gi, 0-based row) of the Hessian's global columns
     // device buffers
     double *dZ = nullptr, *dmu = nullptr, *dg = nullptr, *djac = nullptr, *dhess = nullptr, *dgrad = nullptr, *dJ = nullptr,
            *dpartials = nullptr, *dviol = nullptr, *dw = nullptr, *dy = nullptr;
@@ -144,6 +146,10 @@ extern "C" int dto_create(const dto_problem_desc* d, dto_handle** out) {
     h->k1 = h->sharded ? d->shard_k1 : N;
     if (h->k0 < 1 || h->k1 > N || h->k0 > h->k1) return fail_create(h, DTO_ERR_INVALID, "bad shard range");
     if (h->sharded && d->batch != 1) return fail_create(h, DTO_ERR_UNSUPPORTED, "knot-range shards require batch == 1");
+    const int G = d->global_dim;
+    if (G < 0 || G > 1024) return fail_create(h, DTO_ERR_INVALID, "global_dim outside 0..1024");
+    if (G > 0 && h->sharded) return fail_create(h, DTO_ERR_UNSUPPORTED, "knot-range shards do not support global variables");
+    h->G = G;
 
     DProb& P = h->P;
     memset(&P, 0, sizeof(P));
@@ -161,7 +167,9 @@ extern "C" int dto_create(const dto_problem_desc* d, dto_handle** out) {
     P.n_int = d->n_integrators;
     P.n_obj = d->n_objectives;
     P.n_con = d->n_constraints;
-    P.n_vars_local = (long long)P.nK * z;
+    P.n_vars_local = (long long)P.nK * z + G;
+    P.n_grad_local = (long long)P.nOwn * z + G;
+    P.gl.G = G;
 
     // ---- integrators -------------------------------------------------------------------------
     long long goff = 0, loff = 0;
@@ -287,13 +295,29 @@ extern "C" int dto_create(const dto_problem_desc* d, dto_handle** out) {
         O.fn = s.fn;
         O.weight = s.weight;
         O.nv = s.n_vars;
+        O.nvk = s.n_vars;
         O.nt = s.n_times;
         O.np = s.n_params;
         O.D = s.D;
         if (s.kind == DTO_OBJ_MINTIME || s.kind == DTO_OBJ_NULL) continue;
-        if (s.kind != DTO_OBJ_QUADREG && s.kind != DTO_OBJ_KNOT && s.kind != DTO_OBJ_LINREG) return fail_create(h, DTO_ERR_UNSUPPORTED, "unknown objective kind");
-        if (s.kind == DTO_OBJ_KNOT && !knot_lfun_known(s.fn)) return fail_create(h, DTO_ERR_UNSUPPORTED, "knot objective function is not in the device catalogue");
-        if (s.n_vars < 1 || s.n_vars > DTO_MAX_KNOTFN_VARS || !s.var_offs) return fail_create(h, DTO_ERR_INVALID, "objective: bad variable list");
+        if (s.kind != DTO_OBJ_QUADREG && s.kind != DTO_OBJ_KNOT && s.kind != DTO_OBJ_LINREG && s.kind != DTO_OBJ_GLOBAL_KNOT)
+            return fail_create(h, DTO_ERR_UNSUPPORTED, "unknown objective kind");
+        const bool with_globals = s.kind == DTO_OBJ_GLOBAL_KNOT;
+        if ((s.kind == DTO_OBJ_KNOT || with_globals) && !knot_lfun_known(s.fn))
+            return fail_create(h, DTO_ERR_UNSUPPORTED, "knot objective function is not in the device catalogue");
+        const int ngv = with_globals ? s.n_gvars : 0;
+        if (s.n_vars < (with_globals ? 0 : 1) || s.n_vars + ngv > DTO_MAX_KNOTFN_VARS || (s.n_vars > 0 && !s.var_offs))
+            return fail_create(h, DTO_ERR_INVALID, "objective: bad variable list");
+        if (with_globals && (ngv < 1 || !s.gvar_offs)) return fail_create(h, DTO_ERR_INVALID, "global objective: missing global variable list");
+        std::vector<int> all_offs(s.var_offs, s.var_offs + s.n_vars), g2l(G, -1);
+        for (int v = 0; v < ngv; ++v) {
+            const int go = s.gvar_offs[v];
+            if (go < 0 || go >= G) return fail_create(h, DTO_ERR_INVALID, "global objective: variable outside global_data");
+            if (g2l[go] >= 0) return fail_create(h, DTO_ERR_UNSUPPORTED, "global objective: repeated global variable");
+            g2l[go] = s.n_vars + v;
+            all_offs.push_back(go);
+        }
+        O.nv = s.n_vars + ngv;
         for (int v = 0; v < s.n_vars; ++v) {
             if (s.var_offs[v] < 0 || s.var_offs[v] >= z) return fail_create(h, DTO_ERR_INVALID, "objective: variable outside the knot");
             for (int v2 = 0; v2 < v; ++v2)
@@ -310,7 +334,8 @@ extern "C" int dto_create(const dto_problem_desc* d, dto_handle** out) {
                 ownk.push_back(k - h->k0);
             }
         }
-        O.var_offs = dev_upload(h, s.var_offs, s.n_vars);
+        O.var_offs = dev_upload(h, all_offs.data(), all_offs.size());
+        O.g2l = with_globals ? dev_upload(h, g2l.data(), g2l.size()) : nullptr;
         O.own_ti = dev_upload(h, own.data(), own.size());
         O.own_knot = dev_upload(h, ownk.data(), ownk.size());
         O.nt_own = (int)own.size();
@@ -338,9 +363,23 @@ extern "C" int dto_create(const dto_problem_desc* d, dto_handle** out) {
         const dto_constraint_desc& s = d->constraints[i];
         h->cons.push_back(s);
         if (!knot_cfun_known(s.fn)) return fail_create(h, DTO_ERR_UNSUPPORTED, "knot constraint function is not in the device catalogue");
-        if (s.n_vars < 1 || s.n_vars > DTO_MAX_KNOTFN_VARS || s.g_dim < 1 || s.g_dim > 16 || !s.var_offs)
+        const int ngv = s.n_gvars;
+        if (ngv < 0 || s.n_vars < 0 || s.n_vars + ngv < 1 || s.n_vars + ngv > DTO_MAX_KNOTFN_VARS || s.g_dim < 1 || s.g_dim > 16 ||
+            (s.n_vars > 0 && !s.var_offs) || (ngv > 0 && !s.gvar_offs))
             return fail_create(h, DTO_ERR_INVALID, "constraint: bad variable list or g_dim");
-        if (s.fn != DTO_G_LINEAR && s.g_dim != 1) return fail_create(h, DTO_ERR_INVALID, "constraint: g_dim must be 1 for this function");
+        if (s.fn == DTO_G_NORM_PRODUCT) {
+            if (s.g_dim != 2 || s.n_params < 3) return fail_create(h, DTO_ERR_INVALID, "constraint: norm_product has g_dim 2 and 3 parameters");
+        } else if (s.fn != DTO_G_LINEAR && s.g_dim != 1)
+            return fail_create(h, DTO_ERR_INVALID, "constraint: g_dim must be 1 for this function");
+        std::vector<int> all_offs(s.var_offs, s.var_offs + s.n_vars), g2l(G, -1);
+        for (int v = 0; v < ngv; ++v) {
+            const int go = s.gvar_offs[v];
+            if (go < 0 || go >= G) return fail_create(h, DTO_ERR_INVALID, "constraint: variable outside global_data");
+            if (g2l[go] >= 0) return fail_create(h, DTO_ERR_UNSUPPORTED, "constraint: repeated global variable");
+            g2l[go] = s.n_vars + v;
+            all_offs.push_back(go);
+        }
+        h->con_var_offs.push_back(all_offs);
         if (!d->Z0) return fail_create(h, DTO_ERR_INVALID, "knot constraints need the initial trajectory Z0 (stored Jacobian pattern)");
         for (int v = 0; v < s.n_vars; ++v) {
             if (s.var_offs[v] < 0 || s.var_offs[v] >= z) return fail_create(h, DTO_ERR_INVALID, "constraint: variable outside the knot");
@@ -349,7 +388,8 @@ extern "C" int dto_create(const dto_problem_desc* d, dto_handle** out) {
         }
         DCon& C = P.co[i];
         C.fn = s.fn;
-        C.nv = s.n_vars;
+        C.nv = s.n_vars + ngv;
+        C.nvk = s.n_vars;
         C.gd = s.g_dim;
         C.np = s.n_params;
         std::vector<int> k2o(P.nK, -1);
@@ -365,7 +405,8 @@ extern "C" int dto_create(const dto_problem_desc* d, dto_handle** out) {
         }
         C.nt_own = (int)h->con_own_ti[i].size();
         C.row_off = cloff;
-        C.var_offs = dev_upload(h, s.var_offs, s.n_vars);
+        C.var_offs = dev_upload(h, all_offs.data(), all_offs.size());
+        C.g2l = ngv > 0 ? dev_upload(h, g2l.data(), g2l.size()) : nullptr;
         C.own_ti = dev_upload(h, h->con_own_ti[i].data(), h->con_own_ti[i].size());
         C.own_knot = dev_upload(h, con_own_knot[i].data(), con_own_knot[i].size());
         C.knot_to_own = dev_upload(h, k2o.data(), k2o.size());
@@ -388,9 +429,9 @@ extern "C" int dto_create(const dto_problem_desc* d, dto_handle** out) {
         Q.nK = N;
         Q.nOwn = N;
         Q.nI = N - 1;
-        Q.n_vars_local = (long long)N * z;
+        Q.n_vars_local = (long long)N * z + G;
         Q.halo = nullptr;
-        double* dZ0 = dev_upload(h, d->Z0, (size_t)N * z);
+        double* dZ0 = dev_upload(h, d->Z0, (size_t)N * z + G);
         long long total = 0;
         std::vector<void*> tmp;
         for (int i = 0; i < d->n_constraints; ++i) {
@@ -404,7 +445,7 @@ extern "C" int dto_create(const dto_problem_desc* d, dto_handle** out) {
             C.nt_own = s.n_times;
             C.own_ti = dev_upload(h, all_ti.data(), all_ti.size());
             C.own_knot = dev_upload(h, all_k.data(), all_k.size());
-            total += (long long)s.n_times * s.g_dim * s.n_vars;
+            total += (long long)s.n_times * s.g_dim * (s.n_vars + s.n_gvars);
         }
         double* dprobe = dev_upload<double>(h, nullptr, (size_t)std::max<long long>(total, 1));
         launch_constraint_pattern_probe(Q, dZ0, dprobe, h->stream, &h->launches);
@@ -415,7 +456,7 @@ extern "C" int dto_create(const dto_problem_desc* d, dto_handle** out) {
         long long off = 0;
         for (int i = 0; i < d->n_constraints; ++i) {
             const dto_constraint_desc& s = d->constraints[i];
-            const long long cnt = (long long)s.n_times * s.g_dim * s.n_vars;
+            const long long cnt = (long long)s.n_times * s.g_dim * (s.n_vars + s.n_gvars);
             h->con_stored_all[i].resize((size_t)cnt);
             // SparseArrays' scalar setindex! does not store a zero value (either sign)
             for (long long e = 0; e < cnt; ++e) h->con_stored_all[i][(size_t)e] = probe[(size_t)(off + e)] != 0.0 ? 1 : 0;
@@ -424,17 +465,22 @@ extern "C" int dto_create(const dto_problem_desc* d, dto_handle** out) {
     }
 
     // ---- local Jacobian column pointers and constraint scatter maps ----------------------------
-    std::vector<long long> ccount((size_t)P.nK * z, 0);
+    // local column of variable v of constraint i at local knot kl: a knot column, or one of the G columns after them
+    auto con_col = [&](int i, int v, int kl) -> size_t {
+        return v < P.co[i].nvk ? (size_t)kl * z + h->con_var_offs[i][v] : (size_t)P.nK * z + h->con_var_offs[i][v];
+    };
+    std::vector<long long> ccount((size_t)P.nK * z + G, 0);
     for (int i = 0; i < d->n_constraints; ++i) {
         const dto_constraint_desc& s = d->constraints[i];
+        const int nv = P.co[i].nv;
         for (size_t j = 0; j < h->con_own_ti[i].size(); ++j) {
             const int ti = h->con_own_ti[i][j], kl = con_own_knot[i][j];
-            for (int v = 0; v < s.n_vars; ++v)
+            for (int v = 0; v < nv; ++v)
                 for (int a = 0; a < s.g_dim; ++a)
-                    if (h->con_stored_all[i][((size_t)ti * s.g_dim + a) * s.n_vars + v]) ccount[(size_t)kl * z + s.var_offs[v]]++;
+                    if (h->con_stored_all[i][((size_t)ti * s.g_dim + a) * nv + v]) ccount[con_col(i, v, kl)]++;
         }
     }
-    h->jac_colptr.assign((size_t)P.nK * z + 1, 0);
+    h->jac_colptr.assign((size_t)P.nK * z + G + 1, 0);
     for (int kl = 0; kl < P.nK; ++kl) {
         const long long per_col_int = (long long)P.Dsum * ((kl >= 1 ? 1 : 0) + (kl < P.nI ? 1 : 0));
         for (int l = 0; l < z; ++l) {
@@ -442,23 +488,29 @@ extern "C" int dto_create(const dto_problem_desc* d, dto_handle** out) {
             h->jac_colptr[c + 1] = h->jac_colptr[c] + per_col_int + ccount[c];
         }
     }
+    // global columns hold constraint entries only (integrators do not read globals: _integrators.jl:54-58)
+    for (int gi = 0; gi < G; ++gi) {
+        const size_t c = (size_t)P.nK * z + gi;
+        h->jac_colptr[c + 1] = h->jac_colptr[c] + ccount[c];
+    }
     P.nnz_jac_local = h->jac_colptr.back();
     P.jac_colptr = dev_upload(h, h->jac_colptr.data(), h->jac_colptr.size());
     P.jac_closed = h->con_entries.empty() && d->n_constraints == 0 ? 1 : 0;
     {
-        std::vector<long long> fill((size_t)P.nK * z, 0);
+        std::vector<long long> fill((size_t)P.nK * z + G, 0);
         for (int i = 0; i < d->n_constraints; ++i) {
             const dto_constraint_desc& s = d->constraints[i];
             DCon& C = P.co[i];
-            std::vector<long long> pos((size_t)C.nt_own * s.g_dim * s.n_vars, -1);
+            const int nv = C.nv;
+            std::vector<long long> pos((size_t)C.nt_own * s.g_dim * nv, -1);
             for (size_t j = 0; j < h->con_own_ti[i].size(); ++j) {
                 const int ti = h->con_own_ti[i][j], kl = con_own_knot[i][j];
-                for (int v = 0; v < s.n_vars; ++v)
+                for (int v = 0; v < nv; ++v)
                     for (int a = 0; a < s.g_dim; ++a) {
-                        if (!h->con_stored_all[i][((size_t)ti * s.g_dim + a) * s.n_vars + v]) continue;
-                        const size_t c = (size_t)kl * z + s.var_offs[v];
-                        const long long per_col_int = (long long)P.Dsum * ((kl >= 1 ? 1 : 0) + (kl < P.nI ? 1 : 0));
-                        const long long e = ((long long)j * s.g_dim + a) * s.n_vars + v;
+                        if (!h->con_stored_all[i][((size_t)ti * s.g_dim + a) * nv + v]) continue;
+                        const size_t c = con_col(i, v, kl);
+                        const long long per_col_int = v < C.nvk ? (long long)P.Dsum * ((kl >= 1 ? 1 : 0) + (kl < P.nI ? 1 : 0)) : 0;
+                        const long long e = ((long long)j * s.g_dim + a) * nv + v;
                         const long long p = h->jac_colptr[c] + per_col_int + fill[c]++;
                         pos[(size_t)e] = p;
                         ConEntry ce;
@@ -476,16 +528,112 @@ extern "C" int dto_create(const dto_problem_desc* d, dto_handle** out) {
                          [](const ConEntry& a, const ConEntry& b) { return a.e < b.e; });
     }
 
+    // ---- terms with global variables: slots, Hessian tail (the global columns) -----------------------
+    // Pattern: objective terms mark the dense [knot vars; globals]^2 block of every listed time
+    // (global_objectives.jl:268-291); constraint terms store what their Hessian at Z0 with mu = ones holds
+    // (evaluator.jl:168-171, global_knot_point_constraint.jl:205-249).  Upper triangle: a global column holds the
+    // coupled knot rows in ascending order, then the coupled global rows up to its own.
+    if (G > 0) {
+        DGlob& L = P.gl;
+        std::vector<int> slot_term, slot_j, slot_kl;
+        int KV = 0;
+        for (int i = 0; i < d->n_objectives; ++i)
+            if (P.ob[i].kind == DTO_OBJ_GLOBAL_KNOT) {
+                KV = std::max(KV, P.ob[i].nvk);
+                for (int t = 0; t < d->objectives[i].n_times; ++t) {  // not sharded: owned entry == position in `times`
+                    slot_term.push_back(i);
+                    slot_j.push_back(t);
+                    slot_kl.push_back(d->objectives[i].times[t] - 1);
+                }
+            }
+        L.S_obj = (int)slot_term.size();
+        for (int i = 0; i < d->n_constraints; ++i)
+            if (P.co[i].nv > P.co[i].nvk) {
+                KV = std::max(KV, P.co[i].nvk);
+                for (int t = 0; t < d->constraints[i].n_times; ++t) {
+                    slot_term.push_back(i);
+                    slot_j.push_back(t);
+                    slot_kl.push_back(d->constraints[i].times[t] - 1);
+                }
+            }
+        L.S = (int)slot_term.size();
+        L.KV = KV;
+        const int gtri = G * (G + 1) / 2;
+        if (L.S > 0) {
+            L.slot_term = dev_upload(h, slot_term.data(), slot_term.size());
+            L.slot_j = dev_upload(h, slot_j.data(), slot_j.size());
+            if (L.S_obj > 0) L.scratchG = dev_upload<double>(h, nullptr, (size_t)P.batch * L.S_obj * G);
+            L.scratchH = dev_upload<double>(h, nullptr, (size_t)P.batch * L.S * gtri);
+            if (!L.slot_term || !L.slot_j || !L.scratchH || (L.S_obj > 0 && !L.scratchG))
+                return fail_create(h, DTO_ERR_ALLOC, "device allocation failed (global terms)");
+        }
+        std::vector<double> kg_probe((size_t)L.S * std::max(KV, 1) * G, 0.0), gg_probe;
+        if (L.S > L.S_obj) {  // constraint Hessians at Z0, mu = ones, through the same device templates
+            if (!d->Z0) return fail_create(h, DTO_ERR_INVALID, "constraints need the initial trajectory Z0 (stored pattern)");
+            DProb Q = P;
+            Q.batch = 1;
+            double* dZ0 = dev_upload(h, d->Z0, (size_t)N * z + G);
+            double* dprobe = dev_upload<double>(h, nullptr, kg_probe.size());
+            launch_global_hessian(Q, dZ0, 1.0, nullptr, nullptr, dprobe, h->stream, &h->launches);
+            gg_probe.resize((size_t)L.S * gtri);
+            if (cudaMemcpyAsync(kg_probe.data(), dprobe, sizeof(double) * kg_probe.size(), cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
+                cudaMemcpyAsync(gg_probe.data(), L.scratchH, sizeof(double) * gg_probe.size(), cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
+                cudaStreamSynchronize(h->stream) != cudaSuccess)
+                return fail_create(h, DTO_ERR_CUDA, std::string("global Hessian pattern probe failed: ") + cudaGetErrorString(cudaGetLastError()));
+        }
+        auto pair_index = [&](int gi, int gj) { return gi * G - gi * (gi - 1) / 2 + (gj - gi); };  // gi <= gj
+        std::vector<std::pair<long long, long long>>& tail = h->hess_tail;
+        for (int sl = 0; sl < L.S; ++sl) {
+            const bool is_obj = sl < L.S_obj;
+            const int ti = slot_term[sl];
+            const int nvk = is_obj ? P.ob[ti].nvk : P.co[ti].nvk, nv = is_obj ? P.ob[ti].nv : P.co[ti].nv;
+            const int* koffs = is_obj ? d->objectives[ti].var_offs : d->constraints[ti].var_offs;
+            const int* goffs = is_obj ? d->objectives[ti].gvar_offs : d->constraints[ti].gvar_offs;
+            for (int v = nvk; v < nv; ++v) {
+                const int gi = goffs[v - nvk];
+                for (int a = 0; a < nvk; ++a)
+                    if (is_obj || kg_probe[((size_t)sl * KV + a) * G + gi] != 0.0)
+                        tail.emplace_back((long long)gi, (long long)slot_kl[sl] * z + koffs[a]);
+                for (int v2 = nvk; v2 < nv; ++v2) {
+                    const int g2 = goffs[v2 - nvk];
+                    if (g2 > gi) continue;
+                    if (is_obj || gg_probe[(size_t)sl * gtri + pair_index(g2, gi)] != 0.0) tail.emplace_back((long long)gi, (long long)N * z + g2);
+                }
+            }
+        }
+        std::sort(tail.begin(), tail.end());
+        tail.erase(std::unique(tail.begin(), tail.end()), tail.end());
+        auto find_pos = [&](long long gi, long long row) -> long long {
+            auto it = std::lower_bound(tail.begin(), tail.end(), std::make_pair(gi, row));
+            return (it != tail.end() && it->first == gi && it->second == row) ? (long long)(it - tail.begin()) : -1;
+        };
+        std::vector<long long> kg_pos((size_t)L.S * std::max(KV, 1) * G, -1), gg_pos((size_t)gtri, -1);
+        for (int sl = 0; sl < L.S; ++sl) {
+            const bool is_obj = sl < L.S_obj;
+            const int ti = slot_term[sl];
+            const int nvk = is_obj ? P.ob[ti].nvk : P.co[ti].nvk;
+            const int* koffs = is_obj ? d->objectives[ti].var_offs : d->constraints[ti].var_offs;
+            for (int a = 0; a < nvk; ++a)
+                for (int gi = 0; gi < G; ++gi) kg_pos[((size_t)sl * KV + a) * G + gi] = find_pos(gi, (long long)slot_kl[sl] * z + koffs[a]);
+        }
+        for (int gi = 0; gi < G; ++gi)
+            for (int gj = gi; gj < G; ++gj) gg_pos[(size_t)pair_index(gi, gj)] = find_pos(gj, (long long)N * z + gi);
+        L.kg_pos = dev_upload(h, kg_pos.data(), kg_pos.size());
+        L.gg_pos = dev_upload(h, gg_pos.data(), gg_pos.size());
+        L.n_hess_tail = (long long)tail.size();
+    }
+
     // ---- sizes -----------------------------------------------------------------------------------
     const long long tri = (long long)z * (z + 1) / 2;
-    P.nnz_hess_local = hess_knot_base(P, P.nOwn);  // base of the knot after the last owned one
-    h->sizes_local.n_vars = (long long)P.nOwn * z;
+    P.gl.hess_tail_off = hess_knot_base(P, P.nOwn);  // base of the knot after the last owned one
+    P.nnz_hess_local = P.gl.hess_tail_off + P.gl.n_hess_tail;
+    h->sizes_local.n_vars = (long long)P.nOwn * z + G;
     h->sizes_local.n_dynamics_cons = n_dyn_local;
     h->sizes_local.n_nonlinear_cons = P.n_cons_local - n_dyn_local;
     h->sizes_local.n_cons = P.n_cons_local;
     h->sizes_local.nnz_jac = P.nnz_jac_local;
     h->sizes_local.nnz_hess = P.nnz_hess_local;
-    h->sizes_global.n_vars = (long long)N * z;
+    h->sizes_global.n_vars = (long long)N * z + G;
     h->sizes_global.n_dynamics_cons = n_dyn_global;
     h->sizes_global.n_nonlinear_cons = n_nl_global;
     h->sizes_global.n_cons = n_dyn_global + n_nl_global;
@@ -494,7 +642,7 @@ extern "C" int dto_create(const dto_problem_desc* d, dto_handle** out) {
         for (auto& m : h->con_stored_all)
             for (unsigned char c : m) stored += c;
         h->sizes_global.nnz_jac = (long long)(N - 1) * P.Dsum * 2 * z + stored;
-        h->sizes_global.nnz_hess = (long long)N * tri + (long long)(N - 1) * z * z;
+        h->sizes_global.nnz_hess = (long long)N * tri + (long long)(N - 1) * z * z + P.gl.n_hess_tail;
     }
 
     // equality flags of the local rows
@@ -505,10 +653,8 @@ extern "C" int dto_create(const dto_problem_desc* d, dto_handle** out) {
     h->d_row_is_eq = dev_upload(h, h->row_is_eq.data(), h->row_is_eq.size());
 
     // keep host copies of small arrays the structure queries need
-    h->con_var_offs.resize(d->n_constraints);
     h->con_times.resize(d->n_constraints);
     for (int i = 0; i < d->n_constraints; ++i) {
-        h->con_var_offs[i].assign(d->constraints[i].var_offs, d->constraints[i].var_offs + d->constraints[i].n_vars);
         h->con_times[i].assign(d->constraints[i].times, d->constraints[i].times + d->constraints[i].n_times);
     }
 
@@ -518,7 +664,7 @@ extern "C" int dto_create(const dto_problem_desc* d, dto_handle** out) {
     h->dmu = dev_upload<double>(h, nullptr, B * (size_t)std::max<long long>(P.n_cons_local, 1));
     h->dg = dev_upload<double>(h, nullptr, B * (size_t)std::max<long long>(P.n_cons_local, 1));
     h->djac = dev_upload<double>(h, nullptr, B * (size_t)std::max<long long>(P.nnz_jac_local, 1));
-    h->dgrad = dev_upload<double>(h, nullptr, B * (size_t)P.nOwn * z);
+    h->dgrad = dev_upload<double>(h, nullptr, B * (size_t)P.n_grad_local);
     h->dJ = dev_upload<double>(h, nullptr, B);
     h->dviol = dev_upload<double>(h, nullptr, B);
     h->dpartials = dev_upload<double>(h, nullptr, B * ((size_t)P.nOwn + (size_t)(P.nOwn + 2047) / 2048));
@@ -596,6 +742,13 @@ extern "C" int dto_jac_structure(const dto_handle* h, int64_t* rows, int64_t* co
             }
         }
     }
+    for (int gi = 0; gi < h->G; ++gi)  // global columns: constraint rows only
+        while (ce < h->con_entries.size() && h->con_entries[ce].col_local == (long long)P.nK * z + gi) {
+            rows[w] = h->con_entries[ce].grow + 1;
+            cols[w] = (long long)P.N * z + gi + 1;
+            ++w;
+            ++ce;
+        }
     return w == P.nnz_jac_local ? DTO_OK : DTO_ERR_INVALID;
 }
 
@@ -620,6 +773,11 @@ extern "C" int dto_hess_structure(const dto_handle* h, int64_t* rows, int64_t* c
                 cols[w] = gcol;
             }
         }
+    }
+    for (const auto& e : h->hess_tail) {  // global columns
+        rows[w] = e.second + 1;
+        cols[w] = (long long)P.N * z + e.first + 1;
+        ++w;
     }
     return w == P.nnz_hess_local ? DTO_OK : DTO_ERR_INVALID;
 }
@@ -719,6 +877,7 @@ static void eval_prologue(dto_handle* h, const DProb& P, const double* dZ, doubl
                           EvalFlags f) {
     if (f.want_g || f.want_jac) launch_constraints(P, dZ, dg, djac, f, h->stream, &h->launches);
     if (dJ || dgrad) launch_objective(P, dZ, dJ, dgrad, h->dpartials, h->stream, &h->launches);
+    if (dgrad) launch_global_gradient(P, dZ, dgrad, h->stream, &h->launches);
 }
 
 // Interval kernels, analytic integrators and the Hessian assembler over the active knot range of P.
@@ -744,6 +903,7 @@ static void eval_range(dto_handle* h, const DProb& P, const double* dZ, double s
     }
     if (f.want_g || f.want_jac) launch_analytic(P, dZ, dg, djac, f, h->stream, &h->launches);
     if (f.want_hess) launch_hessian_assemble(P, dZ, sigma, dmu, dhess, h->stream, &h->launches);
+    if (f.want_hess) launch_global_hessian(P, dZ, sigma, dmu, dhess, nullptr, h->stream, &h->launches);
 }
 
 static int check_eval_args(dto_handle* h, const double* dmu, const double* dhess) {
@@ -773,7 +933,7 @@ static int run_eval(dto_handle* h, const double* dZ, double sigma, const double*
 // Every interval kernel of the problem honours DProb::kc0/kc1 (only the persistent bilinear variant does)
 static bool range_capable(const dto_handle* h) {
     const DProb& P = h->P;
-    if (P.batch != 1 || P.any_cross) return false;
+    if (P.batch != 1 || P.any_cross || P.gl.G > 0) return false;
     for (int i = 0; i < P.n_int; ++i)
         if (P.in[i].kind != DTO_INT_DERIVATIVE && !(P.in[i].kind == DTO_INT_BILINEAR && P.in[i].variant == DTO_VAR_PERSISTENT)) return false;
     return true;
@@ -859,7 +1019,7 @@ extern "C" int dto_eval_all(dto_handle* h, const double* Z, double sigma, const 
         CUDA_TRY(h, cudaGetLastError());
     }
     if (J) CUDA_TRY(h, cudaMemcpyAsync(J, h->dJ, sizeof(double) * B, cudaMemcpyDeviceToHost, h->stream));
-    if (grad) CUDA_TRY(h, cudaMemcpyAsync(grad, h->dgrad, sizeof(double) * B * P.nOwn * P.z, cudaMemcpyDeviceToHost, h->stream));
+    if (grad) CUDA_TRY(h, cudaMemcpyAsync(grad, h->dgrad, sizeof(double) * B * P.n_grad_local, cudaMemcpyDeviceToHost, h->stream));
     if (g) CUDA_TRY(h, cudaMemcpyAsync(g, h->dg, sizeof(double) * B * P.n_cons_local, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     if (pipelined) CUDA_TRY(h, cudaStreamSynchronize(h->copy_stream));
@@ -892,7 +1052,7 @@ extern "C" int dto_eval_hessian(dto_handle* h, const double* Z, double sigma, co
 // (evaluator.jl:406-456).  DTO_B200_JVP=materialize forces the latter.
 static bool matrix_free_capable(const dto_handle* h) {
     const DProb& P = h->P;
-    if (h->sharded) return false;
+    if (h->sharded || P.gl.G > 0) return false;
     const char* env = getenv("DTO_B200_JVP");
     if (env && strcmp(env, "materialize") == 0) return false;
     for (int i = 0; i < P.n_int; ++i)

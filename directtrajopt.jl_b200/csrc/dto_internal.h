@@ -37,8 +37,10 @@ struct DObj {
     int kind, fn;
     double weight;
     int nv, nt, np;
+    int nvk;                  // variables 0..nvk-1 are knot components, nvk..nv-1 global variables (nvk == nv without globals)
     double D;
-    const int* var_offs;
+    const int* var_offs;      // knot component offsets, then offsets into global_data
+    const int* g2l;           // terms with globals: [global_dim] -> variable index (>= nvk) or -1
     const int* own_ti;        // owned entries -> index into params/Qs (original position in `times`)
     const int* own_knot;      // owned entries -> local knot (0-based)
     int nt_own;
@@ -52,13 +54,31 @@ struct DObj {
 
 struct DCon {
     int fn, nv, nt_own, gd, np;
+    int nvk;                      // as in DObj
     long long row_off;            // local row of the first owned row
     const int* var_offs;
+    const int* g2l;
     const int* own_ti;
     const int* own_knot;          // local knot (0-based) of each owned entry
     const int* knot_to_own;
     const double* params;
     const long long* jac_pos;     // [nt_own][gd][nv] local Jacobian position or -1
+};
+
+// Terms that read global variables (global_objectives.jl, global_constraint.jl, global_knot_point_constraint.jl):
+// one "slot" per (term, listed time); objective slots first.
+struct DGlob {
+    int G;                    // traj.global_dim
+    int S, S_obj;             // slots; the first S_obj belong to objective terms
+    int KV;                   // largest number of knot variables among the terms with globals
+    const int* slot_term;     // objective index (s < S_obj) or constraint index
+    const int* slot_j;        // owned entry of the term
+    const long long* kg_pos;  // [S][KV][G]: position inside the Hessian tail of (knot variable a, global g) or -1
+    const long long* gg_pos;  // [G(G+1)/2]: position inside the Hessian tail of (g, g'), g <= g', or -1
+    double* scratchG;         // [batch][S_obj][G] per-slot gradient of the globals
+    double* scratchH;         // [batch][S][G(G+1)/2] per-slot global x global Hessian
+    long long hess_tail_off;  // local Hessian values: [knot regions | global columns]
+    long long n_hess_tail;
 };
 
 struct DProb {
@@ -73,7 +93,9 @@ struct DProb {
     int any_cross;        // some integrator produces cross-knot Hessian entries (tdbilinear order 1)
     int n_int, n_obj, n_con;
     int Dsum;       // sum of x_dim over integrators
-    long long n_vars_local;   // nK * z  (stride of one problem in the local Z buffer)
+    long long n_vars_local;   // nK * z + global_dim  (stride of one problem in the local Z buffer)
+    long long n_grad_local;   // nOwn * z + global_dim (stride of one problem's gradient)
+    DGlob gl;
     long long n_cons_local, nnz_jac_local, nnz_hess_local;
     const long long* jac_colptr;  // [nK*z + 1] local
     int jac_closed;               // no knot-constraint entries: column starts follow in closed form (no loads in the kernels)
@@ -153,6 +175,10 @@ void launch_hessian_assemble(const DProb& P, const double* Z, double sigma, cons
 void launch_objective(const DProb& P, const double* Z, double* J, double* grad, double* partials, cudaStream_t st,
                       long long* launches);
 void launch_violation(const DProb& P, const double* g, const int* row_is_eq, double* viol, cudaStream_t st, long long* launches);
+// terms with global variables: global part of the gradient, (knot, global) and (global, global) Hessian entries
+void launch_global_gradient(const DProb& P, const double* Z, double* grad, cudaStream_t st, long long* launches);
+void launch_global_hessian(const DProb& P, const double* Z, double sigma, const double* mu, double* hess, double* kg_probe,
+                           cudaStream_t st, long long* launches);
 void launch_jac_product(const DProb& P, const double* jac, const long long* rows0, const long long* cols0, const double* w,
                         double* y, bool transpose, cudaStream_t st, long long* launches);
 // knot-constraint Jacobian at a host point (used at construction for the stored pattern): runs the

@@ -34,18 +34,26 @@ __host__ __device__ inline HDual hd_sqrt(const HDual& a) {
 }
 __host__ __device__ inline double hd_sqrt(double a) { return sqrt(a); }
 
-// Variable accessors: the knot's variables are never copied into a per-thread array -- `V(i)` builds the
-// i-th (hyper-dual) variable on the fly from the trajectory, seeded in directions a and c.
+// Variable accessors: the variables are never copied into a per-thread array -- `V(i)` builds the i-th
+// (hyper-dual) variable on the fly, seeded in directions a and c.  Variables 0..nvk-1 are components of the
+// knot (`zk[offs[i]]`), variables nvk.. are global variables (`gp[offs[i]]`, global_objectives.jl:230-240,
+// global_knot_point_constraint.jl:151-155: [knot vars; global vars]).
 struct ValueVars {
     const double* zk;
+    const double* gp;
     const int* offs;
-    __host__ __device__ double operator()(int i) const { return zk[offs[i]]; }
+    int nvk;
+    __host__ __device__ double operator()(int i) const { return i < nvk ? zk[offs[i]] : gp[offs[i]]; }
 };
 struct SeededVars {
     const double* zk;
+    const double* gp;
     const int* offs;
+    int nvk;
     int a, c;  // seed directions of d1 and d2 (-1: none)
-    __host__ __device__ HDual operator()(int i) const { return HDual(zk[offs[i]], i == a ? 1.0 : 0.0, i == c ? 1.0 : 0.0, 0.0); }
+    __host__ __device__ HDual operator()(int i) const {
+        return HDual(i < nvk ? zk[offs[i]] : gp[offs[i]], i == a ? 1.0 : 0.0, i == c ? 1.0 : 0.0, 0.0);
+    }
 };
 
 // ---- constraint functions g(v; p) -> out[gd] ---------------------------------------------------
@@ -76,6 +84,15 @@ __host__ __device__ inline void knot_cfun(int fn, const Vars& v, int nv, const d
                 for (int i = 0; i < nv; ++i) s = s + v(i) * p[1 + a + (long long)i * gd];
                 out[a] = s - p[1 + (long long)gd * nv + a];
             }
+        } break;
+        case DTO_G_NORM_PRODUCT: {  // [norm(v1) - c1; norm(v1) norm(v2) - c2], p = [c1, c2, n1]
+            const int n1 = (int)p[2];
+            T s1 = T(0.0), s2 = T(0.0);
+            for (int i = 0; i < n1; ++i) s1 = s1 + v(i) * v(i);
+            for (int i = n1; i < nv; ++i) s2 = s2 + v(i) * v(i);
+            const T r1 = hd_sqrt(s1), r2 = hd_sqrt(s2);
+            out[0] = r1 - p[0];
+            out[1] = r1 * r2 - p[1];
         } break;
         default:
             for (int a = 0; a < gd; ++a) out[a] = T(0.0);
@@ -113,10 +130,19 @@ __host__ __device__ inline T knot_lfun(int fn, const Vars& v, int nv, const doub
             }
             return 1.0 - (a * a + b * b);
         }
+        case DTO_L_SPLIT_SQDIST: {  // norm(v[0:h] - v[h:2h])^2
+            const int h = nv / 2;
+            T s = T(0.0);
+            for (int i = 0; i < h; ++i) {
+                T d = v(i) - v(h + i);
+                s = s + d * d;
+            }
+            return s;
+        }
         default:
             return T(0.0);
     }
 }
 
-inline bool knot_cfun_known(int fn) { return fn >= DTO_G_NORM_MINUS_C && fn <= DTO_G_LINEAR; }
-inline bool knot_lfun_known(int fn) { return fn >= DTO_L_NORMSQ_PLUS_P && fn <= DTO_L_ISO_INFIDELITY; }
+inline bool knot_cfun_known(int fn) { return fn >= DTO_G_NORM_MINUS_C && fn <= DTO_G_NORM_PRODUCT; }
+inline bool knot_lfun_known(int fn) { return fn >= DTO_L_NORMSQ_PLUS_P && fn <= DTO_L_SPLIT_SQDIST; }

@@ -11,7 +11,8 @@ import numpy as np
 
 from . import _lib
 from .components import (AbstractIntegrator, AbstractNonlinearConstraint, AbstractObjective, BilinearIntegrator,
-                         CompositeObjective, DerivativeIntegrator, KnotPointObjective, MinimumTimeObjective, NullObjective,
+                         CompositeObjective, DerivativeIntegrator, GlobalKnotPointObjective, KnotPointObjective,
+                         MinimumTimeObjective, NullObjective, NonlinearGlobalKnotPointConstraint,
                          LinearRegularizer, QuadraticRegularizer, TimeDependentBilinearIntegrator, UnsupportedComponent)
 
 
@@ -43,6 +44,8 @@ class DirectTrajOptProblem:
         spec = {
             "N": t.N, "z": t.dim, "timestep": t.timestep,
             "components": {n: (t.components[n].start, len(t.components[n])) for n in t.names},
+            "global_dim": t.global_dim,
+            "global_components": {n: (t.global_components[n].start, len(t.global_components[n])) for n in t.global_names},
             "integrators": [i.to_spec() for i in self.integrators],
             "objectives": [], "constraints": [c.to_spec(t) for c in self.nonlinear_constraints()],
             "composite": isinstance(self.objective, CompositeObjective),
@@ -155,6 +158,17 @@ class Evaluator:
                 keep += [vo, tm, pr, Qs]
                 d.n_vars, d.var_offs, d.n_times, d.times = len(vo), _ip(vo), len(tm), _ip(tm)
                 d.n_params, d.params, d.Qs = pr.shape[1], _dp(pr), _dp(Qs)
+            elif isinstance(ob, GlobalKnotPointObjective):
+                d.kind = _lib.OBJ_GLOBAL_KNOT
+                d.fn = _lib.L_FUNCS[ob.l.name]
+                vo, go, tm = np.asarray(ob.var_offs, np.int32), np.asarray(ob.gvar_offs, np.int32), np.asarray(ob.times, np.int32)
+                pr, Qs = _f64(ob.params), _f64(ob.Qs)
+                keep += [vo, go, tm, pr, Qs]
+                d.n_vars, d.var_offs, d.n_times, d.times = len(vo), _ip(vo), len(tm), _ip(tm)
+                d.n_gvars, d.gvar_offs = len(go), _ip(go)
+                d.n_params, d.params, d.Qs = pr.shape[1], _dp(pr), _dp(Qs)
+                if len(go) == 0:  # no global variables at all: an ordinary knot objective
+                    d.kind = _lib.OBJ_KNOT
             elif isinstance(ob, NullObjective):
                 d.kind = _lib.OBJ_NULL
             else:
@@ -169,8 +183,12 @@ class Evaluator:
             keep += [vo, tm, pr]
             d.n_vars, d.var_offs, d.n_times, d.times = len(vo), _ip(vo), len(tm), _ip(tm)
             d.g_dim, d.n_params, d.params = c.g_dim, pr.shape[1], _dp(pr)
+            if isinstance(c, NonlinearGlobalKnotPointConstraint):
+                go = np.asarray(c.gvar_offs, np.int32)
+                keep.append(go)
+                d.n_gvars, d.gvar_offs = len(go), _ip(go)
 
-        Z0a = _f64(t.datavec if Z0 is None else Z0).reshape(-1)
+        Z0a = _f64(t.vec() if Z0 is None else Z0).reshape(-1)
         keep.append(Z0a)
         desc = _lib.ProblemDesc()
         desc.abi_version = _lib.ABI_VERSION
@@ -181,6 +199,7 @@ class Evaluator:
         desc.n_integrators, desc.n_objectives, desc.n_constraints = len(prob.integrators), len(terms), len(self.constraints)
         desc.integrators, desc.objectives, desc.constraints = ints, objs, cons
         desc.Z0 = _dp(Z0a)
+        desc.global_dim = t.global_dim
         h = C.c_void_p()
         rc = lib.dto_create(C.byref(desc), C.byref(h))
         if rc != _lib.DTO_OK:
@@ -202,7 +221,8 @@ class Evaluator:
         sl = _lib.ShardLayout()
         _lib.check(lib.dto_shard_info(h, C.byref(sl)), h)
         self.shard_layout = sl
-        self.n_z_in = sl.z_halo_end - sl.z_begin  # doubles of Z one call consumes (per problem)
+        self.global_dim = t.global_dim
+        self.n_z_in = sl.z_halo_end - sl.z_begin + t.global_dim  # doubles of Z one call consumes (per problem)
         self._jac_structure = None
         self._hess_structure = None
         if verbose:
@@ -250,7 +270,7 @@ class Evaluator:
 
     def eval_objective_gradient(self, grad, Z):
         Z = self._z(Z)
-        n = self.shard_layout.z_end - self.shard_layout.z_begin
+        n = self.shard_layout.z_end - self.shard_layout.z_begin + self.global_dim
         self._out(grad, self.batch * n)
         _lib.check(self._lib.dto_eval_gradient(self._h, Z.ctypes.data, grad.ctypes.data), self._h)
 

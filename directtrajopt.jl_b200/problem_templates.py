@@ -9,14 +9,18 @@ built through this package's mirror of the reference API with synthetic (seeded 
   scaled_problem            benchmark/problem_utils.jl:49-77  (BASELINE config c5 shape, c4 shape)
   quantum_gate_problem      BASELINE config c2: isomorphic state dim 32, 4 drives, free dt + MinimumTime
   carrier_problem           BASELINE config c3: TimeDependentBilinear + Derivative chain + knot constraints
+  global_problem            the standard problem with a global component and the reference's four global test
+                            terms (global_objectives.jl:393-475, global_constraint.jl:162-180,
+                            global_knot_point_constraint.jl:260-288)
 """
 from __future__ import annotations
 
 import numpy as np
 
-from .components import (BilinearIntegrator, CarrierGenerator, DerivativeIntegrator, LinearRegularizer, MinimumTimeObjective,
-                         NonlinearKnotPointConstraint, NormMinus, QuadraticRegularizer, SqDist, TerminalObjective,
-                         TimeDependentBilinearIntegrator)
+from .components import (BilinearIntegrator, CarrierGenerator, DerivativeIntegrator, GlobalKnotPointObjective, GlobalObjective,
+                         LinearRegularizer, MinimumTimeObjective, NonlinearGlobalConstraint, NonlinearGlobalKnotPointConstraint,
+                         NonlinearKnotPointConstraint, NormMinus, NormProduct, NormSqPlus, QuadraticRegularizer, SplitSqDist, SqDist,
+                         TerminalObjective, TimeDependentBilinearIntegrator)
 from .evaluator import DirectTrajOptProblem
 from .trajectory import NamedTrajectory
 
@@ -37,7 +41,7 @@ def readme_problem(N=50, seed=42):
     return DirectTrajOptProblem(traj, obj, integrator)
 
 
-def bilinear_dynamics_and_trajectory(N=10, dt=0.1, u_bound=0.1, omega=0.1, add_time=False, seed=0):
+def bilinear_dynamics_and_trajectory(N=10, dt=0.1, u_bound=0.1, omega=0.1, add_time=False, seed=0, add_global=False, global_dim=None):
     rng = np.random.default_rng(seed)
     G = lambda u: omega * GZ + u[0] * GX + u[1] * GY
     comps = {
@@ -49,8 +53,12 @@ def bilinear_dynamics_and_trajectory(N=10, dt=0.1, u_bound=0.1, omega=0.1, add_t
     }
     if add_time:
         comps["t"] = np.arange(N) * dt
+    glob = None
+    if add_global:  # add_component(traj, :g, randn(N), type = :global)  (test/test_utils.jl:173-175)
+        glob = {"g": rng.standard_normal(N if global_dim is None else global_dim)}
     traj = NamedTrajectory(comps, controls=("ddu", "dt"), timestep="dt", bounds={"u": u_bound, "dt": (0.01, 0.5)},
-                           initial={"x": [1.0, 0, 0, 0], "u": [0, 0]}, final={"u": [0, 0]}, goal={"x": [0.0, 1.0, 0, 0]})
+                           initial={"x": [1.0, 0, 0, 0], "u": [0, 0]}, final={"u": [0, 0]}, goal={"x": [0.0, 1.0, 0, 0]},
+                           global_components=glob)
     return G, traj
 
 
@@ -63,6 +71,33 @@ def standard_problem(N=10, seed=0):
     J = J + MinimumTimeObjective(traj)
     g_u_norm = NonlinearKnotPointConstraint(NormMinus(1.0), "u", traj, times=range(2, traj.N), equality=False)
     return DirectTrajOptProblem(traj, J, integrators, constraints=[g_u_norm])
+
+
+def global_problem(N=10, seed=0, global_dim=None, with_goal=True):
+    """The standard problem plus a global component ``g`` and every kind of global term, with the functions of the
+    reference's own tests: GlobalObjective norm(g)^2 (Q = 2), GlobalKnotPointObjective norm(u)^2 + norm(g)^2 at
+    times [1, N] (Qs [1, 2]), NonlinearGlobalConstraint norm(g) - 1 <= 0, NonlinearGlobalKnotPointConstraint
+    [norm(u) - 1; norm(u) norm(g) - 1] <= 0 at every knot; and the documented terminal objective
+    norm(x_N - x_goal)^2 with the goal held in a second global (global_objectives.jl:364-369)."""
+    rng = np.random.default_rng(seed + 100)
+    G, traj = bilinear_dynamics_and_trajectory(N=N, seed=seed, add_global=True, global_dim=global_dim)
+    if with_goal:
+        glob = {"g": traj.global_data.copy(), "x_goal": rng.standard_normal(4)}
+        _, traj = bilinear_dynamics_and_trajectory(N=N, seed=seed)
+        traj = NamedTrajectory({n: traj.data[traj.components[n], :] for n in traj.names}, controls=("ddu", "dt"), timestep="dt",
+                               goal=traj.goal, global_components=glob)
+    integrators = [BilinearIntegrator(G, "x", "u", traj), DerivativeIntegrator("u", "du", traj), DerivativeIntegrator("du", "ddu", traj)]
+    J = QuadraticRegularizer("u", traj, 1.0) + MinimumTimeObjective(traj)
+    J = J + GlobalObjective(NormSqPlus(0.0), "g", traj, Q=2.0)
+    J = J + 0.5 * GlobalKnotPointObjective(NormSqPlus(0.0), ["u"], ["g"], traj, times=[1, traj.N], Qs=[1.0, 2.0])
+    if with_goal:
+        J = J + TerminalObjective(SplitSqDist(), "x", traj, global_names="x_goal", Q=100.0)
+    cons = [
+        NonlinearKnotPointConstraint(NormMinus(1.0), "u", traj, times=range(2, traj.N), equality=False),
+        NonlinearGlobalKnotPointConstraint(NormProduct(2, 1.0, 1.0), ["u"], ["g"], traj, equality=False),
+        NonlinearGlobalConstraint(NormMinus(1.0), "g", traj, equality=False),
+    ]
+    return DirectTrajOptProblem(traj, J, integrators, constraints=cons)
 
 
 def linear_regularizer_problem(N=8, seed=1):

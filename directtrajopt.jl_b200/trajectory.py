@@ -30,7 +30,8 @@ class NamedTrajectory:
     order the knot is laid out.  ``timestep`` names the free time-step component (the reference's
     ``timestep::Symbol``)."""
 
-    def __init__(self, components, controls=(), timestep="dt", bounds=None, initial=None, final=None, goal=None):
+    def __init__(self, components, controls=(), timestep="dt", bounds=None, initial=None, final=None, goal=None,
+                 global_components=None):
         comps = OrderedDict()
         for name, arr in components.items():
             a = np.asarray(arr, dtype=np.float64)
@@ -58,12 +59,27 @@ class NamedTrajectory:
         self.initial = dict(initial or {})
         self.final = dict(final or {})
         self.goal = {k: np.asarray(v, float) for k, v in (goal or {}).items()}
-        self.global_dim = 0
-        self.global_data = np.zeros(0)
+        # global (non-time-varying) variables: appended to the knots in the solver's vector
+        # (NamedTrajectories' global_data / global_components; evaluator.jl:474-482)
+        self.global_components, self.global_dims = {}, {}
+        gvals, off = [], 0
+        for name, arr in (global_components or {}).items():
+            a = np.atleast_1d(np.asarray(arr, dtype=np.float64)).reshape(-1)
+            self.global_components[name] = range(off, off + a.size)
+            self.global_dims[name] = a.size
+            gvals.append(a)
+            off += a.size
+        self.global_names = tuple(self.global_components)
+        self.global_dim = off
+        self.global_data = np.concatenate(gvals) if gvals else np.zeros(0)
 
     @property
     def datavec(self):
         return self.data.reshape(-1, order="F")
+
+    def vec(self):
+        """``vec(traj)`` = [datavec; global_data], the solver's primal vector."""
+        return np.concatenate([self.datavec, self.global_data])
 
     def __getitem__(self, k):
         if not 1 <= k <= self.N:
@@ -79,9 +95,15 @@ class NamedTrajectory:
     def copy_with(self, datavec):
         t = object.__new__(NamedTrajectory)
         t.__dict__.update(self.__dict__)
-        t.data = np.asfortranarray(np.asarray(datavec, float).reshape(self.dim, self.N, order="F").copy())
+        v = np.asarray(datavec, float)
+        t.data = np.asfortranarray(v[: self.dim * self.N].reshape(self.dim, self.N, order="F").copy())
+        if v.size > self.dim * self.N:
+            t.global_data = v[self.dim * self.N :].copy()
         return t
 
     def update(self, Z):
-        """NamedTrajectories.update!(traj, Z; type=:both) for a problem without globals."""
-        self.data[...] = np.asarray(Z, float)[: self.dim * self.N].reshape(self.dim, self.N, order="F")
+        """NamedTrajectories.update!(traj, Z; type=:both)."""
+        Z = np.asarray(Z, float)
+        self.data[...] = Z[: self.dim * self.N].reshape(self.dim, self.N, order="F")
+        if self.global_dim:
+            self.global_data[...] = Z[self.dim * self.N : self.dim * self.N + self.global_dim]

@@ -20,11 +20,15 @@
  *   MOI.eval_constraint_jacobian_transpose_product         src/solvers/evaluator.jl:432     -> dto_eval_jacobian_transpose_product
  *   (benchmark/benchmarks.jl:23-38 times the five above on one iterate)                     -> dto_eval_all[_dev]
  *   get_nonlinear_constraints row bounds                   src/solvers/solve.jl:30-65       -> dto_constraint_bounds
+ *   GlobalObjective / GlobalKnotPointObjective             src/objectives/global_objectives.jl:35-341          -> DTO_OBJ_GLOBAL_KNOT terms
+ *   NonlinearGlobalConstraint                              src/constraints/nonlinear/global_constraint.jl:24-159 -> constraint with n_vars == 0
+ *   NonlinearGlobalKnotPointConstraint                     src/constraints/nonlinear/global_knot_point_constraint.jl:30-256 -> constraint with n_gvars > 0
  *
  * Conventions
  *   - all values are IEEE double, all structure indices are 1-based int64 in the reference's order
  *     (column-major findnz of the Jacobian; upper triangle, column-major, of the Hessian).
- *   - Z is the solver's primal vector [vec(data[z x N]); (no globals in scope)], knot-major.
+ *   - Z is the solver's primal vector [vec(data[z x N]); global_data[global_dim]], knot-major
+ *     (src/solvers/evaluator.jl:474-482); n_vars = z*N + global_dim.
  *   - every output buffer is owned and pre-allocated by the caller and is fully overwritten.
  *   - host-pointer entry points copy between the caller's buffers and device buffers owned by the handle and
  *     return after the stream has drained; with page-locked caller buffers the device->host copies of
@@ -48,7 +52,7 @@
 extern "C" {
 #endif
 
-#define DTO_B200_ABI_VERSION 1
+#define DTO_B200_ABI_VERSION 2
 
 typedef struct dto_handle dto_handle;
 
@@ -63,12 +67,26 @@ typedef enum {
 /* integrator kinds (src/integrators/) */
 enum { DTO_INT_BILINEAR = 1, DTO_INT_DERIVATIVE = 2, DTO_INT_TDBILINEAR = 3 };
 /* objective kinds (src/objectives/) */
-enum { DTO_OBJ_QUADREG = 1, DTO_OBJ_MINTIME = 2, DTO_OBJ_KNOT = 3, DTO_OBJ_NULL = 4, DTO_OBJ_LINREG = 5 };
+enum {
+    DTO_OBJ_QUADREG = 1, DTO_OBJ_MINTIME = 2, DTO_OBJ_KNOT = 3, DTO_OBJ_NULL = 4, DTO_OBJ_LINREG = 5,
+    /* J = sum_i Q_i l([knot vars at times[i]; global vars], p_i) (global_objectives.jl:139-341).  A GlobalObjective
+     * (global_objectives.jl:35-130) is the same term with n_vars == 0, times = [1], Qs = [Q]. */
+    DTO_OBJ_GLOBAL_KNOT = 6
+};
 /* device catalogue of knot constraint functions g(v; p) (replaces the Julia closure of
  * src/constraints/nonlinear/knot_point_constraint.jl:76-83) */
-enum { DTO_G_NORM_MINUS_C = 1, DTO_G_NORMSQ_MINUS_C = 2, DTO_G_SQDIST_MINUS_C = 3, DTO_G_LINEAR = 4 };
+enum {
+    DTO_G_NORM_MINUS_C = 1, DTO_G_NORMSQ_MINUS_C = 2, DTO_G_SQDIST_MINUS_C = 3, DTO_G_LINEAR = 4,
+    /* [norm(v1) - c1; norm(v1) norm(v2) - c2], v = [v1 (n1 entries); v2], p = [c1, c2, n1]: the reference's test
+     * function for knot + global variables (global_knot_point_constraint.jl:267-270) */
+    DTO_G_NORM_PRODUCT = 5
+};
 /* device catalogue of knot objective functions l(v; p) (src/objectives/knot_point_objectives.jl:65-72) */
-enum { DTO_L_NORMSQ_PLUS_P = 1, DTO_L_SQDIST = 2, DTO_L_LINEAR = 3, DTO_L_ISO_INFIDELITY = 4 };
+enum {
+    DTO_L_NORMSQ_PLUS_P = 1, DTO_L_SQDIST = 2, DTO_L_LINEAR = 3, DTO_L_ISO_INFIDELITY = 4,
+    /* norm(v[0:h] - v[h:2h])^2, h = n/2: state against a goal held in a global (global_objectives.jl:364-369) */
+    DTO_L_SPLIT_SQDIST = 5
+};
 
 /* One dynamics integrator (src/integrators/{bilinear,derivative,time_dependent_bilinear}_integrator.jl).
  * Component offsets are 0-based positions inside one knot. */
@@ -114,6 +132,9 @@ typedef struct {
     int32_t _pad;
     const double* params;    /* knot: n_times x n_params, row-major */
     const double* Qs;        /* knot: n_times weights */
+    int32_t n_gvars;         /* global_knot: global variables appended to the knot variables */
+    int32_t _pad2;
+    const int32_t* gvar_offs;/* 0-based positions inside global_data */
 } dto_objective_desc;
 
 /* One NonlinearKnotPointConstraint (src/constraints/nonlinear/knot_point_constraint.jl:27-107). */
@@ -127,6 +148,11 @@ typedef struct {
     int32_t g_dim;
     int32_t n_params;
     const double* params; /* n_times x n_params, row-major */
+    /* global variables appended to the knot variables: g([knot vars; global vars], p).  n_vars == 0 with
+     * times = [1] is a NonlinearGlobalConstraint (rows = g_dim). */
+    int32_t n_gvars;
+    int32_t _pad;
+    const int32_t* gvar_offs; /* 0-based positions inside global_data */
 } dto_constraint_desc;
 
 typedef struct {
@@ -145,14 +171,16 @@ typedef struct {
     const dto_integrator_desc* integrators;
     const dto_objective_desc* objectives;
     const dto_constraint_desc* constraints;
-    /* Initial trajectory ([batch][z*N]); knot-constraint Jacobian entries are stored only where the
+    /* Initial trajectory ([batch][z*N + global_dim]); knot-constraint Jacobian entries are stored only where the
      * derivative at this point is nonzero (src/solvers/evaluator.jl:134-144 + SparseArrays setindex!).
      * With batch > 1 problem 0 defines the pattern.  May be NULL when there are no knot constraints. */
     const double* Z0;
+    int32_t global_dim;  /* traj.global_dim: variables after the knots in Z (0 = none) */
+    int32_t _pad;
 } dto_problem_desc;
 
 typedef struct {
-    int64_t n_vars;           /* z*N */
+    int64_t n_vars;           /* z*N + global_dim */
     int64_t n_dynamics_cons;  /* sum_i d_i (N-1) */
     int64_t n_nonlinear_cons; /* sum_c g_dim_c * n_times_c */
     int64_t n_cons;

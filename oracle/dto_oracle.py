@@ -53,7 +53,26 @@ def dt_offset(spec):
 
 
 def _vars_of(spec, names):
+    if not names:
+        return np.zeros(0, dtype=np.int64)
     return np.concatenate([comp_range(spec, nm) for nm in names])
+
+
+def n_variables(spec):
+    """traj.dim * traj.N + traj.global_dim (evaluator.jl:123, :239)."""
+    return spec["N"] * spec["z"] + spec.get("global_dim", 0)
+
+
+def term_indices(spec, term, k):
+    """0-based positions in Z of the variables a knot term reads at 1-based knot k: its knot components, then -- for the
+    global variants -- the listed global variables at offset z*N  (global_objectives.jl:230-240,
+    global_knot_point_constraint.jl:151-155, global_constraint.jl:96-99)."""
+    idx = knot_slice(k, _vars_of(spec, term["names"]), spec["z"])
+    if term.get("kind") == "global_knot":
+        g = [np.arange(*(lambda od: (od[0], od[0] + od[1]))(spec["global_components"][nm]), dtype=np.int64) for nm in term["global_names"]]
+        gidx = spec["N"] * spec["z"] + (np.concatenate(g) if g else np.zeros(0, np.int64))
+        idx = np.concatenate([idx, gidx])
+    return idx
 
 
 # --------------------------------------------------------------------------------------------
@@ -82,6 +101,18 @@ def _cfun(fn, v, p):
         A = np.asarray(p[1 : 1 + gd * vd]).reshape(vd, gd).T
         b = np.asarray(p[1 + gd * vd : 1 + gd * vd + gd])
         return A @ v - b, A.copy(), np.zeros((gd, vd, vd))
+    if fn == "norm_product":  # [norm(v1) - c1; norm(v1) norm(v2) - c2], p = [c1, c2, n1]  (global_knot_point_constraint.jl:267-270)
+        n1 = int(p[2])
+        v1, v2 = v[:n1], v[n1:]
+        r1, r2 = np.linalg.norm(v1), np.linalg.norm(v2)
+        e1, e2 = np.zeros(vd), np.zeros(vd)
+        e1[:n1], e2[n1:] = v1 / r1, v2 / r2  # gradients of r1, r2
+        H1, H2 = np.zeros((vd, vd)), np.zeros((vd, vd))
+        H1[:n1, :n1] = (np.eye(n1) - np.outer(v1, v1) / r1**2) / r1
+        H2[n1:, n1:] = (np.eye(vd - n1) - np.outer(v2, v2) / r2**2) / r2
+        J = np.stack([e1, r2 * e1 + r1 * e2])
+        H = np.stack([H1, r2 * H1 + r1 * H2 + np.outer(e1, e2) + np.outer(e2, e1)])
+        return np.array([r1 - p[0], r1 * r2 - p[1]]), J, H
     raise ValueError(f"unknown constraint function {fn}")
 
 
@@ -104,6 +135,11 @@ def _lfun(fn, v, p):
         c2 = np.concatenate([-g[h:], g[:h]])
         a, b = c1 @ v, c2 @ v
         return 1 - (a * a + b * b), -2 * (a * c1 + b * c2), -2 * (np.outer(c1, c1) + np.outer(c2, c2))
+    if fn == "split_sqdist":  # norm(v[:h] - v[h:])^2  (global_objectives.jl:364-369)
+        h = vd // 2
+        d = v[:h] - v[h:]
+        I = np.eye(h)
+        return d @ d, np.concatenate([2 * d, -2 * d]), 2 * np.block([[I, -I], [-I, I]])
     raise ValueError(f"unknown objective function {fn}")
 
 
@@ -363,12 +399,10 @@ def _csc_order(rows, cols):
 def constraint_jacobian_entries(spec, c, Z):
     """eval_jacobian of a NonlinearKnotPointConstraint as COO triplets, 0-based local rows
     (knot_point_constraint.jl:254-268)."""
-    z = spec["z"]
-    comps = _vars_of(spec, c["names"])
     rows, cols, vals = [], [], []
     gd = None
     for i, k in enumerate(c["times"]):
-        idx = knot_slice(k, comps, z)
+        idx = term_indices(spec, c, k)
         val, J, _ = _cfun(c["fn"], Z[idx], np.atleast_1d(c["params"][i]))
         gd = val.size
         for a in range(gd):
@@ -380,18 +414,16 @@ def constraint_jacobian_entries(spec, c, Z):
 
 
 def constraint_dim(spec, c):
-    comps = _vars_of(spec, c["names"])
-    val, _, _ = _cfun(c["fn"], np.ones(comps.size), np.atleast_1d(c["params"][0]))
+    nvars = term_indices(spec, c, 1).size
+    val, _, _ = _cfun(c["fn"], np.ones(nvars), np.atleast_1d(c["params"][0]))
     return val.size * len(c["times"])
 
 
 def constraint_hessian_entries(spec, c, Z, mu):
     """eval_hessian_of_lagrangian of a NonlinearKnotPointConstraint (knot_point_constraint.jl:275-294)."""
-    z = spec["z"]
-    comps = _vars_of(spec, c["names"])
     rows, cols, vals = [], [], []
     for i, k in enumerate(c["times"]):
-        idx = knot_slice(k, comps, z)
+        idx = term_indices(spec, c, k)
         val, _, H = _cfun(c["fn"], Z[idx], np.atleast_1d(c["params"][i]))
         gd = val.size
         Hm = np.tensordot(mu[i * gd : (i + 1) * gd], H, axes=(0, 0))
@@ -455,10 +487,11 @@ def objective_hessian_pattern(spec, ob):
             vi = knot_slice(k, vc, z)
             rows.append(vi)
             cols.append(np.full(vi.size, (k - 1) * z + dto))
-    elif ob["kind"] == "knot":
-        comps = _vars_of(spec, ob["names"])
+    elif ob["kind"] in ("knot", "global_knot"):
+        # dense block over [knot vars; global vars] of every listed time (knot_point_objectives.jl:205-220,
+        # global_objectives.jl:92-106, :268-291)
         for k in ob["times"]:
-            vi = knot_slice(k, comps, z)
+            vi = term_indices(spec, ob, k)
             rr, cc = np.meshgrid(vi, vi, indexing="ij")
             rows.append(rr.ravel())
             cols.append(cc.ravel())
@@ -507,7 +540,7 @@ def hessian_structure(spec, Z0):
 
 def _objective_term(spec, ob, Z, want_grad, want_hess):
     N, z = spec["N"], spec["z"]
-    nv = N * z
+    nv = n_variables(spec)
     J = 0.0
     g = np.zeros(nv) if want_grad else None
     hr, hc, hv = [], [], []
@@ -560,15 +593,17 @@ def _objective_term(spec, ob, Z, want_grad, want_hess):
         J = ob["D"] * Z[idx].sum()
         if want_grad:
             g[idx] = ob["D"]
-    elif ob["kind"] == "knot":
-        comps = _vars_of(spec, ob["names"])
+    elif ob["kind"] in ("knot", "global_knot"):
         for i, k in enumerate(ob["times"]):
-            vi = knot_slice(k, comps, z)
+            vi = term_indices(spec, ob, k)
             val, gr, H = _lfun(ob["fn"], Z[vi], np.atleast_1d(ob["params"][i]))
             Q = ob["Qs"][i]
             J += Q * val
             if want_grad:
-                g[vi] = Q * gr
+                if ob["kind"] == "knot":
+                    g[vi] = Q * gr
+                else:  # '.+=' on both parts: the globals collect every listed time (global_objectives.jl:262-266)
+                    g[vi] += Q * gr
             if want_hess:
                 # ForwardDiff.hessian! of Q*l into a sparse view, then triu  (knot_point_objectives.jl:222-243)
                 for a in range(vi.size):
@@ -594,7 +629,7 @@ def eval_objective_gradient(spec, Z):
     (_objectives.jl:119-128).  A bare (non-composite) QuadraticRegularizer accumulates into the
     caller's buffer without zeroing in the reference (regularizers.jl:104,110); the oracle and the
     device path both define the buffer as zero-initialised (documented deviation)."""
-    g = np.zeros(spec["N"] * spec["z"])
+    g = np.zeros(n_variables(spec))
     for ob in spec["objectives"]:
         g += ob.get("weight", 1.0) * _objective_term(spec, ob, Z, True, False)[1]
     return g
@@ -622,9 +657,8 @@ def eval_constraint(spec, Z):
             r, _, _ = f(spec, it, Z[(k - 1) * z : k * z], Z[k * z : (k + 1) * z], None, want_jac=False)
             out.append(r)
     for c in spec.get("constraints", []):
-        comps = _vars_of(spec, c["names"])
         for i, k in enumerate(c["times"]):
-            val, _, _ = _cfun(c["fn"], Z[knot_slice(k, comps, z)], np.atleast_1d(c["params"][i]))
+            val, _, _ = _cfun(c["fn"], Z[term_indices(spec, c, k)], np.atleast_1d(c["params"][i]))
             out.append(val)
     return np.concatenate(out) if out else np.zeros(0)
 
@@ -663,7 +697,7 @@ def eval_constraint_jacobian(spec, Z, structure):
         off += constraint_dim(spec, c)
     if not rows:
         return np.zeros(0)
-    return _lookup(np.concatenate(rows), np.concatenate(cols), np.concatenate(vals), srows, scols, (nd + nn, N * z), False)
+    return _lookup(np.concatenate(rows), np.concatenate(cols), np.concatenate(vals), srows, scols, (nd + nn, n_variables(spec)), False)
 
 
 def eval_hessian_lagrangian(spec, Z, sigma, mu, structure):
@@ -701,7 +735,7 @@ def eval_hessian_lagrangian(spec, Z, sigma, mu, structure):
         return np.zeros(srows.size)
     rows, cols, vals = np.concatenate(rows), np.concatenate(cols), np.concatenate(vals)
     keep = rows <= cols  # 'if row <= col' (evaluator.jl:589, :614, :637)
-    return _lookup(rows[keep], cols[keep], vals[keep], srows, scols, (N * z, N * z), True)
+    return _lookup(rows[keep], cols[keep], vals[keep], srows, scols, (n_variables(spec), n_variables(spec)), True)
 
 
 # --------------------------------------------------------------------------------------------

@@ -35,13 +35,51 @@ def test_create_without_device_fails_loudly():
     assert "no CPU fallback" in str(e.value) or e.value.code == dto._lib.DTO_ERR_CUDA
 
 
-def test_struct_layout_matches_header():
-    # sizes the C compiler gives the descriptor structs (x86-64 SysV) -- guards the ctypes mirror
+def test_struct_layout_matches_header(tmp_path):
+    # sizes and field offsets the C compiler gives the descriptor structs of include/dto_b200.h -- guards the ctypes mirror
+    import subprocess
+
     L = dto._lib
-    assert ctypes.sizeof(L.IntegratorDesc) == 8 * 4 + 8 + 8 + 7 * 8 + 8
-    assert ctypes.sizeof(L.ObjectiveDesc) == 8 + 8 + 8 + 4 * 8 + 8 + 8 + 2 * 8
-    assert ctypes.sizeof(L.ConstraintDesc) == 16 + 16 + 8 + 8
-    assert ctypes.sizeof(L.SizeInfo) == 48
+    src = tmp_path / "layout.c"
+    src.write_text(
+        '#include <stdio.h>\n#include <stddef.h>\n#include "dto_b200.h"\n'
+        "int main(void) { printf(\"%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n\", sizeof(dto_integrator_desc), sizeof(dto_objective_desc),"
+        " sizeof(dto_constraint_desc), sizeof(dto_problem_desc), sizeof(dto_size_info), sizeof(dto_shard_layout),"
+        " offsetof(dto_objective_desc, gvar_offs), offsetof(dto_constraint_desc, gvar_offs), offsetof(dto_problem_desc, global_dim));"
+        " return 0; }\n")
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(v) for v in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    want = [ctypes.sizeof(L.IntegratorDesc), ctypes.sizeof(L.ObjectiveDesc), ctypes.sizeof(L.ConstraintDesc), ctypes.sizeof(L.ProblemDesc),
+            ctypes.sizeof(L.SizeInfo), ctypes.sizeof(L.ShardLayout), L.ObjectiveDesc.gvar_offs.offset, L.ConstraintDesc.gvar_offs.offset,
+            L.ProblemDesc.global_dim.offset]
+    assert got == want
+
+
+def test_global_trajectory_and_components():
+    """Global components sit after the knots in vec(traj); the global terms lower to one catalogue call on
+    [knot vars; global vars] (global_objectives.jl, global_constraint.jl, global_knot_point_constraint.jl)."""
+    prob = pt.global_problem(N=5)
+    t = prob.trajectory
+    assert t.global_names == ("g", "x_goal") and t.global_dim == 5 + 4
+    assert t.vec().size == t.dim * t.N + t.global_dim and np.array_equal(t.vec()[t.dim * t.N :], t.global_data)
+    spec = prob.to_spec()
+    assert spec["global_dim"] == 9 and spec["global_components"] == {"g": (0, 5), "x_goal": (5, 4)}
+    kinds = [o["kind"] for o in spec["objectives"]]
+    assert kinds.count("global_knot") == 3
+    gc = prob.nonlinear_constraints()[2]
+    assert isinstance(gc, dto.NonlinearGlobalConstraint) and gc.dim == 1 and gc.var_dim == 0 and gc.global_dim == 5
+    gk = prob.nonlinear_constraints()[1]
+    assert gk.dim == 2 * t.N and gk.combined_dim == 2 + 5
+    auto = dto.GlobalKnotPointObjective(dto.NormSqPlus(0.0), ["u"], None, t, times=[1])
+    assert auto.global_names == ["g", "x_goal"]
+    t2 = t.copy_with(np.arange(t.vec().size, dtype=float))
+    assert np.array_equal(t2.global_data, np.arange(t.dim * t.N, t.vec().size))
+    # KnotHVP carriers: the trait defaults to nothing (knot_hvp.jl:148)
+    ob = dto.KnotPointObjective(dto.NormSqPlus(0.0), "u", t)
+    assert dto.knot_hvp(ob, t) is None
+    ob.knot_hvp = dto.ConstantLowRankHVP(np.eye(2), "neg2_sign")
+    assert dto.knot_hvp(ob, t).core == "neg2_sign" and isinstance(dto.knot_hvp(ob, t), dto.KnotHVP)
 
 
 def test_generator_lowering_and_spec():

@@ -33,6 +33,8 @@ PROBLEMS = {
     "scaled": lambda: pt.scaled_problem(N=4, state_dim=5, n_controls=2, generator_scale=0.7),
     "gate": lambda: pt.quantum_gate_problem(N=4, levels=3, n_drives=2),
     "linreg": lambda: pt.linear_regularizer_problem(N=5),
+    "global": lambda: pt.global_problem(N=5),
+    "global_ref_fixture": lambda: pt.global_problem(N=4, with_goal=False),
 }
 
 
@@ -40,7 +42,7 @@ PROBLEMS = {
 def test_oracle_jacobian_vs_finite_differences(name):
     prob = PROBLEMS[name]()
     spec = prob.to_spec()
-    Z = prob.trajectory.datavec.copy()
+    Z = prob.trajectory.vec()
     st = orc.jacobian_structure(spec, Z)
     nd, nn = orc.n_constraints(spec)
     J = dense(orc.eval_constraint_jacobian(spec, Z, st), st, (nd + nn, Z.size))
@@ -52,7 +54,7 @@ def test_oracle_jacobian_vs_finite_differences(name):
 def test_oracle_gradient_and_hessian_vs_finite_differences(name):
     prob = PROBLEMS[name]()
     spec = prob.to_spec()
-    Z = prob.trajectory.datavec.copy()
+    Z = prob.trajectory.vec()
     rng = np.random.default_rng(3)
     nd, nn = orc.n_constraints(spec)
     mu = rng.random(nd + nn)
@@ -150,7 +152,7 @@ def test_quadreg_delta_t_squared_quirk():
     the docstring says."""
     prob = pt.readme_problem(N=3)
     spec = prob.to_spec()
-    Z = prob.trajectory.datavec.copy()
+    Z = prob.trajectory.vec()
     u = prob.trajectory.u[0]
     assert np.isclose(orc.eval_objective(spec, Z), 0.5 * np.sum((0.1 * u) ** 2))
 

@@ -78,6 +78,10 @@ PROBLEMS = {
     "n32_theta3": lambda: pt.scaled_problem(N=4, state_dim=32, n_controls=3, generator_scale=3.0),
     "n16_theta12": lambda: pt.scaled_problem(N=4, state_dim=16, n_controls=2, generator_scale=12.0),
     "zero_drive_n16": zero_drive_problem,
+    # global (non-time-varying) variables: all four global term kinds, the reference's test functions
+    "global": lambda: pt.global_problem(N=9),
+    "global_ref_fixture": lambda: pt.global_problem(N=6, with_goal=False),
+    "global_dim3": lambda: pt.global_problem(N=12, global_dim=3, seed=5),
 }
 
 
@@ -91,7 +95,7 @@ def case(request):
 
 def test_structures_bit_exact(case):
     name, prob, ev = case
-    spec, Z = prob.to_spec(), prob.trajectory.datavec.copy()
+    spec, Z = prob.to_spec(), prob.trajectory.vec()
     jr, jc = ev.jacobian_structure()
     orow, ocol = orc.jacobian_structure(spec, Z)
     assert jr.size == orow.size and np.array_equal(jr, orow) and np.array_equal(jc, ocol)
@@ -106,9 +110,10 @@ def test_values_match_oracle(case):
     name, prob, ev = case
     spec = prob.to_spec()
     rng = np.random.default_rng(7)
-    Z0 = prob.trajectory.datavec.copy()
+    Z0 = prob.trajectory.vec()
     Z = Z0 + 0.05 * rng.standard_normal(Z0.size)  # an iterate away from the initial point
-    Z[spec["components"][spec["timestep"]][0] :: spec["z"]] = np.abs(Z[spec["components"][spec["timestep"]][0] :: spec["z"]])
+    dts = slice(spec["components"][spec["timestep"]][0], spec["N"] * spec["z"], spec["z"])
+    Z[dts] = np.abs(Z[dts])
     jst, hst = orc.jacobian_structure(spec, Z0), orc.hessian_structure(spec, Z0)
     mu = rng.random(ev.n_constraints)
     sigma = 2.0
@@ -135,7 +140,7 @@ def test_values_match_oracle(case):
 def test_fused_eval_all_equals_separate_callbacks(case):
     name, prob, ev = case
     rng = np.random.default_rng(11)
-    Z = prob.trajectory.datavec.copy()
+    Z = prob.trajectory.vec()
     mu = rng.random(ev.n_constraints)
     Jv, grad = np.empty(1), np.empty(ev.n_vars)
     g, jac, hess = np.empty(ev.n_constraints), np.empty(ev.nnz_jacobian), np.empty(ev.nnz_hessian)
@@ -153,7 +158,7 @@ def test_jacobian_products(case):
     """evaluator.jl:808-853: products vs the dense Jacobian, atol 1e-10."""
     name, prob, ev = case
     rng = np.random.default_rng(5)
-    Z = prob.trajectory.datavec.copy()
+    Z = prob.trajectory.vec()
     jr, jc = ev.jacobian_structure()
     vals = np.empty(ev.nnz_jacobian)
     ev.eval_constraint_jacobian(vals, Z)
@@ -194,6 +199,29 @@ def test_matrix_free_products_match_materialised(monkeypatch):
         for a, b in zip(res[""][:2], res["materialize"][:2]):
             assert relerr(a, b) <= 1e-12
     monkeypatch.delenv("DTO_B200_JVP", raising=False)
+
+
+def test_global_variables_in_a_batch_and_on_shards():
+    """Batches carry their own global variables ([batch][z*N + global_dim]); knot-range shards reject them."""
+    prob = pt.global_problem(N=7, seed=2)
+    rng = np.random.default_rng(9)
+    B = 3
+    Z = np.stack([prob.trajectory.vec() + 0.03 * rng.standard_normal(prob.trajectory.vec().size) for _ in range(B)])
+    ev1, evb = dto.Evaluator(prob), dto.Evaluator(prob, batch=B)
+    mu = rng.random((B, ev1.n_constraints))
+    Jb, gradb = np.empty(B), np.empty((B, ev1.n_vars))
+    gb, jacb, hessb = np.empty((B, ev1.n_constraints)), np.empty((B, ev1.nnz_jacobian)), np.empty((B, ev1.nnz_hessian))
+    evb.eval_all(Z, 1.3, mu, Jb, gradb, gb, jacb, hessb)
+    for b in range(B):
+        J, grad = np.empty(1), np.empty(ev1.n_vars)
+        g, jac, hess = np.empty(ev1.n_constraints), np.empty(ev1.nnz_jacobian), np.empty(ev1.nnz_hessian)
+        ev1.eval_all(Z[b], 1.3, mu[b], J, grad, g, jac, hess)
+        assert J[0] == Jb[b] and np.array_equal(grad, gradb[b]) and np.array_equal(g, gb[b])
+        assert np.array_equal(jac, jacb[b]) and np.array_equal(hess, hessb[b])
+    with pytest.raises(dto.UnsupportedComponent):
+        dto.Evaluator(prob, shard=(1, 4))
+    ev1.close()
+    evb.close()
 
 
 def test_features_and_bounds():
@@ -237,7 +265,7 @@ def test_tdbilinear_matches_exact_variational_solution(order, n, m, carriers):
                                                      omega_d=1.0 + rng.random(carriers), phi_d=rng.random(carriers))
     spec = prob.to_spec()
     ev = dto.Evaluator(prob)
-    Z0 = prob.trajectory.datavec.copy()
+    Z0 = prob.trajectory.vec()
     Z = Z0 + 0.02 * rng.standard_normal(Z0.size)
     jst, hst = orc.jacobian_structure(spec, Z0), orc.hessian_structure(spec, Z0)
     jr, jc = ev.jacobian_structure()
@@ -265,7 +293,7 @@ def test_tdbilinear_variants_agree(monkeypatch):
     """The tensor-core variant of K7 and the CUDA-core variant integrate the same equations with the same
     extrapolation scheme: they must agree far below the parity tolerance (and the dispatch must pick them)."""
     prob = pt.carrier_problem(N=6, state_dim=16, n_drives=2, spline_order=1, dt=0.2)
-    Z = prob.trajectory.datavec.copy()
+    Z = prob.trajectory.vec()
     outs = {}
     for pin in ("", "generic"):
         if pin:
@@ -286,7 +314,7 @@ def test_host_pipeline_matches_single_pass(monkeypatch):
     blocks leave over PCIe while later ranges are computed; the result must be bit-identical to the
     single-pass evaluation, whatever the chunk plan (and with knot constraints + a derivative integrator)."""
     prob = pt.scaled_problem(N=700, state_dim=32, n_controls=2, generator_scale=0.3)
-    Z = prob.trajectory.datavec.copy()
+    Z = prob.trajectory.vec()
     outs = {}
     for plan in ("0", "0.12,0.55", "0.05,0.2,0.5,0.9"):
         monkeypatch.setenv("DTO_B200_PIPELINE", plan)
