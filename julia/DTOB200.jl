@@ -16,7 +16,7 @@ using NamedTrajectories
 using DirectTrajOpt
 
 const LIB = get(ENV, "DTO_B200_LIB", joinpath(@__DIR__, "..", "directtrajopt.jl_b200", "lib", "libdto_b200.so"))
-const ABI_VERSION = Cint(1)
+const ABI_VERSION = Cint(2)
 
 # ---- mirror of the C descriptor structs (include/dto_b200.h) -------------------------------------
 struct IntegratorDesc
@@ -30,15 +30,18 @@ struct ObjectiveDesc
     kind::Cint; fn::Cint; weight::Cdouble; n_vars::Cint; n_times::Cint
     var_offs::Ptr{Cint}; times::Ptr{Cint}; R::Ptr{Cdouble}; baseline::Ptr{Cdouble}; D::Cdouble
     n_params::Cint; _pad::Cint; params::Ptr{Cdouble}; Qs::Ptr{Cdouble}
+    n_gvars::Cint; _pad2::Cint; gvar_offs::Ptr{Cint}
 end
 struct ConstraintDesc
     fn::Cint; equality::Cint; n_vars::Cint; n_times::Cint
     var_offs::Ptr{Cint}; times::Ptr{Cint}; g_dim::Cint; n_params::Cint; params::Ptr{Cdouble}
+    n_gvars::Cint; _pad::Cint; gvar_offs::Ptr{Cint}
 end
 struct ProblemDesc
     abi_version::Cint; N::Cint; z::Cint; dt_off::Cint; batch::Cint; eval_hessian::Cint
     shard_k0::Cint; shard_k1::Cint; device::Cint; n_integrators::Cint; n_objectives::Cint; n_constraints::Cint
     integrators::Ptr{IntegratorDesc}; objectives::Ptr{ObjectiveDesc}; constraints::Ptr{ConstraintDesc}; Z0::Ptr{Cdouble}
+    global_dim::Cint; _pad::Cint
 end
 struct SizeInfo
     n_vars::Int64; n_dynamics_cons::Int64; n_nonlinear_cons::Int64; n_cons::Int64; nnz_jac::Int64; nnz_hess::Int64
@@ -50,9 +53,16 @@ struct NormMinus <: KnotFunction; c::Float64; end            # g(v) = [norm(v) -
 struct NormSqMinus <: KnotFunction; c::Float64; end          # g(v) = [norm(v)^2 - c]
 struct SqDist <: KnotFunction; target::Vector{Float64}; end  # l(v) = norm(v - target)^2
 struct IsoInfidelity <: KnotFunction; goal::Vector{Float64}; end
-cfun_id(::NormMinus) = Cint(1); cfun_id(::NormSqMinus) = Cint(2)
-lfun_id(::SqDist) = Cint(2); lfun_id(::IsoInfidelity) = Cint(4)
+struct NormSqPlus <: KnotFunction; p::Float64; end           # l(v) = norm(v)^2 + p
+struct SplitSqDist <: KnotFunction; end                      # l(v) = norm(v[1:h] - v[h+1:2h])^2 (state vs a goal held in a global)
+struct NormProduct <: KnotFunction; n1::Int; c1::Float64; c2::Float64; end  # g(v) = [norm(v1) - c1; norm(v1) norm(v2) - c2]
+cfun_id(::NormMinus) = Cint(1); cfun_id(::NormSqMinus) = Cint(2); cfun_id(::NormProduct) = Cint(5)
+lfun_id(::NormSqPlus) = Cint(1); lfun_id(::SqDist) = Cint(2); lfun_id(::IsoInfidelity) = Cint(4); lfun_id(::SplitSqDist) = Cint(5)
 params(f::NormMinus) = [f.c]; params(f::NormSqMinus) = [f.c]; params(f::SqDist) = f.target; params(f::IsoInfidelity) = f.goal
+params(f::NormSqPlus) = [f.p]; params(::SplitSqDist) = [0.0]; params(f::NormProduct) = [f.c1, f.c2, Float64(f.n1)]
+# 0-based positions inside traj.global_data of the listed global components
+goffs(traj, names) = isempty(names) ? Cint[] : Cint.(vcat([collect(traj.global_components[n]) for n in names]...) .- 1)
+koffs(traj, names) = isempty(names) ? Cint[] : Cint.(vcat([collect(traj.components[n]) for n in names]...) .- 1)
 
 """Lower `G::Function` of a BilinearIntegrator to (G_drift, G_drives) by probing; error if G is not affine in u
 (no CPU fallback: unsupported components raise at construction, never mid-solve)."""
@@ -117,13 +127,13 @@ function B200Evaluator(prob; eval_hessian = true, knot_functions = Dict())
             vo = Cint.(collect(traj.components[ob.name]) .- 1); tm = Cint.(ob.times); R = copy(ob.R); base = copy(ob.baseline)
             append!(keep, (vo, tm, R, base))
             push!(objs, ObjectiveDesc(1, 0, w, length(vo), length(tm), pointer(vo), pointer(tm), pointer(R),
-                                      any(!iszero, base) ? pointer(base) : C_NULL, 0.0, 0, 0, C_NULL, C_NULL))
+                                      any(!iszero, base) ? pointer(base) : C_NULL, 0.0, 0, 0, C_NULL, C_NULL, 0, 0, C_NULL))
         elseif ob isa LinearRegularizer
             vo = Cint.(collect(traj.components[ob.name]) .- 1); tm = Cint.(ob.times); R = copy(ob.R)
             append!(keep, (vo, tm, R))
-            push!(objs, ObjectiveDesc(5, 0, w, length(vo), length(tm), pointer(vo), pointer(tm), pointer(R), C_NULL, 0.0, 0, 0, C_NULL, C_NULL))
+            push!(objs, ObjectiveDesc(5, 0, w, length(vo), length(tm), pointer(vo), pointer(tm), pointer(R), C_NULL, 0.0, 0, 0, C_NULL, C_NULL, 0, 0, C_NULL))
         elseif ob isa MinimumTimeObjective
-            push!(objs, ObjectiveDesc(2, 0, w, 0, 0, C_NULL, C_NULL, C_NULL, C_NULL, ob.D, 0, 0, C_NULL, C_NULL))
+            push!(objs, ObjectiveDesc(2, 0, w, 0, 0, C_NULL, C_NULL, C_NULL, C_NULL, ob.D, 0, 0, C_NULL, C_NULL, 0, 0, C_NULL))
         elseif ob isa KnotPointObjective
             f = get(knot_functions, ob, nothing)
             f === nothing && error("KnotPointObjective needs a catalogue entry in `knot_functions`")
@@ -131,9 +141,21 @@ function B200Evaluator(prob; eval_hessian = true, knot_functions = Dict())
             pr = repeat(params(f), length(tm)); Qs = copy(ob.Qs)
             append!(keep, (vo, tm, pr, Qs))
             push!(objs, ObjectiveDesc(3, lfun_id(f), w, length(vo), length(tm), pointer(vo), pointer(tm), C_NULL, C_NULL, 0.0,
-                                      length(params(f)), 0, pointer(pr), pointer(Qs)))
+                                      length(params(f)), 0, pointer(pr), pointer(Qs), 0, 0, C_NULL))
+        elseif ob isa GlobalKnotPointObjective || ob isa GlobalObjective
+            # J = sum_i Q_i l([knot vars; global vars]) (global_objectives.jl:139-341); a GlobalObjective is the same term
+            # without knot variables, listed once with Qs = [Q] (global_objectives.jl:35-130)
+            f = get(knot_functions, ob, nothing)
+            f === nothing && error("$(typeof(ob)) needs a catalogue entry in `knot_functions`")
+            isknot = ob isa GlobalKnotPointObjective
+            vo = isknot ? koffs(traj, ob.var_names) : Cint[]; go = goffs(traj, ob.global_names)
+            tm = isknot ? Cint.(ob.times) : Cint[1]; Qs = isknot ? copy(ob.Qs) : [ob.Q]
+            pr = repeat(params(f), length(tm))
+            append!(keep, (vo, go, tm, pr, Qs))
+            push!(objs, ObjectiveDesc(6, lfun_id(f), w, length(vo), length(tm), isempty(vo) ? C_NULL : pointer(vo), pointer(tm), C_NULL, C_NULL,
+                                      0.0, length(params(f)), 0, pointer(pr), pointer(Qs), length(go), 0, pointer(go)))
         elseif ob isa NullObjective
-            push!(objs, ObjectiveDesc(4, 0, w, 0, 0, C_NULL, C_NULL, C_NULL, C_NULL, 0.0, 0, 0, C_NULL, C_NULL))
+            push!(objs, ObjectiveDesc(4, 0, w, 0, 0, C_NULL, C_NULL, C_NULL, C_NULL, 0.0, 0, 0, C_NULL, C_NULL, 0, 0, C_NULL))
         else
             error("objective $(typeof(ob)) has no device lowering")
         end
@@ -142,16 +164,25 @@ function B200Evaluator(prob; eval_hessian = true, knot_functions = Dict())
     cons = ConstraintDesc[]
     for c in nl
         f = get(knot_functions, c, nothing)
-        (c isa NonlinearKnotPointConstraint && f !== nothing) || error("constraint $(typeof(c)) needs a catalogue entry")
-        vo = Cint.(vcat([collect(traj.components[n]) for n in c.var_names]...) .- 1); tm = Cint.(c.times)
-        pr = repeat(params(f), length(tm)); append!(keep, (vo, tm, pr))
-        push!(cons, ConstraintDesc(cfun_id(f), c.equality, length(vo), length(tm), pointer(vo), pointer(tm), c.g_dim,
-                                   length(params(f)), pointer(pr)))
+        f !== nothing || error("constraint $(typeof(c)) needs a catalogue entry")
+        if c isa NonlinearKnotPointConstraint
+            vo = koffs(traj, c.var_names); go = Cint[]; tm = Cint.(c.times); gd = c.g_dim
+        elseif c isa NonlinearGlobalKnotPointConstraint   # global_knot_point_constraint.jl:30-256
+            vo = koffs(traj, c.var_names); go = goffs(traj, c.global_names); tm = Cint.(c.times); gd = c.g_dim
+        elseif c isa NonlinearGlobalConstraint            # global_constraint.jl:24-159: no knot variables, listed once
+            vo = Cint[]; go = goffs(traj, c.global_names); tm = Cint[1]; gd = c.dim
+        else
+            error("constraint $(typeof(c)) has no device lowering")
+        end
+        pr = repeat(params(f), length(tm)); append!(keep, (vo, go, tm, pr))
+        push!(cons, ConstraintDesc(cfun_id(f), c.equality, length(vo), length(tm), isempty(vo) ? C_NULL : pointer(vo), pointer(tm), gd,
+                                   length(params(f)), pointer(pr), length(go), 0, isempty(go) ? C_NULL : pointer(go)))
     end
-    Z0 = collect(traj.datavec)
+    Z0 = vcat(collect(traj.datavec), collect(traj.global_data))   # the solver's vector: [knots; globals]
     desc = Ref(ProblemDesc(ABI_VERSION, traj.N, traj.dim, off(traj.timestep), 1, eval_hessian, 0, 0, -1,
                            length(ints), length(objs), length(cons),
-                           pointer(ints), isempty(objs) ? C_NULL : pointer(objs), isempty(cons) ? C_NULL : pointer(cons), pointer(Z0)))
+                           pointer(ints), isempty(objs) ? C_NULL : pointer(objs), isempty(cons) ? C_NULL : pointer(cons), pointer(Z0),
+                           traj.global_dim, 0))
     h = Ref{Ptr{Cvoid}}(C_NULL)
     GC.@preserve keep ints objs cons Z0 begin
         rc = ccall((:dto_create, LIB), Cint, (Ref{ProblemDesc}, Ref{Ptr{Cvoid}}), desc, h)
