@@ -25,65 +25,12 @@
 #include <stdlib.h>
 
 #include "dto_internal.h"
+#include "series_tables.cuh"
 
 namespace {
 
 constexpr int kMaxDrives = 4;
 constexpr int kMaxWarps = 12;
-
-__constant__ double kInvFact[64] = {
-    1.0, 1.0, 0.5, 0.16666666666666666,
-    0.041666666666666664, 0.008333333333333333, 0.001388888888888889, 0.0001984126984126984,
-    2.48015873015873e-05, 2.7557319223985893e-06, 2.755731922398589e-07, 2.505210838544172e-08,
-    2.08767569878681e-09, 1.6059043836821613e-10, 1.1470745597729725e-11, 7.647163731819816e-13,
-    4.779477332387385e-14, 2.8114572543455206e-15, 1.5619206968586225e-16, 8.22063524662433e-18,
-    4.110317623312165e-19, 1.9572941063391263e-20, 8.896791392450574e-22, 3.868170170630684e-23,
-    1.6117375710961184e-24, 6.446950284384474e-26, 2.4795962632247976e-27, 9.183689863795546e-29,
-    3.279889237069838e-30, 1.1309962886447716e-31, 3.7699876288159054e-33, 1.216125041553518e-34,
-    3.8003907548547434e-36, 1.151633562077195e-37, 3.387157535521162e-39, 9.67759295863189e-41,
-    2.6882202662866363e-42, 7.265460179153071e-44, 1.911963205040282e-45, 4.902469756513544e-47,
-    1.2256174391283858e-48, 2.9893108271424046e-50, 7.117406731291439e-52, 1.6552108677421951e-53,
-    3.7618428812322616e-55, 8.359650847182804e-57, 1.817315401561479e-58, 3.866628513960594e-60,
-    8.055476070751236e-62, 1.643974708316579e-63, 3.287949416633158e-65, 6.446959640457172e-67,
-    1.2397999308571486e-68, 2.3392451525606576e-70, 4.331935467704922e-72, 7.876246304918039e-74,
-    1.4064725544496498e-75, 2.4674957095607893e-77, 4.254302947518602e-79, 7.2106829618959365e-81,
-    1.2017804936493226e-82, 1.9701319568021682e-84, 3.1776321883905942e-86, 5.043860616493007e-88};
-
-// kTermThr[T] = (2^-56 T!)^(1/T): theta <= kTermThr[T]  <=>  theta^T / T! <= 2^-56;  kInv[t] = 1/t
-__constant__ double kTermThr[64] = {
-    0.0, 1.3877787807814457e-17, 5.268356063861754e-09, 4.366738290990188e-06,
-    0.00013509300777591815, 0.0011073892359697531, 0.004640970307744105, 0.013203184215395689,
-    0.029408989058618194, 0.05554895835340545, 0.09337020827678473, 0.14404487618659187,
-    0.20823549866087968, 0.2861946964536857, 0.3778659482136564, 0.4829712994609099,
-    0.6010820235361274, 0.7316729269701641, 0.8741627421291117, 1.0279434021622011,
-    1.1924007567545727, 1.366928857608371, 1.5509394972483046, 1.7438682928017233,
-    1.9451782866329281, 2.1543617854833412, 2.3709409688061474, 2.594467653547391,
-    2.8245224960110504, 3.060713832769101, 3.3026763048201806, 3.5500693669735828,
-    3.802575753674299, 4.059899950157507, 4.3217667016810974, 4.5879195819761005,
-    4.858119633758812, 5.132144088270396, 5.409785166693326, 5.690848963457876,
-    5.975154409543074, 6.262532312636557, 6.552824470257129, 6.845882851524014,
-    7.141568843076471, 7.43975255463284, 7.740312179775477, 8.043133407718637,
-    8.348108882032204, 8.65513770253534, 8.964124966826535, 9.27498134817052,
-    9.587622706711219, 9.901969731219332, 10.217947608810235, 10.535485720281251,
-    10.854517358916425, 11.174979470791282, 11.49681241478032, 11.819959740626354,
-    12.144367983574272, 12.46998647420296, 12.796767162208864, 13.124664453003925};
-__constant__ double kInv[64] = {
-    0.0, 1.0, 0.5, 0.3333333333333333,
-    0.25, 0.2, 0.16666666666666666, 0.14285714285714285,
-    0.125, 0.1111111111111111, 0.1, 0.09090909090909091,
-    0.08333333333333333, 0.07692307692307693, 0.07142857142857142, 0.06666666666666667,
-    0.0625, 0.058823529411764705, 0.05555555555555555, 0.05263157894736842,
-    0.05, 0.047619047619047616, 0.045454545454545456, 0.043478260869565216,
-    0.041666666666666664, 0.04, 0.038461538461538464, 0.037037037037037035,
-    0.03571428571428571, 0.034482758620689655, 0.03333333333333333, 0.03225806451612903,
-    0.03125, 0.030303030303030304, 0.029411764705882353, 0.02857142857142857,
-    0.027777777777777776, 0.02702702702702703, 0.02631578947368421, 0.02564102564102564,
-    0.025, 0.024390243902439025, 0.023809523809523808, 0.023255813953488372,
-    0.022727272727272728, 0.022222222222222223, 0.021739130434782608, 0.02127659574468085,
-    0.020833333333333332, 0.02040816326530612, 0.02, 0.0196078431372549,
-    0.019230769230769232, 0.018867924528301886, 0.018518518518518517, 0.01818181818181818,
-    0.017857142857142856, 0.017543859649122806, 0.017241379310344827, 0.01694915254237288,
-    0.016666666666666666, 0.01639344262295082, 0.016129032258064516, 0.015873015873015872};
 
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
@@ -139,36 +86,6 @@ __device__ __forceinline__ void frag_zero(double (&f)[MT][NT][2]) {
     for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) f[mt][nt][0] = f[mt][nt][1] = 0.0;
-}
-
-struct Series {
-    int stages, terms;
-    double inv_stages;
-};
-
-// number of Taylor terms T with theta^T / T! <= 2^-56
-__device__ __forceinline__ int taylor_terms(double ths) {
-    // smallest T in [1, 60] with ths <= kTermThr[T] (the table is increasing): binary search, no divisions
-    int lo = 1, hi = 60;
-#pragma unroll
-    for (int it = 0; it < 6; ++it) {
-        const int mid = (lo + hi) >> 1;
-        if (ths <= kTermThr[mid]) hi = mid;
-        else lo = mid + 1;
-    }
-    return hi;
-}
-
-__device__ __forceinline__ Series choose_series(double theta) {
-    Series s{1, 2, 1.0};
-    if (theta < 1e8) {
-        if (theta > 4.0) {  // one stage up to ||dt G||_1 = 4 (e^4 round-off amplification)
-            s.stages = (int)ceil(theta * 0.25);
-            s.inv_stages = 1.0 / (double)s.stages;
-        }
-        s.terms = taylor_terms(theta * s.inv_stages) + 2;  // +2: the derivative rows lag the value row
-    }
-    return s;
 }
 
 enum { ROLE_FWD = 0, ROLE_EXP = 1, ROLE_ADJ = 2 };

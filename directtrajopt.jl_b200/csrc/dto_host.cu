@@ -210,10 +210,13 @@ extern "C" int dto_create(const dto_problem_desc* d, dto_handle** out) {
             // DTO_B200_KERNEL=generic|dmma pins an older variant (A/B measurements, parity tests of every variant)
             const char* pin = getenv("DTO_B200_KERNEL");
             const bool pin_generic = pin && strcmp(pin, "generic") == 0, pin_dmma = pin && strcmp(pin, "dmma") == 0;
+            const bool pin_persistent = pin && strcmp(pin, "persistent") == 0;
             if (bilinear_persistent_supported(s.x_dim, s.u_dim) && s.G_batch_stride == 0 && !pin_dmma && !pin_generic) {
                 I.variant = DTO_VAR_PERSISTENT;
                 I.wq = dev_upload<unsigned long long>(h, nullptr, 4);
                 if (!I.wq) return fail_create(h, DTO_ERR_ALLOC, "device allocation failed (work queue)");
+                // small states: eight intervals per warp, one tile per jet component (bilinear_octet.cu)
+                if (bilinear_octet_supported(s.x_dim, s.u_dim) && !pin_persistent) I.variant = DTO_VAR_OCTET;
             }
             if (pin_generic) I.variant = DTO_VAR_GENERIC;
             if (s.x_dim > 96) return fail_create(h, DTO_ERR_UNSUPPORTED, "bilinear integrator: state dimension > 96 not supported");
@@ -278,7 +281,7 @@ extern "C" int dto_create(const dto_problem_desc* d, dto_handle** out) {
         goff += (long long)s.x_dim * (N - 1);
         loff += (long long)s.x_dim * P.nI;
         doff += s.x_dim;
-        h->variants.push_back(s.kind == DTO_INT_BILINEAR ? (I.variant == DTO_VAR_PERSISTENT ? "persistent" : I.variant == DTO_VAR_DMMA ? "dmma" : "generic")
+        h->variants.push_back(s.kind == DTO_INT_BILINEAR ? (I.variant == DTO_VAR_OCTET ? "octet" : I.variant == DTO_VAR_PERSISTENT ? "persistent" : I.variant == DTO_VAR_DMMA ? "dmma" : "generic")
                                                          : (s.kind == DTO_INT_DERIVATIVE ? "analytic" : (I.variant == DTO_VAR_DMMA ? "gbs-dmma" : "gbs")));
     }
     P.Dsum = doff;
@@ -890,7 +893,8 @@ static void eval_range(dto_handle* h, const DProb& P, const double* dZ, double s
         if (timed) cudaEventRecord(h->ev_pool[h->ev_used].first, h->stream);
         if (P.in[i].kind == DTO_INT_BILINEAR) {
             bool done = false;
-            if (P.in[i].variant == DTO_VAR_PERSISTENT) done = launch_bilinear_persistent(P, i, dZ, dmu, dg, djac, f, h->stream, &h->launches);
+            if (P.in[i].variant == DTO_VAR_OCTET) done = launch_bilinear_octet(P, i, dZ, dmu, dg, djac, f, h->stream, &h->launches);
+            if (!done && P.in[i].variant >= DTO_VAR_PERSISTENT) done = launch_bilinear_persistent(P, i, dZ, dmu, dg, djac, f, h->stream, &h->launches);
             if (!done && P.in[i].variant >= DTO_VAR_DMMA && bilinear_dmma_supported(P.in[i].n, P.in[i].m))
                 done = launch_bilinear_dmma(P, i, dZ, dmu, dg, djac, f, h->stream, &h->launches);
             if (!done) launch_bilinear_generic(P, i, dZ, dmu, dg, djac, f, h->stream, &h->launches);
@@ -935,7 +939,7 @@ static bool range_capable(const dto_handle* h) {
     const DProb& P = h->P;
     if (P.batch != 1 || P.any_cross || P.gl.G > 0) return false;
     for (int i = 0; i < P.n_int; ++i)
-        if (P.in[i].kind != DTO_INT_DERIVATIVE && !(P.in[i].kind == DTO_INT_BILINEAR && P.in[i].variant == DTO_VAR_PERSISTENT)) return false;
+        if (P.in[i].kind != DTO_INT_DERIVATIVE && !(P.in[i].kind == DTO_INT_BILINEAR && P.in[i].variant >= DTO_VAR_PERSISTENT)) return false;
     return true;
 }
 
@@ -1056,7 +1060,7 @@ static bool matrix_free_capable(const dto_handle* h) {
     const char* env = getenv("DTO_B200_JVP");
     if (env && strcmp(env, "materialize") == 0) return false;
     for (int i = 0; i < P.n_int; ++i)
-        if (P.in[i].kind != DTO_INT_DERIVATIVE && !(P.in[i].kind == DTO_INT_BILINEAR && P.in[i].variant == DTO_VAR_PERSISTENT)) return false;
+        if (P.in[i].kind != DTO_INT_DERIVATIVE && !(P.in[i].kind == DTO_INT_BILINEAR && P.in[i].variant >= DTO_VAR_PERSISTENT)) return false;
     return true;
 }
 

@@ -131,7 +131,7 @@ __host__ __device__ inline long long hess_knot_base(const DProb& P, int kl) {
 __host__ __device__ inline bool hess_knot_has_cross(const DProb& P, int kl) { return kl > 0 || P.first_has_cross; }
 
 // variants of the bilinear kernel
-enum { DTO_VAR_GENERIC = 0, DTO_VAR_DMMA = 1, DTO_VAR_PERSISTENT = 2 };
+enum { DTO_VAR_GENERIC = 0, DTO_VAR_DMMA = 1, DTO_VAR_PERSISTENT = 2, DTO_VAR_OCTET = 3 };
 
 // cudaFuncSetAttribute is per device: a launcher opts a kernel into large dynamic shared memory once per device
 struct PerDeviceOnce {
@@ -157,6 +157,9 @@ bool bilinear_dmma_supported(int n, int m);
 bool launch_bilinear_persistent(const DProb& P, int ii, const double* Z, const double* mu, double* g, double* jac, EvalFlags f,
                                 cudaStream_t st, long long* launches);
 bool bilinear_persistent_supported(int n, int m);
+bool launch_bilinear_octet(const DProb& P, int ii, const double* Z, const double* mu, double* g, double* jac, EvalFlags f,
+                           cudaStream_t st, long long* launches);
+bool bilinear_octet_supported(int n, int m);
 bool launch_bilinear_product(const DProb& P, int ii, const double* Z, const double* w, double* y, bool transpose, cudaStream_t st,
                              long long* launches);
 void launch_analytic_product(const DProb& P, const double* Z, const double* w, double* y, bool transpose, cudaStream_t st,

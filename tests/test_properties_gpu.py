@@ -90,6 +90,31 @@ def test_repeated_evaluations_are_bit_identical(c2):
         assert np.array_equal(np.asarray(x), np.asarray(y))
 
 
+@pytest.mark.parametrize("n,m,N,scale", [(8, 2, 13, 0.35), (8, 1, 9, 0.5), (8, 3, 10, 0.4), (8, 4, 8, 0.4), (16, 2, 19, 0.3), (16, 1, 8, 0.3),
+                                         (8, 2, 21, 9.0), (16, 2, 11, 6.0)])
+def test_octet_variant_agrees_with_persistent(monkeypatch, n, m, N, scale):
+    """Small states run eight intervals per warp (one tile per jet component, bilinear_octet.cu).  Same series, different
+    association of the products: agreement with the one-interval-per-warp kernel far below the parity tolerance,
+    including partial octets (N - 1 not a multiple of 8), multi-stage series (scale 6, 9) and batches."""
+    prob = pt.scaled_problem(N=N, state_dim=n, n_controls=m, generator_scale=scale)
+    res = {}
+    for pin in ("", "persistent"):
+        if pin:
+            monkeypatch.setenv("DTO_B200_KERNEL", pin)
+        ev = dto.Evaluator(prob, batch=3)
+        assert ev.kernel_variant(0) == (pin or "octet")
+        Z = np.tile(prob.trajectory.datavec, 3) + 0.01 * np.random.default_rng(4).standard_normal(3 * ev.n_vars)
+        mu = np.random.default_rng(5).random(3 * ev.n_constraints)
+        bufs = [np.empty(3), np.empty(3 * ev.n_vars), np.empty(3 * ev.n_constraints), np.empty(3 * ev.nnz_jacobian), np.empty(3 * ev.nnz_hessian)]
+        ev.eval_all(Z, 1.0, mu, *bufs)
+        assert all(np.isfinite(b).all() for b in bufs)
+        res[pin] = bufs
+        ev.close()
+    for x, y in zip(res[""], res["persistent"]):
+        x, y = np.asarray(x), np.asarray(y)
+        assert np.abs(x - y).max() <= 1e-12 * max(np.abs(y).max(), 1.0)
+
+
 def test_k1_variants_agree(monkeypatch):
     prob = pt.quantum_gate_problem(N=40, levels=16, n_drives=4)
     rng = np.random.default_rng(3)
