@@ -6,6 +6,7 @@
 //   violation_kernel     max-norm constraint violation
 //   jac_product_kernel   y = J w / J' w from the COO values                              (evaluator.jl:406-456)
 #include "dto_internal.h"
+#include "analytic_block.cuh"
 #include "knotfun.cuh"
 
 namespace {
@@ -42,40 +43,8 @@ __global__ void analytic_kernel(DProb P, const double* __restrict__ Z, double* _
     const long long item = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / GS;
     if (item >= total) return;
     const int nIc = min(P.kc1, P.nI) - P.kc0;  // intervals of the active range
-    const int b = (int)(item / nIc), kl = P.kc0 + (int)(item % nIc), z = P.z, lane = threadIdx.x % GS;
-    const double* zk = Z + (long long)b * P.n_vars_local + (long long)kl * z;
-    const double* zk1 = zk + z;
-    if (P.halo != nullptr && kl + 1 == P.nK - 1) zk1 = P.halo;
-    const double dt = zk[P.dt_off];
-    for (int ii = 0; ii < P.n_int; ++ii) {
-        const DInt& I = P.in[ii];
-        if (I.kind != DTO_INT_DERIVATIVE) continue;
-        const int d = I.n;
-        if (g != nullptr) {
-            double* gp = g + (long long)b * P.n_cons_local + I.row_off + (long long)kl * d;
-            for (int a = lane; a < d; a += GS) gp[a] = zk1[I.x_off + a] - zk[I.x_off + a] - dt * zk[I.u_off + a];
-        }
-        if (jac != nullptr) {
-            double* jp = jac + (long long)b * P.nnz_jac_local;
-            const long long own_off = jac_own_off(P, kl, I.doff, d);
-            const long long prev_off = jac_prev_off(P, kl + 1, I.doff);
-            for (int e = lane; e < 2 * z * d; e += GS) {
-                const int l = e / d, a = e % d;
-                double v = 0.0;
-                long long pos;
-                if (l < z) {
-                    if (l == I.x_off + a) v += -1.0;
-                    if (l == I.u_off + a) v += -dt;
-                    if (l == P.dt_off) v += -zk[I.u_off + a];
-                    pos = jac_col(P, kl, l) + own_off + a;
-                } else {
-                    if (l - z == I.x_off + a) v = 1.0;
-                    pos = jac_col(P, (kl + 1), (l - z)) + prev_off + a;
-                }
-                jp[pos] = v;
-            }
-        }
-    }
+    const int b = (int)(item / nIc), kl = P.kc0 + (int)(item % nIc);
+    analytic_interval(P, Z, g, jac, b, kl, threadIdx.x % GS, GS);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -553,6 +522,7 @@ void launch_analytic(const DProb& P, const double* Z, double* g, double* jac, Ev
     bool any_deriv = false;
     for (int i = 0; i < P.n_int; ++i) any_deriv |= P.in[i].kind == DTO_INT_DERIVATIVE;
     const int nIc = std::min(P.kc1, P.nI) - P.kc0;
+    if (P.analytic_fused) return;  // written by the bilinear kernel together with its own columns (bilinear_octet.cu)
     if (any_deriv && nIc > 0) {
         const long long total = (long long)nIc * P.batch;
         int dmax = 0;

@@ -27,6 +27,7 @@
 #include <stdlib.h>
 
 #include "dto_internal.h"
+#include "analytic_block.cuh"
 #include "series_tables.cuh"
 
 namespace {
@@ -381,11 +382,17 @@ __global__ void __launch_bounds__(NT == 1 ? 256 : 128)
         }
 
         // =========================== EXP: -E block, one interval at a time (rows = columns of E) ===========================
+        const bool fused = P.analytic_fused == ii + 1;  // this kernel also writes the derivative integrators' rows
+        if (fused && !want_jac) {
+            for (int r = 0; r < 8 && oct * 8 + r < nItems; ++r)
+                analytic_interval(P, Z, g, nullptr, (int)((oct * 8 + r) / nIc), P.kc0 + (int)((oct * 8 + r) % nIc), lane, 32);
+        }
         if (want_jac) {
             for (int r = 0; r < 8; ++r) {
                 const long long idr = oct * 8 + r;
                 if (idr >= nItems) break;
                 const int br = (int)(idr / nIc), kr = P.kc0 + (int)(idr % nIc);
+                if (fused) analytic_interval(P, Z, g, jac, br, kr, lane, 32);
                 // the interval's own scalars, broadcast from the lanes of row r
                 const double cdt_r = __shfl_sync(0xffffffffu, cdt, 4 * r);
                 const int terms_r = __shfl_sync(0xffffffffu, ser.terms, 4 * r), stages_r = __shfl_sync(0xffffffffu, ser.stages, 4 * r);

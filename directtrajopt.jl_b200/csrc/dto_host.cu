@@ -286,6 +286,15 @@ extern "C" int dto_create(const dto_problem_desc* d, dto_handle** out) {
     }
     P.Dsum = doff;
     const long long n_dyn_global = goff, n_dyn_local = loff;
+    {
+        // small-state bilinear kernel + derivative integrators: one kernel writes whole Jacobian columns
+        bool any_deriv = false;
+        for (int i = 0; i < P.n_int; ++i) any_deriv |= P.in[i].kind == DTO_INT_DERIVATIVE;
+        const char* env = getenv("DTO_B200_FUSE_ANALYTIC");
+        if (any_deriv && !(env && strcmp(env, "0") == 0))
+            for (int i = 0; i < P.n_int && !P.analytic_fused; ++i)
+                if (P.in[i].kind == DTO_INT_BILINEAR && P.in[i].variant == DTO_VAR_OCTET) P.analytic_fused = i + 1;
+    }
 
     // ---- objectives --------------------------------------------------------------------------
     h->obj_var_offs.resize(d->n_objectives);
@@ -887,13 +896,17 @@ static void eval_prologue(dto_handle* h, const DProb& P, const double* dZ, doubl
 static void eval_range(dto_handle* h, const DProb& P, const double* dZ, double sigma, const double* dmu, double* dg, double* djac,
                        double* dhess, EvalFlags f) {
     if (!(f.want_g || f.want_jac || f.want_hess)) return;
+    bool fused_missed = false;
     for (int i = 0; i < P.n_int; ++i) {
         if (P.in[i].kind == DTO_INT_DERIVATIVE) continue;
         const bool timed = h->timing && h->ev_used < h->ev_pool.size();
         if (timed) cudaEventRecord(h->ev_pool[h->ev_used].first, h->stream);
         if (P.in[i].kind == DTO_INT_BILINEAR) {
             bool done = false;
-            if (P.in[i].variant == DTO_VAR_OCTET) done = launch_bilinear_octet(P, i, dZ, dmu, dg, djac, f, h->stream, &h->launches);
+            if (P.in[i].variant == DTO_VAR_OCTET) {
+                done = launch_bilinear_octet(P, i, dZ, dmu, dg, djac, f, h->stream, &h->launches);
+                if (!done && P.analytic_fused == i + 1) fused_missed = true;
+            }
             if (!done && P.in[i].variant >= DTO_VAR_PERSISTENT) done = launch_bilinear_persistent(P, i, dZ, dmu, dg, djac, f, h->stream, &h->launches);
             if (!done && P.in[i].variant >= DTO_VAR_DMMA && bilinear_dmma_supported(P.in[i].n, P.in[i].m))
                 done = launch_bilinear_dmma(P, i, dZ, dmu, dg, djac, f, h->stream, &h->launches);
@@ -905,7 +918,15 @@ static void eval_range(dto_handle* h, const DProb& P, const double* dZ, double s
         }
         if (timed) cudaEventRecord(h->ev_pool[h->ev_used++].second, h->stream);
     }
-    if (f.want_g || f.want_jac) launch_analytic(P, dZ, dg, djac, f, h->stream, &h->launches);
+    if (f.want_g || f.want_jac) {
+        if (fused_missed) {
+            DProb Pn = P;
+            Pn.analytic_fused = 0;
+            launch_analytic(Pn, dZ, dg, djac, f, h->stream, &h->launches);
+        } else {
+            launch_analytic(P, dZ, dg, djac, f, h->stream, &h->launches);
+        }
+    }
     if (f.want_hess) launch_hessian_assemble(P, dZ, sigma, dmu, dhess, h->stream, &h->launches);
     if (f.want_hess) launch_global_hessian(P, dZ, sigma, dmu, dhess, nullptr, h->stream, &h->launches);
 }
