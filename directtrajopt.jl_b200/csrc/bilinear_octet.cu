@@ -110,6 +110,28 @@ __device__ __forceinline__ double tdot(const double (&muf)[NT][2], const Tile<NT
     return quad_sum(s);
 }
 
+// An n x n matrix in fragment form: r[mt] holds rows 8*mt .. 8*mt+7 (lane: row 8*mt + lane/4, columns 8*t + 2*(lane%4) + {0,1}).
+// The C fragment of a tile is at the same time the B fragment of that tile's matrix: out = V * W' needs no data movement
+// (out[i][s] = sum_k V[i][k] W[s][k]; for k-step (t, e) the B operand of lane (s', q) is W[8*nt + s'][8*t + 2q + e] = W.r[nt].v[t][e]).
+template <int NT>
+struct Mat {
+    Tile<NT> r[NT];
+};
+template <int NT>
+__device__ __forceinline__ void mul_t(Mat<NT>& out, const Mat<NT>& V, const Mat<NT>& W) {
+#pragma unroll
+    for (int mt = 0; mt < NT; ++mt) {
+        tzero(out.r[mt]);
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) dmma(out.r[mt].v[nt][0], out.r[mt].v[nt][1], V.r[mt].v[t][0], W.r[nt].v[t][0]);
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) dmma(out.r[mt].v[nt][0], out.r[mt].v[nt][1], V.r[mt].v[t][1], W.r[nt].v[t][1]);
+        }
+    }
+}
+
 template <int NT, int M>
 __global__ void __launch_bounds__(NT == 1 ? 256 : 128)
     bilinear_octet_kernel(DProb P, int ii, const double* __restrict__ Z, const double* __restrict__ mu, double* __restrict__ g,
@@ -416,8 +438,67 @@ __global__ void __launch_bounds__(NT == 1 ? 256 : 128)
                     }
                 double* jr = jac + (long long)br * P.nnz_jac_local;
                 const long long own_r = jac_own_off(P, kr, I.doff, n);
+                if (stages_r == 1) {
+                    // Paterson-Stockmeyer in A^3 on fragments.  Wanted: tile rows = columns of E, i.e. R = exp(B), B = A' (A = dt G(u_r)).
+                    // With mul_t(V, W) = V W':  B^2 = mul_t(B, A),  A^2 = mul_t(A, B),  A^3 = mul_t(A^2, B),  R B^3 = mul_t(R, A^3).
+                    // exp(B) ~ sum_{j < nb} (c_3j I + c_3j+1 B + c_3j+2 B^2) (B^3)^j: 3 + (nb - 1) products instead of `terms` tile sweeps.
+                    Mat<NT> A, B;
+#pragma unroll
+                    for (int mt = 0; mt < NT; ++mt)
+#pragma unroll
+                        for (int t = 0; t < NT; ++t) {
+                            double2 v = bf[(((M + 1) * NT + t) * NT + mt) * 32 + lane];  // G_0'
+#pragma unroll
+                            for (int i = 0; i < M; ++i) {
+                                const double2 gi = bf[(((M + 2 + i) * NT + t) * NT + mt) * 32 + lane];
+                                v.x = fma(ur[i], gi.x, v.x);
+                                v.y = fma(ur[i], gi.y, v.y);
+                            }
+                            B.r[mt].v[t][0] = cdt_r * v.x;
+                            B.r[mt].v[t][1] = cdt_r * v.y;
+                            A.r[mt].v[t][0] = cdt_r * bu[t][mt].x;
+                            A.r[mt].v[t][1] = cdt_r * bu[t][mt].y;
+                        }
+                    Mat<NT> B2, A3, R;
+                    mul_t<NT>(B2, B, A);
+                    {
+                        Mat<NT> A2;
+                        mul_t<NT>(A2, A, B);
+                        mul_t<NT>(A3, A2, B);
+                    }
+                    const int nb = (terms_r - 2 + 3) / 3;  // degree 3 nb - 1 >= terms - 2 (value series only)
 #pragma unroll 1
-                for (int mt = 0; mt < NT; ++mt) {  // 8 columns of E at a time
+                    for (int j3 = nb - 1; j3 >= 0; --j3) {
+                        const double c0 = kInvFact[3 * j3], c1 = kInvFact[3 * j3 + 1], c2 = kInvFact[3 * j3 + 2];
+                        Mat<NT> Rn;
+                        if (j3 == nb - 1) {
+#pragma unroll
+                            for (int mt = 0; mt < NT; ++mt) tzero(Rn.r[mt]);
+                        } else {
+                            mul_t<NT>(Rn, R, A3);
+                        }
+#pragma unroll
+                        for (int mt = 0; mt < NT; ++mt)
+#pragma unroll
+                            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                                for (int e = 0; e < 2; ++e) {
+                                    const bool diag = (8 * nt + 2 * q + e) == (8 * mt + row8);
+                                    R.r[mt].v[nt][e] = Rn.r[mt].v[nt][e] + fma(c2, B2.r[mt].v[nt][e], fma(c1, B.r[mt].v[nt][e], diag ? c0 : 0.0));
+                                }
+                    }
+#pragma unroll
+                    for (int mt = 0; mt < NT; ++mt) {
+                        double* cp = jr + jac_col(P, kr, I.x_off + 8 * mt + row8) + own_r;
+#pragma unroll
+                        for (int nt = 0; nt < NT; ++nt) {
+                            cp[8 * nt + 2 * q] = -R.r[mt].v[nt][0];
+                            cp[8 * nt + 2 * q + 1] = -R.r[mt].v[nt][1];
+                        }
+                    }
+                } else {
+#pragma unroll 1
+                for (int mt = 0; mt < NT; ++mt) {  // several stages: 8 columns of E at a time through the series
                     Tile<NT> F, term;
 #pragma unroll
                     for (int nt = 0; nt < NT; ++nt) {
@@ -452,6 +533,7 @@ __global__ void __launch_bounds__(NT == 1 ? 256 : 128)
                         cp[8 * nt + 2 * q] = -F.v[nt][0];
                         cp[8 * nt + 2 * q + 1] = -F.v[nt][1];
                     }
+                }
                 }
                 // zero and identity columns of this interval (everything except the x, u, dt columns of the own knot)
                 const long long prev_r = jac_prev_off(P, kr + 1, I.doff);
