@@ -100,6 +100,30 @@ def global_problem(N=10, seed=0, global_dim=None, with_goal=True):
     return DirectTrajOptProblem(traj, J, integrators, constraints=cons)
 
 
+def global_goal_problem(N=11, seed=0):
+    """A well-posed problem with global variables for the solver-in-the-loop check: the state has to reach a goal that is
+    itself a decision variable on the unit sphere (global ``x_goal``: terminal objective norm(x_N - x_goal)^2 as in
+    global_objectives.jl:364-369, pulled towards a target by a GlobalObjective, norm(x_goal)^2 = 1 as a
+    NonlinearGlobalConstraint), and the drives stay in a ball whose radius is set by a second global ``gam``
+    (NonlinearGlobalKnotPointConstraint norm([u; gam])^2 <= c)."""
+    from .components import NormSqMinus
+
+    G, traj0 = bilinear_dynamics_and_trajectory(N=N, seed=seed)
+    glob = {"x_goal": np.array([0.1, 0.9, 0.1, 0.05]), "gam": np.array([0.1])}  # no exact zeros: the stored Jacobian pattern is value-dependent
+    traj = NamedTrajectory({n: traj0.data[traj0.components[n], :] for n in traj0.names}, controls=("ddu", "dt"), timestep="dt",
+                           bounds=traj0.bounds, initial=traj0.initial, final=traj0.final, goal=traj0.goal, global_components=glob)
+    integrators = [BilinearIntegrator(G, "x", "u", traj), DerivativeIntegrator("u", "du", traj), DerivativeIntegrator("du", "ddu", traj)]
+    J = QuadraticRegularizer("u", traj, 1.0) + QuadraticRegularizer("du", traj, 1.0) + QuadraticRegularizer("ddu", traj, 1.0)
+    J = J + TerminalObjective(SplitSqDist(), "x", traj, global_names="x_goal", Q=100.0)
+    J = J + GlobalObjective(SqDist(np.array([0.0, 0.8, 0.6, 0.0])), "x_goal", traj, Q=10.0)
+    J = J + GlobalObjective(SqDist(np.array([0.3])), "gam", traj, Q=1.0)
+    cons = [
+        NonlinearGlobalConstraint(NormSqMinus(1.0), "x_goal", traj, equality=True),
+        NonlinearGlobalKnotPointConstraint(NormSqMinus(0.06), ["u"], ["gam"], traj, times=range(2, traj.N), equality=False),
+    ]
+    return DirectTrajOptProblem(traj, J, integrators, constraints=cons)
+
+
 def linear_regularizer_problem(N=8, seed=1):
     """The standard problem with LinearRegularizer terms (regularizers.jl:207-313): vector R, a subset of
     times, a scaled term inside the composite."""

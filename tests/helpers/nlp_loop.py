@@ -18,7 +18,7 @@ class OracleCallbacks:
         import dto_oracle as orc
 
         self.orc, self.spec = orc, prob.to_spec()
-        Z0 = prob.trajectory.datavec.copy()
+        Z0 = prob.trajectory.vec()
         self.n_vars = Z0.size
         self.jstruct = orc.jacobian_structure(self.spec, Z0)
         self.hstruct = orc.hessian_structure(self.spec, Z0)
@@ -104,7 +104,9 @@ def variable_bounds(traj):
         lo[traj.components[name], 0] = hi[traj.components[name], 0] = np.asarray(v, float)
     for name, v in traj.final.items():
         lo[traj.components[name], -1] = hi[traj.components[name], -1] = np.asarray(v, float)
-    return lo.reshape(-1, order="F"), hi.reshape(-1, order="F")
+    g = traj.global_dim  # global variables are unbounded here
+    return (np.concatenate([lo.reshape(-1, order="F"), np.full(g, -np.inf)]),
+            np.concatenate([hi.reshape(-1, order="F"), np.full(g, np.inf)]))
 
 
 def solve(prob, cb, max_iter=100, gtol=1e-8, xtol=1e-10):
@@ -121,7 +123,7 @@ def solve(prob, cb, max_iter=100, gtol=1e-8, xtol=1e-10):
                               jac=lambda Z: coo_matrix((cb.jacobian(Z), (jr, jc)), shape=(m, n)).tocsr(),
                               hess=lambda Z, v: sym(cb.hessian(Z, 0.0, v)))
     lo, hi = variable_bounds(prob.trajectory)
-    Z0 = np.clip(prob.trajectory.datavec.copy(), lo, hi)
+    Z0 = np.clip(prob.trajectory.vec(), lo, hi)
     res = minimize(cb.objective, Z0, jac=cb.gradient, hess=lambda Z: sym(cb.hessian(Z, 1.0, np.zeros(m))), method="trust-constr",
                    constraints=[con], bounds=Bounds(lo, hi), options={"maxiter": max_iter, "gtol": gtol, "xtol": xtol, "verbose": 0})
     return res.x, {"objective": float(res.fun), "iterations": int(res.nit), "violation": float(res.constr_violation),

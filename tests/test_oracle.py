@@ -35,6 +35,7 @@ PROBLEMS = {
     "linreg": lambda: pt.linear_regularizer_problem(N=5),
     "global": lambda: pt.global_problem(N=5),
     "global_ref_fixture": lambda: pt.global_problem(N=4, with_goal=False),
+    "global_goal": lambda: pt.global_goal_problem(N=5),
 }
 
 

@@ -82,6 +82,7 @@ PROBLEMS = {
     "global": lambda: pt.global_problem(N=9),
     "global_ref_fixture": lambda: pt.global_problem(N=6, with_goal=False),
     "global_dim3": lambda: pt.global_problem(N=12, global_dim=3, seed=5),
+    "global_goal": lambda: pt.global_goal_problem(N=11),
 }
 
 

@@ -13,6 +13,8 @@ pytestmark = pytest.mark.gpu
 CASES = {
     "readme_c1": (lambda: pt.readme_problem(N=50), 100),
     "bilinear_benchmark": (lambda: pt.bilinear_benchmark(N=21), 300),
+    # global variables (goal on the unit sphere + a drive radius as decision variables): 60 iterations of the same path
+    "global_goal": (lambda: pt.global_goal_problem(N=11), 60),
 }
 
 
