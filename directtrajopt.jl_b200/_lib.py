@@ -98,6 +98,7 @@ SYMBOLS = [
     ("dto_halo_attach", C.c_int, [_H, _H]),
     ("dto_local_Z", C.c_void_p, [_H]),
     ("dto_launch_count", C.c_int64, [_H]),
+    ("dto_last_download_bytes", C.c_int64, [_H]),
     ("dto_kernel_variant", C.c_char_p, [_H, C.c_int]),
     ("dto_kernel_timing", C.c_int, [_H, C.c_int]),
     ("dto_kernel_time_ms", C.c_int, [_H, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),

@@ -7,8 +7,12 @@
 #include <string.h>
 
 #include <algorithm>
+#include <condition_variable>
+#include <functional>
 #include <limits>
+#include <mutex>
 #include <new>
+#include <thread>
 
 #include "dto_internal.h"
 #include "knotfun.cuh"
@@ -21,6 +25,68 @@ struct ConEntry {
     long long lrow;       // local 0-based row
     long long e;          // index into the constraint's dense [j][a][i] table
     int ci;
+};
+
+// Host threads that write structural zeros into the caller's Hessian buffer while the GPU computes and the copy
+// engine delivers only the value-dependent runs (see HRun).  No arithmetic happens on the host.
+struct ZeroFill {
+    std::vector<std::thread> workers;
+    std::mutex m;
+    std::condition_variable cv, cv_done;
+    long long gen = 0;
+    int pending = 0;
+    bool stop = false;
+    std::function<void(int, int)> job;  // job(part, parts): writes this part's share of the constants
+    int parts = 1;
+
+    void run_part(int part) { job(part, parts); }
+    void start(int nthreads) {
+        parts = std::max(1, nthreads);
+        for (int t = 1; t < parts; ++t)
+            workers.emplace_back([this, t] {
+                long long seen = 0;
+                while (true) {
+                    {
+                        std::unique_lock<std::mutex> lk(m);
+                        cv.wait(lk, [&] { return stop || gen != seen; });
+                        if (stop) return;
+                        seen = gen;
+                    }
+                    run_part(t);
+                    {
+                        std::lock_guard<std::mutex> lk(m);
+                        if (--pending == 0) cv_done.notify_all();
+                    }
+                }
+            });
+    }
+    // the calling thread takes part 0 in finish(): the workers run while the caller enqueues GPU work
+    void launch(std::function<void(int, int)> j) {
+        std::lock_guard<std::mutex> lk(m);
+        job = std::move(j);
+        pending = parts - 1;
+        ++gen;
+        cv.notify_all();
+    }
+    void finish() {
+        run_part(0);
+        std::unique_lock<std::mutex> lk(m);
+        cv_done.wait(lk, [&] { return pending == 0; });
+    }
+    ~ZeroFill() {
+        {
+            std::lock_guard<std::mutex> lk(m);
+            stop = true;
+            cv.notify_all();
+        }
+        for (auto& w : workers) w.join();
+    }
+};
+
+// Consecutive owned knots whose Hessian columns below l0 are structurally zero (no term of the problem touches them):
+// only the tail of each knot's region crosses PCIe, as one 2-D copy per run.
+struct HRun {
+    int k0, cnt, l0;
 };
 
 struct dto_handle {
@@ -55,10 +121,17 @@ struct dto_handle {
     long long *d_rows0 = nullptr, *d_cols0 = nullptr;
     void* ipc_peer = nullptr;
     long long launches = 0;
+    long long last_d2h_bytes = 0;
     // host-pointer path: outputs leave over PCIe while later knot ranges are still being computed
     cudaStream_t copy_stream = nullptr;
     std::vector<cudaEvent_t> chunk_events;
     std::vector<double> pipeline_fracs;  // cumulative interval fractions of the chunk boundaries (empty = no pipelining)
+    std::vector<HRun> hess_runs;         // empty: the Hessian is delivered whole
+    std::vector<std::pair<long long, long long>> hess_zero_segs;  // structural-zero prefixes of the knot regions
+    // Jacobian: the previous-interval block of the first integrator is a constant (identity / zero) at the head of every
+    // column of knots 1..nI-1; jac_skip = its length (0: the Jacobian is delivered whole)
+    int jac_skip = 0;
+    ZeroFill* zero_fill = nullptr;
     std::vector<std::string> variants;
     // optional device timing of the interval kernels (bench.py's roofline numerator)
     int timing = 0;
@@ -109,6 +182,7 @@ extern "C" void dto_destroy(dto_handle* h) {
     for (void* p : h->allocs) cudaFree(p);
     for (cudaEvent_t e : h->chunk_events) cudaEventDestroy(e);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    delete h->zero_fill;
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -701,6 +775,97 @@ extern "C" int dto_create(const dto_problem_desc* d, dto_handle** out) {
             std::sort(h->pipeline_fracs.begin(), h->pipeline_fracs.end());
         }
     }
+    // ---- structural zeros of the Hessian (host-pointer path) -------------------------------------------------------
+    // For bilinear/derivative problems every entry of a knot's region in a column below l0(k) is identically zero
+    // (x enters the dynamics linearly: the cross block and the (x, x) block carry no term).
+    // l0(k) = smallest column any term of the problem can write at knot k (column of a pair = its larger component).
+    {
+        const char* env = getenv("DTO_B200_SPARSE_D2H");
+        bool ok = d->eval_hessian && d->batch == 1 && !P.any_cross && G == 0 && !(env && strcmp(env, "0") == 0);
+        for (int i = 0; i < P.n_int; ++i) ok = ok && (P.in[i].kind == DTO_INT_BILINEAR || P.in[i].kind == DTO_INT_DERIVATIVE);
+        if (ok) {
+            int l_int = z;  // knots that own an interval
+            for (int i = 0; i < P.n_int; ++i) {
+                const dto_integrator_desc& s = d->integrators[i];
+                if (s.kind == DTO_INT_BILINEAR) {
+                    for (int p = 0; p <= s.u_dim; ++p) {
+                        const int c = p < s.u_dim ? s.u_off + p : d->dt_off;
+                        l_int = std::min(l_int, std::max(s.x_off, c));  // (x_a, param): smallest with a = 0
+                        l_int = std::min(l_int, c);                     // (param, param)
+                    }
+                } else {
+                    l_int = std::min(l_int, std::max(s.u_off, d->dt_off));  // (xdot_a, dt)
+                }
+            }
+            std::vector<int> l0((size_t)P.nOwn, z);
+            for (int kl = 0; kl < P.nOwn; ++kl)
+                if (kl < P.nI) l0[kl] = l_int;
+            auto touch = [&](const int* times, int nt, int lmin) {
+                for (int t = 0; t < nt; ++t) {
+                    const int k = times[t];
+                    if (k >= h->k0 && k <= h->k1) l0[k - h->k0] = std::min(l0[k - h->k0], lmin);
+                }
+            };
+            for (int i = 0; i < d->n_objectives; ++i) {
+                const dto_objective_desc& s = d->objectives[i];
+                if (s.kind == DTO_OBJ_MINTIME || s.kind == DTO_OBJ_NULL) continue;
+                int lmin = z;
+                for (int v = 0; v < s.n_vars; ++v) lmin = std::min(lmin, s.var_offs[v]);
+                if (s.kind == DTO_OBJ_QUADREG || s.kind == DTO_OBJ_LINREG) lmin = std::min(lmin, d->dt_off);
+                touch(s.times, s.n_times, lmin);
+            }
+            for (int i = 0; i < d->n_constraints; ++i) {
+                const dto_constraint_desc& s = d->constraints[i];
+                int lmin = z;
+                for (int v = 0; v < s.n_vars; ++v) lmin = std::min(lmin, s.var_offs[v]);
+                touch(s.times, s.n_times, lmin);
+            }
+            long long zeros = 0;
+            for (int kl = 0; kl < P.nOwn; ++kl) {
+                const long long nc = hess_knot_has_cross(P, kl) ? z : 0;
+                const long long skip = (long long)l0[kl] * nc + (long long)l0[kl] * (l0[kl] + 1) / 2;
+                if (skip > 0) h->hess_zero_segs.emplace_back(hess_knot_base(P, kl), skip);
+                zeros += skip;
+                if (!h->hess_runs.empty() && h->hess_runs.back().l0 == l0[kl] &&
+                    hess_knot_has_cross(P, h->hess_runs.back().k0) == hess_knot_has_cross(P, kl))
+                    h->hess_runs.back().cnt++;
+                else
+                    h->hess_runs.push_back(HRun{kl, 1, l0[kl]});
+            }
+            // worth it only when most of the array is structural and the runs are long (few copies)
+            if (zeros * 2 < P.nnz_hess_local || h->hess_runs.size() > 64) {
+                h->hess_runs.clear();
+                h->hess_zero_segs.clear();
+            } else {
+                int nth = 4;
+                if (const char* e2 = getenv("DTO_B200_HOST_THREADS")) nth = std::max(1, std::min(32, atoi(e2)));
+                h->zero_fill = new (std::nothrow) ZeroFill();
+                if (h->zero_fill) h->zero_fill->start(nth);
+                else {
+                    h->hess_runs.clear();
+                    h->hess_zero_segs.clear();
+                }
+            }
+        }
+    }
+    {
+        // Jacobian: d r_{k-1} / d z_k of a bilinear or derivative integrator is the constant [0 .. I .. 0] block
+        // (bilinear_integrator.jl:81, derivative_integrator.jl:45: x_{k+1} enters linearly).  With one column layout for
+        // all inner knots (no knot-constraint rows) the rest of every column is one strided copy.
+        const char* env = getenv("DTO_B200_SPARSE_D2H");
+        const int k0i = P.in[0].kind;
+        const long long L = 2LL * P.Dsum, d1 = P.in[0].n;
+        if (d->batch == 1 && P.jac_closed && G == 0 && P.nI >= 3 && (k0i == DTO_INT_BILINEAR || k0i == DTO_INT_DERIVATIVE) &&
+            env && strcmp(env, "2") == 0 && 8 * (L - d1) >= 256) {  // opt-in: 256-byte rows make a slow strided copy
+            if (!h->zero_fill) {
+                int nth = 4;
+                if (const char* e2 = getenv("DTO_B200_HOST_THREADS")) nth = std::max(1, std::min(32, atoi(e2)));
+                h->zero_fill = new (std::nothrow) ZeroFill();
+                if (h->zero_fill) h->zero_fill->start(nth);
+            }
+            if (h->zero_fill) h->jac_skip = (int)d1;
+        }
+    }
     if (cudaStreamSynchronize(h->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess)
         return fail_create(h, DTO_ERR_CUDA, "CUDA failure during construction");
     *out = h;
@@ -715,6 +880,7 @@ extern "C" int dto_sizes(const dto_handle* h, dto_size_info* out) {
 
 extern "C" void* dto_stream(const dto_handle* h) { return h ? (void*)h->stream : nullptr; }
 extern "C" int64_t dto_launch_count(const dto_handle* h) { return h ? h->launches : 0; }
+extern "C" int64_t dto_last_download_bytes(const dto_handle* h) { return h ? h->last_d2h_bytes : 0; }
 extern "C" const char* dto_kernel_variant(const dto_handle* h, int i) {
     if (!h || i < 0 || i >= (int)h->variants.size()) return "";
     return h->variants[i].c_str();
@@ -993,6 +1159,7 @@ extern "C" int dto_eval_all(dto_handle* h, const double* Z, double sigma, const 
     CUDA_TRY(h, cudaSetDevice(h->device));
     CUDA_TRY(h, cudaMemcpyAsync(h->dZ, Z, sizeof(double) * B * P.n_vars_local, cudaMemcpyHostToDevice, h->stream));
     if (hess) CUDA_TRY(h, cudaMemcpyAsync(h->dmu, mu, sizeof(double) * B * P.n_cons_local, cudaMemcpyHostToDevice, h->stream));
+    long long d2h = 8LL * B * ((J ? 1 : 0) + (grad ? P.n_grad_local : 0) + (g ? P.n_cons_local : 0));
     double* dJ = J ? h->dJ : nullptr;
     double* dgrad = grad ? h->dgrad : nullptr;
     double* dg = g ? h->dg : nullptr;
@@ -1009,6 +1176,8 @@ extern "C" int dto_eval_all(dto_handle* h, const double* Z, double sigma, const 
         if (rc != DTO_OK) return rc;
         if (jac) CUDA_TRY(h, cudaMemcpyAsync(jac, h->djac, sizeof(double) * B * P.nnz_jac_local, cudaMemcpyDeviceToHost, h->stream));
         if (hess) CUDA_TRY(h, cudaMemcpyAsync(hess, h->dhess, sizeof(double) * B * P.nnz_hess_local, cudaMemcpyDeviceToHost, h->stream));
+        if (hess) d2h += 8LL * B * P.nnz_hess_local;
+        if (jac) d2h += 8LL * B * P.nnz_jac_local;
     } else {
         if (!h->copy_stream) CUDA_TRY(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
         std::vector<int> bounds{0};
@@ -1022,6 +1191,33 @@ extern "C" int dto_eval_all(dto_handle* h, const double* Z, double sigma, const 
             CUDA_TRY(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
             h->chunk_events.push_back(e);
         }
+        const bool sparse_hess = hess && !h->hess_runs.empty();
+        const bool sparse_jac = jac && h->jac_skip > 0;
+        if (sparse_hess || sparse_jac) {
+            // host threads write the structural constants into the caller's buffers while the GPU computes
+            const dto_handle* hh = h;
+            double* hz = sparse_hess ? hess : nullptr;
+            double* jz = sparse_jac ? jac : nullptr;
+            h->zero_fill->launch([hh, hz, jz](int part, int parts) {
+                const DProb& Q = hh->P;
+                if (hz) {
+                    const size_t n = hh->hess_zero_segs.size(), lo = n * part / parts, hi = n * (part + 1) / parts;
+                    for (size_t i = lo; i < hi; ++i)
+                        memset(hz + hh->hess_zero_segs[i].first, 0, sizeof(double) * (size_t)hh->hess_zero_segs[i].second);
+                }
+                if (jz) {
+                    // head of every column of knots 1..nI-1: [0 .. 1 (row l - x_off) .. 0]
+                    const long long nk = Q.nI - 1, k_lo = 1 + nk * part / parts, k_hi = 1 + nk * (part + 1) / parts;
+                    const int d1 = hh->jac_skip, xo = Q.in[0].x_off;
+                    for (long long kl = k_lo; kl < k_hi; ++kl)
+                        for (int l = 0; l < Q.z; ++l) {
+                            double* c = jz + hh->jac_colptr[(size_t)kl * Q.z + l];
+                            memset(c, 0, sizeof(double) * (size_t)d1);
+                            if (l >= xo && l < xo + d1) c[l - xo] = 1.0;
+                        }
+                }
+            });
+        }
         eval_prologue(h, P, h->dZ, dJ, dgrad, dg, djac, f);  // knot-constraint entries land before any column leaves
         DProb Pr = P;
         for (size_t c = 0; c + 1 < bounds.size(); ++c) {
@@ -1030,17 +1226,59 @@ extern "C" int dto_eval_all(dto_handle* h, const double* Z, double sigma, const 
             eval_range(h, Pr, h->dZ, sigma, h->dmu, dg, djac, dhess, f);
             CUDA_TRY(h, cudaEventRecord(h->chunk_events[c], h->stream));
             CUDA_TRY(h, cudaStreamWaitEvent(h->copy_stream, h->chunk_events[c], 0));
-            if (jac) {
+            if (jac && !sparse_jac) {
                 // columns of knots [kc0, kc1): their own-interval rows were written by this range, the
                 // previous-interval rows of knot kc0 by the range before
                 const long long p0 = h->jac_colptr[(size_t)Pr.kc0 * P.z], p1 = h->jac_colptr[(size_t)Pr.kc1 * P.z];
                 CUDA_TRY(h, cudaMemcpyAsync(jac + p0, h->djac + p0, sizeof(double) * (p1 - p0), cudaMemcpyDeviceToHost, h->copy_stream));
+                d2h += 8LL * (p1 - p0);
             }
-            if (hess) {
+            if (sparse_jac) {
+                // knot 0 and the last knot whole; inner knots: every column minus its constant head, one strided copy
+                auto whole = [&](int ka, int kb2) -> int {
+                    if (ka >= kb2) return DTO_OK;
+                    const long long p0 = h->jac_colptr[(size_t)ka * P.z], p1 = h->jac_colptr[(size_t)kb2 * P.z];
+                    CUDA_TRY(h, cudaMemcpyAsync(jac + p0, h->djac + p0, sizeof(double) * (p1 - p0), cudaMemcpyDeviceToHost, h->copy_stream));
+                    d2h += 8LL * (p1 - p0);
+                    return DTO_OK;
+                };
+                int rc = whole(Pr.kc0, std::min(Pr.kc1, 1));
+                if (rc != DTO_OK) return rc;
+                const int ka = std::max(Pr.kc0, 1), kb2 = std::min(Pr.kc1, P.nI);
+                if (ka < kb2) {
+                    const long long Lc = 2LL * P.Dsum, sk = h->jac_skip;
+                    const long long p0 = h->jac_colptr[(size_t)ka * P.z] + sk;
+                    CUDA_TRY(h, cudaMemcpy2DAsync(jac + p0, sizeof(double) * Lc, h->djac + p0, sizeof(double) * Lc, sizeof(double) * (Lc - sk),
+                                                  (size_t)(kb2 - ka) * P.z, cudaMemcpyDeviceToHost, h->copy_stream));
+                    d2h += 8LL * (Lc - sk) * (kb2 - ka) * P.z;
+                }
+                rc = whole(std::max(Pr.kc0, P.nI), Pr.kc1);
+                if (rc != DTO_OK) return rc;
+            }
+            if (hess && !sparse_hess) {
                 const long long p0 = hess_knot_base(P, Pr.kc0), p1 = hess_knot_base(P, std::min(Pr.kc1, P.nOwn));
                 CUDA_TRY(h, cudaMemcpyAsync(hess + p0, h->dhess + p0, sizeof(double) * (p1 - p0), cudaMemcpyDeviceToHost, h->copy_stream));
+                d2h += 8LL * (p1 - p0);
+            }
+            if (sparse_hess) {
+                // only the columns >= l0 of every knot of the range: one 2-D copy per run of equal knots
+                const int ka = Pr.kc0, kb2 = std::min(Pr.kc1, P.nOwn);
+                for (const HRun& r : h->hess_runs) {
+                    const int a = std::max(r.k0, ka), b2 = std::min(r.k0 + r.cnt, kb2);
+                    if (a >= b2) continue;
+                    const long long nc = hess_knot_has_cross(P, a) ? P.z : 0;
+                    const long long region = nc * P.z + (long long)P.z * (P.z + 1) / 2;
+                    const long long skip = (long long)r.l0 * nc + (long long)r.l0 * (r.l0 + 1) / 2;
+                    if (region == skip) continue;
+                    const long long p0 = hess_knot_base(P, a) + skip;
+                    CUDA_TRY(h, cudaMemcpy2DAsync(hess + p0, sizeof(double) * region, h->dhess + p0, sizeof(double) * region,
+                                                  sizeof(double) * (region - skip), (size_t)(b2 - a), cudaMemcpyDeviceToHost, h->copy_stream));
+                    d2h += 8LL * (region - skip) * (b2 - a);
+                }
             }
         }
+        // everything is enqueued: the calling thread writes its share of the structural zeros while the GPU works
+        if (sparse_hess || sparse_jac) h->zero_fill->finish();
         CUDA_TRY(h, cudaGetLastError());
     }
     if (J) CUDA_TRY(h, cudaMemcpyAsync(J, h->dJ, sizeof(double) * B, cudaMemcpyDeviceToHost, h->stream));
@@ -1048,6 +1286,7 @@ extern "C" int dto_eval_all(dto_handle* h, const double* Z, double sigma, const 
     if (g) CUDA_TRY(h, cudaMemcpyAsync(g, h->dg, sizeof(double) * B * P.n_cons_local, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     if (pipelined) CUDA_TRY(h, cudaStreamSynchronize(h->copy_stream));
+    h->last_d2h_bytes = d2h;
     return DTO_OK;
 }
 

@@ -377,6 +377,11 @@ class Evaluator:
     def launch_count(self):
         return int(self._lib.dto_launch_count(self._h))
 
+    @property
+    def last_d2h_bytes(self):
+        """Bytes the last host-pointer evaluation moved device -> host."""
+        return int(self._lib.dto_last_download_bytes(self._h))
+
     def kernel_timing(self, enable=True):
         _lib.check(self._lib.dto_kernel_timing(self._h, int(enable)), self._h)
 

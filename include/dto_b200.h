@@ -32,7 +32,11 @@
  *   - every output buffer is owned and pre-allocated by the caller and is fully overwritten.
  *   - host-pointer entry points copy between the caller's buffers and device buffers owned by the handle and
  *     return after the stream has drained; with page-locked caller buffers the device->host copies of
- *     finished knot ranges overlap the remaining computation.  `_dev` entry points take device pointers
+ *     finished knot ranges overlap the remaining computation.  For bilinear/derivative problems the structural
+ *     zeros of the Hessian (the cross-knot block and every column below the first one a term can touch) do not
+ *     cross PCIe: a few host threads of the handle write them into the caller's buffer meanwhile
+ *     (DTO_B200_HOST_THREADS, default 4; DTO_B200_SPARSE_D2H=0 delivers the whole array, =2 also leaves the constant
+ *     identity/zero head of every Jacobian column to the host threads).  `_dev` entry points take device pointers
  *     valid on the handle's device and enqueue on the handle's stream (dto_stream) without synchronising.
  *   - return value: 0 on success, negative dto_status otherwise; no exception crosses the boundary.
  *     dto_last_error() gives the message.  A handle is not thread-safe (matches the reference, whose
@@ -247,6 +251,9 @@ double* dto_local_Z(dto_handle* h);
 /* ---- instrumentation ---- */
 /* kernels launched by this handle since creation (bench.py's gpu_launches) */
 int64_t dto_launch_count(const dto_handle* h);
+/* bytes the last host-pointer evaluation moved device -> host.  Less than the size of the outputs when structural zeros
+ * of the Hessian (columns no term of the problem can touch) are written by host threads instead of crossing PCIe. */
+int64_t dto_last_download_bytes(const dto_handle* h);
 /* name of the bilinear kernel variant chosen for integrator i ("dmma", "generic", ...) */
 const char* dto_kernel_variant(const dto_handle* h, int integrator);
 /* CUDA-event timing of the interval kernels (K1/K7) on the handle's stream: enable, run evaluations,

@@ -331,3 +331,34 @@ def test_host_pipeline_matches_single_pass(monkeypatch):
     for plan, got in outs.items():
         for a, b in zip(ref, got):
             assert np.array_equal(np.asarray(a), np.asarray(b)), plan
+
+
+def test_structural_zero_hessian_delivery(monkeypatch):
+    """Host-pointer path of bilinear/derivative problems: only the Hessian columns a term can touch cross PCIe (one 2-D
+    copy per run of equal knots), host threads write the structural zeros of the caller's buffer meanwhile.  Must be
+    bit-identical to delivering the whole array, including knots where an objective reaches into the x block."""
+    prob = pt.quantum_gate_problem(N=640, levels=16, n_drives=4)
+    t = prob.trajectory
+    J = prob.objective + dto.KnotPointObjective(dto.SqDist(np.linspace(-1, 1, 32)), "x", t, times=[5, 6, 300], Qs=[1.0, 2.0, 3.0])
+    prob2 = dto.DirectTrajOptProblem(t, J, prob.integrators)
+    for pr in (prob, prob2, pt.scaled_problem(N=700, state_dim=32, n_controls=2, generator_scale=0.3)):
+        Z = pr.trajectory.vec()
+        outs = {}
+        for mode in ("1", "0", "2"):  # 2: also the constant heads of the Jacobian columns (opt-in)
+            monkeypatch.setenv("DTO_B200_SPARSE_D2H", mode)
+            ev = dto.Evaluator(pr)
+            mu = np.random.default_rng(5).random(ev.n_constraints)
+            for rep in range(2):  # the second call reuses the handle's worker threads
+                bufs = [np.full(1, np.nan), np.full(ev.n_vars, np.nan), np.full(ev.n_constraints, np.nan),
+                        np.full(ev.nnz_jacobian, np.nan), np.full(ev.nnz_hessian, np.nan)]
+                ev.eval_all(Z, 1.7, mu, *bufs)
+                assert all(np.isfinite(b).all() for b in bufs), mode
+            H = np.full(ev.nnz_hessian, np.nan)
+            ev.eval_hessian_lagrangian(H, Z, 1.7, mu)
+            assert np.array_equal(H, bufs[4])
+            outs[mode] = bufs
+            ev.close()
+        for mode in ("1", "2"):
+            for a, b in zip(outs[mode], outs["0"]):
+                assert np.array_equal(a, b)
+
