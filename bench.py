@@ -184,6 +184,9 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
+    # host threads of the handle (they write the Hessian's structural zeros into the caller's buffer on the host-pointer
+    # path): share the box's cores between the ranks; below 3 the library delivers the whole array over PCIe instead
+    os.environ.setdefault("DTO_B200_HOST_THREADS", str(max(1, min(4, (os.cpu_count() or 4) // (2 * world)))))
 
     import torch
     import torch.distributed as dist

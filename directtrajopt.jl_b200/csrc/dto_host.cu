@@ -833,12 +833,14 @@ extern "C" int dto_create(const dto_problem_desc* d, dto_handle** out) {
                     h->hess_runs.push_back(HRun{kl, 1, l0[kl]});
             }
             // worth it only when most of the array is structural and the runs are long (few copies)
-            if (zeros * 2 < P.nnz_hess_local || h->hess_runs.size() > 64) {
+            // host threads for the zero fill: at most 4, at most half the cores; with fewer than 3 the fill would be slower
+            // than the bus it relieves (one thread writes ~10 GB/s), so the whole array is delivered instead
+            int nth = (int)std::min<unsigned>(4, std::max(1u, std::thread::hardware_concurrency() / 2));
+            if (const char* e2 = getenv("DTO_B200_HOST_THREADS")) nth = std::max(1, std::min(32, atoi(e2)));
+            if (zeros * 2 < P.nnz_hess_local || h->hess_runs.size() > 64 || nth < 3) {
                 h->hess_runs.clear();
                 h->hess_zero_segs.clear();
             } else {
-                int nth = 4;
-                if (const char* e2 = getenv("DTO_B200_HOST_THREADS")) nth = std::max(1, std::min(32, atoi(e2)));
                 h->zero_fill = new (std::nothrow) ZeroFill();
                 if (h->zero_fill) h->zero_fill->start(nth);
                 else {
