@@ -58,12 +58,17 @@ CASES = {
     "standard_N10": lambda: pt.standard_problem(N=10, seed=0),
     "readme_N50": lambda: pt.readme_problem(N=50, seed=42),
     "gate_n32_N6": lambda: pt.quantum_gate_problem(N=6, levels=16, n_drives=4, seed=42),
+    # global variables: all four global component kinds with the reference's own test functions
+    "global_N7": lambda: pt.global_problem(N=7, seed=0),
+    # small states (n = 8, 16): the eight-intervals-per-warp kernel, a partial octet
+    "scaled_n8_N12": lambda: pt.scaled_problem(N=12, state_dim=8, n_controls=2, generator_scale=0.35),
+    "scaled_n16_N11": lambda: pt.scaled_problem(N=11, state_dim=16, n_controls=2, generator_scale=0.25),
 }
 
 
 def evaluate(prob, seed=123):
     spec = prob.to_spec()
-    Z = prob.trajectory.datavec.copy()
+    Z = prob.trajectory.vec()
     rng = np.random.default_rng(seed)
     jst, hst = orc.jacobian_structure(spec, Z), orc.hessian_structure(spec, Z)
     nd, nn = orc.n_constraints(spec)
@@ -76,6 +81,8 @@ def evaluate(prob, seed=123):
 
 if __name__ == "__main__":
     for name, build in CASES.items():
+        if os.path.exists(os.path.join(HERE, f"{name}.npz")) and "--all" not in sys.argv:
+            continue  # committed vectors are never regenerated silently
         out = evaluate(build())
         np.savez_compressed(os.path.join(HERE, f"{name}.npz"), **out)
         print(name, {k: (v.shape if hasattr(v, "shape") else v) for k, v in out.items()})
