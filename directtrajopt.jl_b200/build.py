@@ -21,6 +21,8 @@ INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 NVCC_FLAGS = os.environ.get("DTO_EXTRA_NVCC_FLAGS", "").split() + [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
+    # NOT -split-compile: it cuts the build from 4 min to under 2 but the kernels come out slower (measured on B200:
+    # K1 at c2 0.273 -> 0.403 ms, K7 at c3 8.6 -> 9.7 ms)
     "-Xcompiler", "-fPIC",
     "-I", INCLUDE,
 ]
