@@ -132,7 +132,11 @@ __device__ __forceinline__ void mul_t(Mat<NT>& out, const Mat<NT>& V, const Mat<
     }
 }
 
-template <int NT, int M>
+// PP: every problem of the batch has its own generators (dto_integrator_desc::G_batch_stride != 0).  An octet then holds
+// intervals of ONE problem (the last octet of a problem may be partial) and reads that problem's fragment-ordered
+// generators straight from global memory (DInt::bfrag, 2 (M+1) NT^2 KB-sized blocks that stay in L1/L2) instead of the
+// CTA's shared copy.
+template <int NT, int M, bool PP>
 __global__ void __launch_bounds__(NT == 1 ? 256 : 128)
     bilinear_octet_kernel(DProb P, int ii, const double* __restrict__ Z, const double* __restrict__ mu, double* __restrict__ g,
                           double* __restrict__ jac, int want_jac, int want_hess) {
@@ -143,10 +147,14 @@ __global__ void __launch_bounds__(NT == 1 ? 256 : 128)
     const int z = P.z;
 
     // ---- stage once per CTA: the matrices row-major (for the 1-norms) and the B fragments of G_j and G_j' ----
-    double* Gs = sm;                                                  // (M+1) * nn
-    double2* bf = reinterpret_cast<double2*>(sm + (M + 1) * nn);      // 2 (M+1) NT NT 32 double2: [G_0..G_M | G_0'..G_M']
-    for (int e = threadIdx.x; e < (M + 1) * nn; e += blockDim.x) Gs[e] = I.Grm[e];
-    for (int e = threadIdx.x; e < 2 * (M + 1) * NT * NT * 32; e += blockDim.x) {
+    const double* Gs = sm;                                                  // (M+1) * nn
+    const double2* bf = reinterpret_cast<const double2*>(sm + (M + 1) * nn);  // 2 (M+1) NT NT 32 double2: [G_0..G_M | G_0'..G_M']
+    constexpr int kFrag = 2 * (M + 1) * NT * NT * 32;
+    if constexpr (!PP) {
+    double* Gw = sm;
+    double2* bw = reinterpret_cast<double2*>(sm + (M + 1) * nn);
+    for (int e = threadIdx.x; e < (M + 1) * nn; e += blockDim.x) Gw[e] = I.Grm[e];
+    for (int e = threadIdx.x; e < kFrag; e += blockDim.x) {
         const int l = e & 31, f = e >> 5;
         const int nt = f % NT, t = (f / NT) % NT, mat = f / (NT * NT);
         const int s = 8 * nt + (l >> 2), k = 8 * t + 2 * (l & 3);
@@ -158,21 +166,40 @@ __global__ void __launch_bounds__(NT == 1 ? 256 : 128)
             b.x = I.G[(mat - M - 1) * nn + s * n + k];
             b.y = I.G[(mat - M - 1) * nn + s * n + k + 1];
         }
-        bf[e] = b;
+        bw[e] = b;
     }
     __syncthreads();
+    }
 
     const int nIc = min(P.kc1, P.nI) - P.kc0;  // intervals of the active range
     const long long nItems = (long long)P.batch * nIc;
-    const long long nOct = (nItems + 7) / 8;
+    const long long opp = (nIc + 7) / 8;       // PP: octets per problem
+    const long long nOct = PP ? opp * P.batch : (nItems + 7) / 8;
+    // (problem, local interval) of row r of octet `oct`; false for the padding rows of a partial octet
+    auto locate = [&](long long oct, int r, int& b, int& kk) -> bool {
+        if constexpr (PP) {
+            b = (int)(oct / opp);
+            const long long id = (oct % opp) * 8 + r;
+            kk = P.kc0 + (int)(id < nIc ? id : nIc - 1);
+            return id < nIc;
+        } else {
+            const long long id = oct * 8 + r;
+            const long long idc = id < nItems ? id : nItems - 1;
+            b = (int)(idc / nIc);
+            kk = P.kc0 + (int)(idc % nIc);
+            return id < nItems;
+        }
+    };
     const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const long long nWarps = (long long)gridDim.x * (blockDim.x >> 5);
 
     for (long long oct = warp0; oct < nOct; oct += nWarps) {
-        const long long id = oct * 8 + row8;
-        const bool valid = id < nItems;
-        const long long idc = valid ? id : nItems - 1;
-        const int b = (int)(idc / nIc), kk = P.kc0 + (int)(idc % nIc);
+        int b, kk;
+        const bool valid = locate(oct, row8, b, kk);
+        if constexpr (PP) {  // this problem's generators
+            Gs = I.Grm + (long long)b * I.G_stride;
+            bf = reinterpret_cast<const double2*>(I.bfrag) + (long long)b * kFrag;
+        }
         const double* zk = Z + (long long)b * P.n_vars_local + (long long)kk * z;
         const double* zk1 = zk + z;
         if (P.halo != nullptr && kk + 1 == P.nK - 1) zk1 = P.halo;
@@ -406,14 +433,15 @@ __global__ void __launch_bounds__(NT == 1 ? 256 : 128)
         // =========================== EXP: -E block, one interval at a time (rows = columns of E) ===========================
         const bool fused = P.analytic_fused == ii + 1;  // this kernel also writes the derivative integrators' rows
         if (fused && !want_jac) {
-            for (int r = 0; r < 8 && oct * 8 + r < nItems; ++r)
-                analytic_interval(P, Z, g, nullptr, (int)((oct * 8 + r) / nIc), P.kc0 + (int)((oct * 8 + r) % nIc), lane, 32);
+            for (int r = 0; r < 8; ++r) {
+                int br, kr;
+                if (locate(oct, r, br, kr)) analytic_interval(P, Z, g, nullptr, br, kr, lane, 32);
+            }
         }
         if (want_jac) {
             for (int r = 0; r < 8; ++r) {
-                const long long idr = oct * 8 + r;
-                if (idr >= nItems) break;
-                const int br = (int)(idr / nIc), kr = P.kc0 + (int)(idr % nIc);
+                int br, kr;
+                if (!locate(oct, r, br, kr)) break;
                 if (fused) analytic_interval(P, Z, g, jac, br, kr, lane, 32);
                 // the interval's own scalars, broadcast from the lanes of row r
                 const double cdt_r = __shfl_sync(0xffffffffu, cdt, 4 * r);
@@ -551,12 +579,12 @@ __global__ void __launch_bounds__(NT == 1 ? 256 : 128)
     }
 }
 
-template <int NT, int M>
-bool launch_octet(const DProb& P, int ii, const double* Z, const double* mu, double* g, double* jac, EvalFlags f, cudaStream_t st,
-                  long long* launches) {
+template <int NT, int M, bool PP>
+bool launch_octet_pp(const DProb& P, int ii, const double* Z, const double* mu, double* g, double* jac, EvalFlags f, cudaStream_t st,
+                     long long* launches) {
     constexpr int n = 8 * NT;
-    const size_t smem = sizeof(double) * (size_t)(M + 1) * n * n + sizeof(double2) * (size_t)2 * (M + 1) * NT * NT * 32;
-    auto kern = bilinear_octet_kernel<NT, M>;
+    const size_t smem = PP ? 0 : sizeof(double) * (size_t)(M + 1) * n * n + sizeof(double2) * (size_t)2 * (M + 1) * NT * NT * 32;
+    auto kern = bilinear_octet_kernel<NT, M, PP>;
     static PerDeviceOnce configured;
     if (smem > 48 * 1024 && configured.first()) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return false;
@@ -567,15 +595,40 @@ bool launch_octet(const DProb& P, int ii, const double* Z, const double* mu, dou
     const int threads = NT == 1 ? 256 : 128;
     int per_sm = 1;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
-    const long long items = (long long)P.batch * (std::min(P.kc1, P.nI) - P.kc0);
-    const long long octs = (items + 7) / 8, wpc = threads / 32;
+    const long long nIc = std::min(P.kc1, P.nI) - P.kc0, items = (long long)P.batch * nIc;
+    const long long octs = PP ? (long long)P.batch * ((nIc + 7) / 8) : (items + 7) / 8, wpc = threads / 32;
     const int grid = (int)std::max<long long>(1, std::min<long long>((long long)sms * per_sm, (octs + wpc - 1) / wpc));
     kern<<<grid, threads, smem, st>>>(P, ii, Z, mu, f.want_g ? g : nullptr, jac, f.want_jac ? 1 : 0, f.want_hess ? 1 : 0);
     ++*launches;
     return true;
 }
 
+template <int NT, int M>
+bool launch_octet(const DProb& P, int ii, const double* Z, const double* mu, double* g, double* jac, EvalFlags f, cudaStream_t st,
+                  long long* launches) {
+    if (P.in[ii].G_stride != 0) {
+        if (P.in[ii].bfrag == nullptr) return false;
+        return launch_octet_pp<NT, M, true>(P, ii, Z, mu, g, jac, f, st, launches);
+    }
+    return launch_octet_pp<NT, M, false>(P, ii, Z, mu, g, jac, f, st, launches);
+}
+
 }  // namespace
+
+// fragment-ordered copy of one problem's generators [G_0..G_m | G_0'..G_m'] (the layout the kernel stages in shared memory)
+void bilinear_octet_fragments(int n, int m, const double* Gcm /* (m+1) column-major matrices */, double* out) {
+    const int NT = n / 8, nn = n * n;
+    for (int mat = 0; mat < 2 * (m + 1); ++mat)
+        for (int t = 0; t < NT; ++t)
+            for (int nt = 0; nt < NT; ++nt)
+                for (int l = 0; l < 32; ++l) {
+                    const int s = 8 * nt + (l >> 2), k = 8 * t + 2 * (l & 3);
+                    double* o = out + ((((size_t)mat * NT + t) * NT + nt) * 32 + l) * 2;
+                    for (int e = 0; e < 2; ++e)  // G[s][k] = Gcm[k*n + s];  G'[s][k] = G[k][s] = Gcm[s*n + k]
+                        o[e] = mat <= m ? Gcm[(size_t)mat * nn + (size_t)(k + e) * n + s] : Gcm[(size_t)(mat - m - 1) * nn + (size_t)s * n + k + e];
+                }
+}
+size_t bilinear_octet_fragment_doubles(int n, int m) { return (size_t)2 * (m + 1) * (n / 8) * (n / 8) * 32 * 2; }
 
 bool bilinear_octet_supported(int n, int m) {
     if (n == 8) return m >= 1 && m <= 4;
@@ -587,7 +640,7 @@ bool launch_bilinear_octet(const DProb& P, int ii, const double* Z, const double
                            cudaStream_t st, long long* launches) {
     const DInt& I = P.in[ii];
     if (std::min(P.kc1, P.nI) - P.kc0 <= 0) return true;
-    if (!bilinear_octet_supported(I.n, I.m) || I.G_stride != 0) return false;
+    if (!bilinear_octet_supported(I.n, I.m)) return false;
     if (I.n == 8) {
         switch (I.m) {
             case 1: return launch_octet<1, 1>(P, ii, Z, mu, g, jac, f, st, launches);

@@ -292,6 +292,16 @@ extern "C" int dto_create(const dto_problem_desc* d, dto_handle** out) {
                 // small states: eight intervals per warp, one tile per jet component (bilinear_octet.cu)
                 if (bilinear_octet_supported(s.x_dim, s.u_dim) && !pin_persistent) I.variant = DTO_VAR_OCTET;
             }
+            if (s.G_batch_stride != 0 && bilinear_octet_supported(s.x_dim, s.u_dim) && !pin_dmma && !pin_generic && !pin_persistent) {
+                // per-problem generators at small n: the octet kernel reads each problem's fragment-ordered copy
+                const size_t fd = bilinear_octet_fragment_doubles(s.x_dim, s.u_dim);
+                std::vector<double> frag(fd * (size_t)d->batch);
+                for (int b = 0; b < d->batch; ++b)
+                    bilinear_octet_fragments(s.x_dim, s.u_dim, s.G + (size_t)b * s.G_batch_stride, frag.data() + (size_t)b * fd);
+                I.bfrag = dev_upload(h, frag.data(), frag.size());
+                if (!I.bfrag) return fail_create(h, DTO_ERR_ALLOC, "device allocation failed (generator fragments)");
+                I.variant = DTO_VAR_OCTET;
+            }
             if (pin_generic) I.variant = DTO_VAR_GENERIC;
             if (s.x_dim > 96) return fail_create(h, DTO_ERR_UNSUPPORTED, "bilinear integrator: state dimension > 96 not supported");
         } else if (s.kind == DTO_INT_DERIVATIVE) {
@@ -1075,7 +1085,7 @@ static void eval_range(dto_handle* h, const DProb& P, const double* dZ, double s
                 done = launch_bilinear_octet(P, i, dZ, dmu, dg, djac, f, h->stream, &h->launches);
                 if (!done && P.analytic_fused == i + 1) fused_missed = true;
             }
-            if (!done && P.in[i].variant >= DTO_VAR_PERSISTENT) done = launch_bilinear_persistent(P, i, dZ, dmu, dg, djac, f, h->stream, &h->launches);
+            if (!done && P.in[i].variant >= DTO_VAR_PERSISTENT && P.in[i].G_stride == 0) done = launch_bilinear_persistent(P, i, dZ, dmu, dg, djac, f, h->stream, &h->launches);
             if (!done && P.in[i].variant >= DTO_VAR_DMMA && bilinear_dmma_supported(P.in[i].n, P.in[i].m))
                 done = launch_bilinear_dmma(P, i, dZ, dmu, dg, djac, f, h->stream, &h->launches);
             if (!done) launch_bilinear_generic(P, i, dZ, dmu, dg, djac, f, h->stream, &h->launches);

@@ -25,6 +25,7 @@ struct DInt {
     long long G_stride;
     const double* G;    // column-major matrices
     const double* Grm;  // bilinear: row-major copies of the same matrices
+    const double* bfrag;  // bilinear, octet variant with per-problem generators: fragment-ordered copies [batch][...]
     const double *A, *B, *omega, *phi, *D, *omega_d, *phi_d;
     const double *Asw, *Bsw, *Dsw;  // tdbilinear, DMMA variant: swizzled row-major copies (Grm holds G0)
     double* tdb_scratch;            // tdbilinear, DMMA variant: per-CTA extrapolation scratch
@@ -161,6 +162,8 @@ bool bilinear_persistent_supported(int n, int m);
 bool launch_bilinear_octet(const DProb& P, int ii, const double* Z, const double* mu, double* g, double* jac, EvalFlags f,
                            cudaStream_t st, long long* launches);
 bool bilinear_octet_supported(int n, int m);
+void bilinear_octet_fragments(int n, int m, const double* Gcm, double* out);
+size_t bilinear_octet_fragment_doubles(int n, int m);
 bool launch_bilinear_product(const DProb& P, int ii, const double* Z, const double* w, double* y, bool transpose, cudaStream_t st,
                              long long* launches);
 void launch_analytic_product(const DProb& P, const double* Z, const double* w, double* y, bool transpose, cudaStream_t st,

@@ -41,18 +41,22 @@ def test_batch_equals_independent_problems(builder):
     batched.close()
 
 
-def test_batch_with_per_problem_generators():
-    B, n, m = 4, 8, 2
+@pytest.mark.parametrize("B,n,m,N,variant", [(4, 8, 2, 6, "octet"), (3, 8, 2, 20, "octet"), (3, 16, 2, 12, "octet"), (2, 8, 3, 10, "octet"),
+                                             (2, 24, 2, 5, "dmma")])
+def test_batch_with_per_problem_generators(B, n, m, N, variant):
+    """Every problem of the batch brings its own generators: small states run the octet kernel with one problem per octet
+    (partial last octets), the others the warp-per-interval tensor-core kernel."""
     rng = np.random.default_rng(5)
-    prob = pt.scaled_problem(N=6, state_dim=n, n_controls=m)
-    Gs = rng.standard_normal((B, m + 1, n, n))
+    prob = pt.scaled_problem(N=N, state_dim=n, n_controls=m)
+    Gs = rng.standard_normal((B, m + 1, n, n)) * (8.0 / n)
     batched = dto.Evaluator(prob, batch=B, batch_G=Gs)
+    assert batched.kernel_variant(0) == variant
     Z0 = prob.trajectory.datavec
     Zs = Z0[None, :] + 0.03 * rng.standard_normal((B, Z0.size))
     mus = rng.random((B, batched.n_constraints))
     out_b = all_outputs(batched, Zs, 1.0, mus)
     for b in range(B):
-        pb = pt.scaled_problem(N=6, state_dim=n, n_controls=m)
+        pb = pt.scaled_problem(N=N, state_dim=n, n_controls=m)
         pb.integrators[0].G = Gs[b]
         spec = pb.to_spec()
         jst, hst = orc.jacobian_structure(spec, Z0), orc.hessian_structure(spec, Z0)
