@@ -431,6 +431,27 @@ __global__ void __launch_bounds__(NT == 1 ? 256 : 128)
         }
 
         // =========================== EXP: -E block, one interval at a time (rows = columns of E) ===========================
+        // zero and identity columns (everything except the x, u, dt columns of the own knot), all eight intervals at once:
+        // the four lanes of a row write the 8 NT rows of their interval's column
+        if (want_jac && valid) {
+            const long long prev_off = jac_prev_off(P, kk + 1, I.doff);
+            for (int l = 0; l < 2 * z; ++l) {
+                if (l < z) {
+                    if ((l >= I.x_off && l < I.x_off + n) || (l >= I.u_off && l < I.u_off + M) || l == P.dt_off) continue;
+                    double* c = jp + jac_col(P, kk, l) + own_off;
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt) c[8 * nt + 2 * q] = c[8 * nt + 2 * q + 1] = 0.0;
+                } else {
+                    double* c = jp + jac_col(P, kk + 1, l - z) + prev_off;
+                    const int dg = l - z - I.x_off;  // the row that holds the 1 of d x_{k+1} / d x_{k+1}
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt) {
+                        c[8 * nt + 2 * q] = (dg == 8 * nt + 2 * q) ? 1.0 : 0.0;
+                        c[8 * nt + 2 * q + 1] = (dg == 8 * nt + 2 * q + 1) ? 1.0 : 0.0;
+                    }
+                }
+            }
+        }
         const bool fused = P.analytic_fused == ii + 1;  // this kernel also writes the derivative integrators' rows
         if (fused && !want_jac) {
             for (int r = 0; r < 8; ++r) {
@@ -562,17 +583,6 @@ __global__ void __launch_bounds__(NT == 1 ? 256 : 128)
                         cp[8 * nt + 2 * q + 1] = -F.v[nt][1];
                     }
                 }
-                }
-                // zero and identity columns of this interval (everything except the x, u, dt columns of the own knot)
-                const long long prev_r = jac_prev_off(P, kr + 1, I.doff);
-                for (int e = lane; e < 2 * z * n; e += 32) {
-                    const int l = e / n, a = e % n;
-                    if (l < z) {
-                        if ((l >= I.x_off && l < I.x_off + n) || (l >= I.u_off && l < I.u_off + M) || l == P.dt_off) continue;
-                        jr[jac_col(P, kr, l) + own_r + a] = 0.0;
-                    } else {
-                        jr[jac_col(P, (kr + 1), (l - z)) + prev_r + a] = (l - z - I.x_off == a) ? 1.0 : 0.0;
-                    }
                 }
             }
         }
