@@ -128,10 +128,27 @@ __global__ void hessian_assemble_kernel(DProb P, const double* __restrict__ Z, d
     const int warp = (threadIdx.x >> 5) * GPW + lane / GS;  // group index inside the CTA
     const unsigned gmask = GS == 32 ? 0xffffffffu : (((1u << GS) - 1u) << ((lane / GS) * GS));
     const long long item = (long long)blockIdx.x * warps_per_cta * GPW + warp;
+    const int tiles = P.any_cross ? 2 : 1;
+    // gather table of the stream-out, built once per CTA: entry e of a knot's region (column-major upper triangle with the
+    // z cross rows in front of every column) -> index into the knot's [diag | cross] tiles, 0xFFFFFFFF = structural zero
+    // (only for narrow knots, GS < 32: many knots share a CTA and the table; a wide knot has a CTA almost to itself and
+    // decodes its entries incrementally instead)
+    unsigned int* tab = reinterpret_cast<unsigned int*>(sm + (size_t)warps_per_cta * GPW * tiles * z * z);
+    if constexpr (GS < 32) {
+        const int region_c = z * z + z * (z + 1) / 2;
+        for (int e = threadIdx.x; e < region_c; e += blockDim.x) {
+            int l = 0, i = e;
+            while (i >= z + l + 1) {
+                i -= z + l + 1;
+                ++l;
+            }
+            tab[e] = i < z ? (P.any_cross ? (unsigned int)(z * z + i * z + l) : 0xFFFFFFFFu) : (unsigned int)((i - z) * z + l);
+        }
+        __syncthreads();
+    }
     if (item >= total) return;
     const int nKc = min(P.kc1, P.nOwn) - P.kc0;  // owned knots of the active range
     const int b = (int)(item / nKc), kl = P.kc0 + (int)(item % nKc);
-    const int tiles = P.any_cross ? 2 : 1;
     double* diag = sm + (size_t)warp * tiles * z * z;  // z*z, entries (i<=l) used
     double* cross = diag + z * z;                      // z*z if any_cross: cross[i*z + l] = H[knot kl-1 comp i][knot kl comp l]
     const double* zk = Z + (long long)b * P.n_vars_local + (long long)kl * z;
@@ -261,8 +278,13 @@ __global__ void hessian_assemble_kernel(DProb P, const double* __restrict__ Z, d
     double* hp = hess + (long long)b * P.nnz_hess_local + hess_knot_base(P, kl);
     const int ncross = has_cross ? z : 0;
     const int region = ncross * z + z * (z + 1) / 2;
-    {
-        // lane-private (column l, row-in-column i) cursor advanced by GS entries per iteration
+    if (GS < 32 && has_cross) {
+        for (int e = tid; e < region; e += GS) {
+            const unsigned t = tab[e];
+            hp[e] = t == 0xFFFFFFFFu ? 0.0 : diag[t];
+        }
+    } else {
+        // wide knots, and the first knot of the trajectory (no cross rows): lane-private (column l, row-in-column i) cursor advanced by GS entries
         int l = 0, i = tid;
         while (l < z && i >= ncross + l + 1) {
             i -= ncross + l + 1;
@@ -567,7 +589,8 @@ void launch_hessian_assemble(const DProb& P, const double* Z, double sigma, cons
     const int GS = P.z <= 16 ? 8 : (P.z <= 24 ? 16 : 32), GPW = 32 / GS;
     int W = 8;
     while (W > 1 && W * GPW * per_group > 64 * 1024) W >>= 1;
-    const size_t smem = W * GPW * per_group;
+    const size_t tab_bytes = (sizeof(unsigned int) * ((size_t)P.z * P.z + (size_t)P.z * (P.z + 1) / 2) + 15) / 16 * 16;
+    const size_t smem = W * GPW * per_group + (GS < 32 ? tab_bytes : 0);
     static PerDeviceOnce configured;
     if (smem > 48 * 1024 && configured.first()) {
         cudaFuncSetAttribute(hessian_assemble_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
