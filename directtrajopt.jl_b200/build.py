@@ -43,16 +43,21 @@ def _deps_hash():
 
 
 def _compile(src, dephash, verbose):
-    obj = os.path.join(OBJDIR, os.path.basename(src)[:-3] + ".o")
-    stamp = obj + ".stamp"
-    key = hashlib.sha256(open(src, "rb").read() + dephash.encode()).hexdigest()
-    if os.path.exists(obj) and os.path.exists(stamp) and open(stamp).read() == key:
+    # the object is named by the hash of everything that went into it (source, headers, flags): an object from another
+    # checkout can never be mistaken for a current one, and nothing about the build cache is tracked by git
+    key = hashlib.sha256(open(src, "rb").read() + dephash.encode()).hexdigest()[:16]
+    stem = os.path.basename(src)[:-3]
+    obj = os.path.join(OBJDIR, f"{stem}.{key}.o")
+    if os.path.exists(obj):
         return obj, ""
-    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+    for f in os.listdir(OBJDIR):  # older objects of the same source
+        if f.startswith(stem + ".") and f.endswith(".o"):
+            os.remove(os.path.join(OBJDIR, f))
+    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj + ".tmp"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
-    open(stamp, "w").write(key)
+    os.replace(obj + ".tmp", obj)
     return obj, r.stderr
 
 
@@ -69,12 +74,16 @@ def build(verbose: bool = False, force: bool = False) -> str:
         for obj, log in ex.map(lambda s: _compile(s, dephash, verbose), srcs):
             objs.append(obj)
             logs.append(log)
-    newest = max(os.path.getmtime(o) for o in objs)
-    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < newest:
+    # relink when the set of objects changed (their names carry their content keys)
+    manifest = os.path.join(OBJDIR, "linked.txt")
+    want = "\n".join(sorted(os.path.basename(o) for o in objs))
+    have = open(manifest).read() if os.path.exists(manifest) else ""
+    if force or not os.path.exists(LIB) or have != want:
         cmd = ["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+        open(manifest, "w").write(want)
     if verbose:
         sys.stderr.write("\n".join(logs))
     return LIB

@@ -7,6 +7,7 @@ import pytest
 import dto_b200 as dto
 import dto_oracle as orc
 from dto_b200 import problem_templates as pt
+from helpers import blocks
 
 pytestmark = pytest.mark.gpu
 
@@ -125,17 +126,21 @@ def test_values_match_oracle(case):
     assert relerr(grad, orc.eval_objective_gradient(spec, Z)) <= TOL
     g = np.full(ev.n_constraints, np.nan)
     ev.eval_constraint(g, Z)
-    assert relerr(g, orc.eval_constraint(spec, Z)) <= TOL
+    gref = orc.eval_constraint(spec, Z)
+    assert relerr(g, gref) <= TOL and blocks.vec_block_relerr(spec, g, gref) <= TOL
     J = np.full(ev.nnz_jacobian, np.nan)
     ev.eval_constraint_jacobian(J, Z)
-    assert relerr(J, orc.eval_constraint_jacobian(spec, Z, jst)) <= TOL
+    Jref = orc.eval_constraint_jacobian(spec, Z, jst)
+    # relative to the block norm: per (row block, component) Jacobian block, per Hessian knot region
+    assert relerr(J, Jref) <= TOL and blocks.jac_block_relerr(spec, jst, J, Jref) <= TOL
     H = np.full(ev.nnz_hessian, np.nan)
     ev.eval_hessian_lagrangian(H, Z, sigma, mu)
     Href = orc.eval_hessian_lagrangian(spec, Z, sigma, mu, hst)
-    assert relerr(H, Href) <= TOL
+    assert relerr(H, Href) <= TOL and blocks.hess_block_relerr(spec, hst, H, Href) <= TOL
     # sigma == 0 skips the objective (evaluator.jl:626)
     ev.eval_hessian_lagrangian(H, Z, 0.0, mu)
-    assert relerr(H, orc.eval_hessian_lagrangian(spec, Z, 0.0, mu, hst)) <= TOL
+    H0 = orc.eval_hessian_lagrangian(spec, Z, 0.0, mu, hst)
+    assert relerr(H, H0) <= TOL and blocks.hess_block_relerr(spec, hst, H, H0) <= TOL
 
 
 def test_fused_eval_all_equals_separate_callbacks(case):
@@ -278,15 +283,62 @@ def test_tdbilinear_matches_exact_variational_solution(order, n, m, carriers):
     assert relerr(g, orc.eval_constraint(spec, Z)) <= TDB_TOL
     J = np.empty(ev.nnz_jacobian)
     ev.eval_constraint_jacobian(J, Z)
-    assert relerr(J, orc.eval_constraint_jacobian(spec, Z, jst)) <= TDB_TOL
+    Jref = orc.eval_constraint_jacobian(spec, Z, jst)
+    assert relerr(J, Jref) <= TDB_TOL and blocks.jac_block_relerr(spec, jst, J, Jref) <= TDB_TOL
     H = np.empty(ev.nnz_hessian)
     ev.eval_hessian_lagrangian(H, Z, 1.5, mu)
     Href = orc.eval_hessian_lagrangian(spec, Z, 1.5, mu, hst)
-    assert relerr(H, Href) <= TDB_TOL
+    assert relerr(H, Href) <= TDB_TOL and blocks.hess_block_relerr(spec, hst, H, Href) <= TDB_TOL
     if order == 1:  # cross-knot Hessian entries are genuinely nonzero for the linear spline
         z = spec["z"]
         cross = (hr - 1) // z != (hc - 1) // z
         assert np.abs(Href[cross]).max() > 1e-6
+    ev.close()
+
+
+def test_c3_shape_matches_oracle():
+    """BASELINE config c3 at its real shape (n = 64, 2 drives, linear spline, derivative chain u -> du -> ddu, knot
+    constraint norm(u) - 1 <= 0 at knots 2..N-1) on a short trajectory: the `tdb_dmma_kernel<8,8>` + `tdb_exp_kernel<8>`
+    instantiations, whole problem against the oracle, values relative to the block norm."""
+    rng = np.random.default_rng(13)
+    prob = pt.carrier_problem(N=8, state_dim=64, n_drives=2, spline_order=1)
+    spec = prob.to_spec()
+    ev = dto.Evaluator(prob)
+    assert ev.kernel_variant(0) == "gbs-dmma"
+    Z0 = prob.trajectory.vec()
+    Z = Z0 + 0.02 * rng.standard_normal(Z0.size)
+    jst, hst = orc.jacobian_structure(spec, Z0), orc.hessian_structure(spec, Z0)
+    jr, jc = ev.jacobian_structure()
+    hr, hc = ev.hessian_lagrangian_structure()
+    assert np.array_equal(jr, jst[0]) and np.array_equal(jc, jst[1]) and np.array_equal(hr, hst[0]) and np.array_equal(hc, hst[1])
+    mu = rng.random(ev.n_constraints)
+    Jv, grad = np.empty(1), np.empty(ev.n_vars)
+    g, J, H = np.empty(ev.n_constraints), np.empty(ev.nnz_jacobian), np.empty(ev.nnz_hessian)
+    ev.eval_all(Z, 1.5, mu, Jv, grad, g, J, H)
+    gref, Jref = orc.eval_constraint(spec, Z), orc.eval_constraint_jacobian(spec, Z, jst)
+    Href = orc.eval_hessian_lagrangian(spec, Z, 1.5, mu, hst)
+    assert relerr(g, gref) <= TDB_TOL and blocks.vec_block_relerr(spec, g, gref) <= TDB_TOL
+    assert relerr(J, Jref) <= TDB_TOL and blocks.jac_block_relerr(spec, jst, J, Jref) <= TDB_TOL
+    assert relerr(H, Href) <= TDB_TOL and blocks.hess_block_relerr(spec, hst, H, Href) <= TDB_TOL
+    assert relerr(grad, orc.eval_objective_gradient(spec, Z)) <= TOL
+    assert abs(Jv[0] - orc.eval_objective(spec, Z)) <= TOL * max(1.0, abs(Jv[0]))
+    ev.close()
+
+
+def test_c3_full_size_sampled_intervals():
+    """config c3 at N = 1000: sampled intervals (first, last, random) against the oracle's variational solve."""
+    rng = np.random.default_rng(14)
+    prob = pt.carrier_problem(N=1000, state_dim=64, n_drives=2, spline_order=1)
+    spec = prob.to_spec()
+    ev = dto.Evaluator(prob)
+    Z = prob.trajectory.vec() + 0.02 * rng.standard_normal(ev.n_vars)
+    mu = rng.random(ev.n_constraints)
+    Jv, grad = np.empty(1), np.empty(ev.n_vars)
+    g, J, H = np.empty(ev.n_constraints), np.empty(ev.nnz_jacobian), np.empty(ev.nnz_hessian)
+    ev.eval_all(Z, 0.8, mu, Jv, grad, g, J, H)
+    ks = sorted({1, 2, 999, 1000} | {int(k) for k in rng.integers(1, 1001, size=12)})
+    er, ej, eh = blocks.sampled_interval_check(spec, Z, 0.8, mu, g, J, H, ks, jac_structure=ev.jacobian_structure())
+    assert er <= TDB_TOL and ej <= TDB_TOL and eh <= TDB_TOL, (er, ej, eh)
     ev.close()
 
 
