@@ -538,7 +538,70 @@ __global__ void constraint_product_kernel(DProb P, int ci, const double* __restr
         for (int a = 0; a < gd; ++a) y[row0 + a] = acc[a];
 }
 
+
+// (parameter, parameter) block of the compact Hessian of a bilinear integrator from the stored second-order vectors of
+// the forward jet (DInt::jets, written by the mu-independent pass over the iterate): hpp = -mu' W.  One quad per
+// entry; the lane owns elements 8 nt + 2 q + {0,1} and the sums run in the order of the interval kernels
+// (fma chain over nt, then the two xor-shuffles), so the two-pass result has the bits of the single pass.
+__global__ void hpp_contract_kernel(DProb P, int ii, const double* __restrict__ mu) {
+    const DInt& I = P.in[ii];
+    const int n = I.n, m = I.m, np = m + 1, J2 = m * (m + 1) / 2, nout = J2 + 1 + m, NT = n / 8;
+    const int q = threadIdx.x & 3;
+    const long long nIc = min(P.kc1, P.nI) - P.kc0;
+    const long long total = (long long)P.batch * nIc * nout;
+    const long long quad = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    const bool valid = quad < total;
+    const long long qd = valid ? quad : total - 1;
+    const int o = (int)(qd % nout);
+    const long long item = qd / nout;
+    const int b = (int)(item / nIc), kk = P.kc0 + (int)(item % nIc);
+    const double* mup = mu + (long long)b * P.n_cons_local + I.row_off + (long long)kk * n;
+    const double* W = I.jets + ((long long)b * P.nI + kk) * I.jet_stride;
+    auto dot = [&](int v) {
+        const double* w = W + (long long)v * n;
+        double s = 0.0;
+        for (int nt = 0; nt < NT; ++nt) s = fma(mup[8 * nt + 2 * q], w[8 * nt + 2 * q], fma(mup[8 * nt + 2 * q + 1], w[8 * nt + 2 * q + 1], s));
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        return s;
+    };
+    double* hpp = I.hs + ((long long)b * P.nI + kk) * I.hs_stride + (long long)np * n;
+    if (o < J2) {
+        const double s1 = dot(o);
+        int p = o, a = 0;
+        while (p >= m - a) {
+            p -= m - a;
+            ++a;
+        }
+        const int bb = a + p;
+        if (valid && q == 0) {
+            hpp[a * np + bb] = -s1;
+            hpp[bb * np + a] = -s1;
+        }
+    } else if (o == J2) {
+        const double dtt = dot(J2);
+        if (valid && q == 0) hpp[m * np + m] = -dtt;
+    } else {
+        const int i = o - J2 - 1;
+        const double dA = dot(J2 + 1 + i), dB = dot(J2 + 1 + m + i);
+        if (valid && q == 0) {
+            hpp[i * np + m] = -(dA + dB);
+            hpp[m * np + i] = -(dA + dB);
+        }
+    }
+}
+
 }  // namespace
+
+void launch_hpp_contract(const DProb& P, int ii, const double* mu, cudaStream_t st, long long* launches) {
+    const DInt& I = P.in[ii];
+    const long long nIc = std::min(P.kc1, P.nI) - P.kc0;
+    if (nIc <= 0 || I.jets == nullptr || I.hs == nullptr) return;
+    const long long quads = (long long)P.batch * nIc * (I.m * (I.m + 1) / 2 + 1 + I.m);
+    const int threads = 256;
+    hpp_contract_kernel<<<(unsigned)((quads * 4 + threads - 1) / threads), threads, 0, st>>>(P, ii, mu);
+    ++*launches;
+}
 
 void launch_analytic(const DProb& P, const double* Z, double* g, double* jac, EvalFlags f, cudaStream_t st, long long* launches) {
     bool any_deriv = false;

@@ -139,7 +139,7 @@ __device__ __forceinline__ void mul_t(Mat<NT>& out, const Mat<NT>& V, const Mat<
 template <int NT, int M, bool PP>
 __global__ void __launch_bounds__(NT == 1 ? 256 : 128)
     bilinear_octet_kernel(DProb P, int ii, const double* __restrict__ Z, const double* __restrict__ mu, double* __restrict__ g,
-                          double* __restrict__ jac, int want_jac, int want_hess) {
+                          double* __restrict__ jac, int want_jac, int want_hess, int jets) {
     constexpr int n = 8 * NT, nn = n * n, J = 1 + M + M * (M + 1) / 2;
     extern __shared__ __align__(16) double sm[];
     const DInt& I = P.in[ii];
@@ -233,10 +233,12 @@ __global__ void __launch_bounds__(NT == 1 ? 256 : 128)
         const long long mu_off = (long long)b * P.n_cons_local + I.row_off + (long long)kk * n;
         double* jp = jac + (long long)b * P.nnz_jac_local;
         const long long own_off = jac_own_off(P, kk, I.doff, n);
-        const bool deriv = want_jac || want_hess;
+        const bool store = jets == DTO_JETS_STORE;       // keep the second-order vectors for a later Hessian pass
+        const bool second = store || (want_hess && jets == DTO_JETS_NONE);
+        const bool deriv = want_jac || second;
 
         // =========================== FWD ===========================
-        {
+        if (jets != DTO_JETS_USE) {
             Tile<NT> F[J], term[J];
 #pragma unroll
             for (int j = 0; j < J; ++j) tzero(F[j]);
@@ -245,7 +247,7 @@ __global__ void __launch_bounds__(NT == 1 ? 256 : 128)
                 F[0].v[nt][0] = zk[I.x_off + 8 * nt + 2 * q];  // knots are not 16-byte aligned (odd z)
                 F[0].v[nt][1] = zk[I.x_off + 8 * nt + 2 * q + 1];
             }
-            const int JJ = deriv ? (want_hess ? J : 1 + M) : 1;  // tiles carried (uniform)
+            const int JJ = deriv ? (second ? J : 1 + M) : 1;  // tiles carried (uniform)
             for (int st = 0; st < Smax; ++st) {
                 const bool act_s = st < ser.stages;
 #pragma unroll
@@ -330,7 +332,51 @@ __global__ void __launch_bounds__(NT == 1 ? 256 : 128)
                         col[8 * nt + 2 * q + 1] = -GF0.v[nt][1];
                     }
                 }
-                if (want_hess) {
+                if (store && valid) {
+                    // the vectors the (parameter, parameter) entries are contractions of (launch_hpp_contract)
+                    constexpr int J2 = M * (M + 1) / 2;
+                    double* W = I.jets + ((long long)b * P.nI + kk) * I.jet_stride;
+                    auto put = [&](int slot, const Tile<NT>& t) {
+                        double* w = W + (long long)slot * n;
+#pragma unroll
+                        for (int nt = 0; nt < NT; ++nt) {
+                            w[8 * nt + 2 * q] = t.v[nt][0];
+                            w[8 * nt + 2 * q + 1] = t.v[nt][1];
+                        }
+                    };
+#pragma unroll
+                    for (int a = 0; a < M; ++a)
+#pragma unroll
+                        for (int c = a; c < M; ++c) put(idx2<M>(a, c) - 1 - M, F[idx2<M>(a, c)]);
+                }
+                if (store) {
+                    constexpr int J2 = M * (M + 1) / 2;
+                    double* W = I.jets + ((long long)b * P.nI + kk) * I.jet_stride;
+                    Tile<NT> GGF;
+                    apply_gu<NT, M>(GGF, GF0, u, bf, 0, lane);
+#pragma unroll
+                    for (int i = 0; i < M; ++i) {
+                        Tile<NT> GFi;
+                        apply_gu<NT, M>(GFi, F[1 + i], u, bf, 0, lane);
+                        if (valid) {
+#pragma unroll
+                            for (int nt = 0; nt < NT; ++nt) {
+                                W[(long long)(J2 + 1 + i) * n + 8 * nt + 2 * q] = GiF0[i].v[nt][0];
+                                W[(long long)(J2 + 1 + i) * n + 8 * nt + 2 * q + 1] = GiF0[i].v[nt][1];
+                                W[(long long)(J2 + 1 + M + i) * n + 8 * nt + 2 * q] = GFi.v[nt][0];
+                                W[(long long)(J2 + 1 + M + i) * n + 8 * nt + 2 * q + 1] = GFi.v[nt][1];
+                            }
+                        }
+                    }
+                    if (valid) {
+#pragma unroll
+                        for (int nt = 0; nt < NT; ++nt) {
+                            W[(long long)J2 * n + 8 * nt + 2 * q] = GGF.v[nt][0];
+                            W[(long long)J2 * n + 8 * nt + 2 * q + 1] = GGF.v[nt][1];
+                        }
+                    }
+                }
+                if (want_hess && jets == DTO_JETS_NONE) {
                     // hpp[p][q] over parameters [u_1..u_M, dt]; hs = hx[np][n] | hpp[np][np]
                     constexpr int np = M + 1;
                     double* hpp = I.hs + ((long long)b * P.nI + kk) * I.hs_stride + (long long)np * n;
@@ -453,7 +499,7 @@ __global__ void __launch_bounds__(NT == 1 ? 256 : 128)
             }
         }
         const bool fused = P.analytic_fused == ii + 1;  // this kernel also writes the derivative integrators' rows
-        if (fused && !want_jac) {
+        if (fused && !want_jac && g != nullptr) {
             for (int r = 0; r < 8; ++r) {
                 int br, kr;
                 if (locate(oct, r, br, kr)) analytic_interval(P, Z, g, nullptr, br, kr, lane, 32);
@@ -608,7 +654,7 @@ bool launch_octet_pp(const DProb& P, int ii, const double* Z, const double* mu, 
     const long long nIc = std::min(P.kc1, P.nI) - P.kc0, items = (long long)P.batch * nIc;
     const long long octs = PP ? (long long)P.batch * ((nIc + 7) / 8) : (items + 7) / 8, wpc = threads / 32;
     const int grid = (int)std::max<long long>(1, std::min<long long>((long long)sms * per_sm, (octs + wpc - 1) / wpc));
-    kern<<<grid, threads, smem, st>>>(P, ii, Z, mu, f.want_g ? g : nullptr, jac, f.want_jac ? 1 : 0, f.want_hess ? 1 : 0);
+    kern<<<grid, threads, smem, st>>>(P, ii, Z, mu, f.want_g ? g : nullptr, jac, f.want_jac ? 1 : 0, f.want_hess ? 1 : 0, f.jets);
     ++*launches;
     return true;
 }
@@ -651,6 +697,7 @@ bool launch_bilinear_octet(const DProb& P, int ii, const double* Z, const double
     const DInt& I = P.in[ii];
     if (std::min(P.kc1, P.nI) - P.kc0 <= 0) return true;
     if (!bilinear_octet_supported(I.n, I.m)) return false;
+    if (f.jets != DTO_JETS_NONE && I.jets == nullptr) return false;
     if (I.n == 8) {
         switch (I.m) {
             case 1: return launch_octet<1, 1>(P, ii, Z, mu, g, jac, f, st, launches);

@@ -105,6 +105,7 @@ struct Ctx {
     double* M3;        // EXP (Paterson-Stockmeyer) only
     double* S2;
     int lane, want_jac, want_hess;
+    int jets;          // EvalFlags::jets
 };
 
 // G(u) = G_0 + sum_i u_i G_i in the shared layout; returns ||G(u)||_1 (identical arithmetic in every role)
@@ -201,7 +202,7 @@ __device__ __forceinline__ void role_forward(const Ctx<NT>& c, int b, int kk, co
     for (int i = 0; i < kMaxDrives; ++i) uu[i] = i < m ? zk[I.u_off + i] : 0.0;
     const Series ser = choose_series(fabs(dt) * build_generator<NT>(c, uu, m));
     const long long mu_off = (long long)b * P.n_cons_local + I.row_off + (long long)kk * n;
-    const bool deriv = c.want_jac || c.want_hess;
+    const bool deriv = c.want_jac || c.want_hess || c.jets == DTO_JETS_STORE;
     const double* Gu = c.Gu;
 
     double F[MT][NT][2], term[MT][NT][2];
@@ -298,7 +299,7 @@ __device__ __forceinline__ void role_forward(const Ctx<NT>& c, int b, int kk, co
             }
         }
     }
-    if (c.want_hess) {
+    if (c.want_hess && c.jets == DTO_JETS_NONE) {
         // hpp[p][q] over parameters [u_1..u_m, dt]; hs = hx[np][n] | hpp[np][np]
         const int np = m + 1;
         double* hpp = I.hs + ((long long)b * P.nI + kk) * I.hs_stride + (long long)np * n;
@@ -360,6 +361,59 @@ __device__ __forceinline__ void role_forward(const Ctx<NT>& c, int b, int kk, co
     }
 }
 
+    if (c.jets == DTO_JETS_STORE) {
+        // the vectors the (parameter, parameter) entries are contractions of, for launch_hpp_contract (same order of
+        // summation there: the two passes give the bits of the single pass)
+        const int J2 = m * (m + 1) / 2;
+        double* W = I.jets + ((long long)b * P.nI + kk) * I.jet_stride;
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+            const int r = mt * 8 + row8;
+            if (r >= 1 + m && r < 1 + m + J2) {
+                double* w = W + (long long)(r - 1 - m) * n;
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    w[8 * nt + 2 * q] = F[mt][nt][0];
+                    w[8 * nt + 2 * q + 1] = F[mt][nt][1];
+                }
+            }
+        }
+        double GGF[1][NT][2];
+        frag_zero(GGF);
+        mma_apply<1, NT, 1>(GGF, GF, Gu, lane);
+        if (row8 == 0) {
+            double* w = W + (long long)J2 * n;
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                w[8 * nt + 2 * q] = GGF[0][nt][0];
+                w[8 * nt + 2 * q + 1] = GGF[0][nt][1];
+            }
+        }
+        if (row8 >= 1 && row8 <= m) {  // G dF/du_i sits in row 1+i of GF
+            double* w = W + (long long)(J2 + 1 + m + (row8 - 1)) * n;
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                w[8 * nt + 2 * q] = GF[0][nt][0];
+                w[8 * nt + 2 * q + 1] = GF[0][nt][1];
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < kMaxDrives; ++i) {
+            if (i < m) {
+                double GiF[1][NT][2];
+                frag_zero(GiF);
+                mma_apply<1, NT, MT>(GiF, F, c.Gs + (1 + i) * nn, lane);
+                if (row8 == 0) {
+                    double* w = W + (long long)(J2 + 1 + i) * n;
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt) {
+                        w[8 * nt + 2 * q] = GiF[0][nt][0];
+                        w[8 * nt + 2 * q + 1] = GiF[0][nt][1];
+                    }
+                }
+            }
+        }
+    }
 // ------------------------------------------------------------------------------------------------------------------
 // EXP, series mode: columns of the identity, MT tiles at a time, through the Taylor series
 // ------------------------------------------------------------------------------------------------------------------
@@ -759,7 +813,7 @@ template <int NT, int MT>
 __global__ void __launch_bounds__(max_warps<NT>() * 32, 1)
     bilinear_persistent_kernel(DProb P, int ii, const double* __restrict__ Z, const double* __restrict__ mu, double* __restrict__ g,
                                double* __restrict__ jac, int want_jac, int want_hess, unsigned long long* __restrict__ wq, int nE,
-                               int fetch) {
+                               int fetch, int jets) {
     extern __shared__ __align__(16) double sm[];
     constexpr int n = 8 * NT, nn = n * n;
     const DInt& I = P.in[ii];
@@ -791,6 +845,7 @@ __global__ void __launch_bounds__(max_warps<NT>() * 32, 1)
     c.lane = lane;
     c.want_jac = want_jac;
     c.want_hess = want_hess;
+    c.jets = jets;
     const bool ps = warp < nE;  // this warp owns the two spare matrices of the Paterson-Stockmeyer propagator
 
     // forward rows: r = mt*8 + row8 : 0 -> x, 1+i -> d/du_i, 1+m+p -> d2/(du_i du_j); where the drive products go
@@ -833,7 +888,7 @@ __global__ void __launch_bounds__(max_warps<NT>() * 32, 1)
     int order[3];
     int nroles = 0;
     if (ps && want_jac) order[nroles++] = ROLE_EXP;
-    order[nroles++] = ROLE_FWD;
+    if (jets != DTO_JETS_USE) order[nroles++] = ROLE_FWD;
     if (nE == 0 && want_jac) order[nroles++] = ROLE_EXP;
     if (want_hess) order[nroles++] = ROLE_ADJ;
     for (int ri = 0; ri < nroles; ++ri) {
@@ -1089,6 +1144,7 @@ __global__ void __launch_bounds__(max_warps<NT>() * 32, 1)
     c.M3 = c.S2 = nullptr;
     c.lane = lane;
     c.want_jac = c.want_hess = 0;
+    c.jets = DTO_JETS_NONE;
     const unsigned long long nItems = (unsigned long long)P.batch * (unsigned long long)P.nI;
     while (true) {
         unsigned long long id0 = 0;
@@ -1178,14 +1234,14 @@ bool launch_variant(const DProb& P, int ii, const double* Z, const double* mu, d
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return false;
     }
     const long long items = (long long)P.batch * (std::min(P.kc1, P.nI) - P.kc0);
-    const long long roles = 1 + (f.want_jac ? 1 : 0) + (f.want_hess ? 1 : 0);
+    const long long roles = (f.jets != DTO_JETS_USE ? 1 : 0) + (f.want_jac ? 1 : 0) + (f.want_hess ? 1 : 0);
     const long long want_ctas = (items * roles + W - 1) / W;
     const int grid = (int)std::max<long long>(1, std::min<long long>(sms, want_ctas));
     if (cudaMemsetAsync(I.wq, 0, 3 * sizeof(unsigned long long), st) != cudaSuccess) return false;
     // small items (n <= 16) are fetched several at a time: the atomic's round trip is as long as the item itself
     const long long per_warp = items / ((long long)grid * W);
     const int fetch = (NT <= 2) ? (int)std::max<long long>(1, std::min<long long>(8, per_warp / 8)) : 1;
-    kern<<<grid, W * 32, smem, st>>>(P, ii, Z, mu, f.want_g ? g : nullptr, jac, f.want_jac ? 1 : 0, f.want_hess ? 1 : 0, I.wq, nE, fetch);
+    kern<<<grid, W * 32, smem, st>>>(P, ii, Z, mu, f.want_g ? g : nullptr, jac, f.want_jac ? 1 : 0, f.want_hess ? 1 : 0, I.wq, nE, fetch, f.jets);
     ++*launches;
     return true;
 }
@@ -1202,7 +1258,9 @@ bool launch_bilinear_persistent(const DProb& P, int ii, const double* Z, const d
     const DInt& I = P.in[ii];
     if (std::min(P.kc1, P.nI) - P.kc0 <= 0) return true;
     if (!bilinear_persistent_supported(I.n, I.m) || I.G_stride != 0 || I.wq == nullptr) return false;
-    const int nrows = f.want_hess ? 1 + I.m + I.m * (I.m + 1) / 2 : 1 + I.m;
+    if (f.jets != DTO_JETS_NONE && I.jets == nullptr) return false;
+    const bool second = (f.want_hess && f.jets == DTO_JETS_NONE) || f.jets == DTO_JETS_STORE;  // forward role carries d2/du du
+    const int nrows = second ? 1 + I.m + I.m * (I.m + 1) / 2 : 1 + I.m;
     const bool two = nrows > 8;
 #define DTO_DISPATCH(NTv)                                                                                      \
     case NTv:                                                                                                  \

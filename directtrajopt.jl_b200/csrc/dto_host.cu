@@ -139,6 +139,17 @@ struct dto_handle {
     size_t ev_used = 0;
     double k1_ms = 0.0;
     long long k1_count = 0;
+    // ---- iterate cache (evaluator.jl:474-482: the reference copies Z once per callback; the solvers call the five
+    // callbacks separately on one iterate, ipopt_solver/solver.jl:85).  The handle keeps a page-locked copy of the iterate
+    // that is resident on the device; a callback whose Z equals it re-uses the upload and everything already computed.
+    int cache_mode = 1;        // 0: off; 1: one mu-independent pass (g + Jacobian + second-order jets) per new iterate; 2: compute only what is asked
+    double* hZpin = nullptr;   // [batch][n_vars_local]
+    bool z_valid = false;      // dZ holds hZpin
+    bool have_obj = false;     // dJ, dgrad
+    bool have_g = false, have_jac = false;  // dg, djac
+    bool have_jets = false;    // DInt::jets of every bilinear integrator
+    bool jets_ok = false;      // every interval kernel of the problem can keep / use the jets
+    long long cache_hits = 0, cache_misses = 0;
 };
 
 #define CUDA_TRY(h, call)                                                                       \
@@ -182,6 +193,7 @@ extern "C" void dto_destroy(dto_handle* h) {
     for (void* p : h->allocs) cudaFree(p);
     for (cudaEvent_t e : h->chunk_events) cudaEventDestroy(e);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->hZpin) cudaFreeHost(h->hZpin);
     delete h->zero_fill;
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -767,6 +779,34 @@ extern "C" int dto_create(const dto_problem_desc* d, dto_handle** out) {
     if (d->eval_hessian) h->dhess = dev_upload<double>(h, nullptr, B * (size_t)std::max<long long>(P.nnz_hess_local, 1));
     if (!h->dZ || !h->dmu || !h->dg || !h->djac || !h->dgrad || !h->dJ || !h->dpartials || (d->eval_hessian && !h->dhess))
         return fail_create(h, DTO_ERR_ALLOC, "device allocation failed (work buffers)");
+    {
+        // iterate cache: DTO_B200_ITERATE_CACHE=0 disables it, =lazy computes only what each callback asks for
+        const char* env = getenv("DTO_B200_ITERATE_CACHE");
+        h->cache_mode = env && strcmp(env, "0") == 0 ? 0 : (env && strcmp(env, "lazy") == 0 ? 2 : 1);
+        if (h->cache_mode && cudaHostAlloc((void**)&h->hZpin, sizeof(double) * B * (size_t)P.n_vars_local, cudaHostAllocDefault) != cudaSuccess) {
+            cudaGetLastError();
+            h->hZpin = nullptr;
+            h->cache_mode = 0;
+        }
+        bool ok = d->eval_hessian && h->cache_mode == 1;
+        bool any = false;
+        for (int i = 0; i < P.n_int; ++i) {
+            if (P.in[i].kind == DTO_INT_DERIVATIVE) continue;
+            any = true;
+            ok = ok && P.in[i].kind == DTO_INT_BILINEAR && P.in[i].variant >= DTO_VAR_PERSISTENT;
+        }
+        if (ok && any) {
+            for (int i = 0; i < P.n_int && ok; ++i) {
+                DInt& I = P.in[i];
+                if (I.kind != DTO_INT_BILINEAR) continue;
+                I.jet_stride = (I.m * (I.m + 1) / 2 + 1 + 2 * I.m) * I.n;
+                I.jets = dev_upload<double>(h, nullptr, B * (size_t)std::max(P.nI, 1) * I.jet_stride);
+                ok = I.jets != nullptr;
+            }
+            if (!ok) cudaGetLastError();
+            h->jets_ok = ok;
+        }
+    }
     {
         // chunk boundaries of the host-pointer pipeline as cumulative fractions of the intervals; DTO_B200_PIPELINE=0
         // disables it, DTO_B200_PIPELINE=0.1,0.4,0.7 overrides the plan

@@ -31,6 +31,12 @@ struct DInt {
     double* tdb_scratch;            // tdbilinear, DMMA variant: per-CTA extrapolation scratch
     int tdb_scratch_ctas;           // CTAs the scratch was sized for (one per SM)
     double* hs;         // [batch][n_intervals][hs_stride]
+    // bilinear (persistent / octet variants): the second-order vectors of the forward jet, kept between the mu-independent
+    // pass over a new iterate and the Hessian callback on the same iterate (EvalFlags::jets):
+    // [batch][n_intervals][jet_stride], jet_stride = (m(m+1)/2 + 1 + 2m) n :
+    //   d2(Ex)/(du_a du_b) (a <= b, row-major over the upper triangle) | G G E x | G_i E x (i < m) | G d(Ex)/du_i (i < m)
+    double* jets;
+    int jet_stride;
     unsigned long long* wq;  // bilinear, persistent variant: three work-queue counters (FWD, EXP, ADJ)
 };
 
@@ -148,9 +154,18 @@ struct PerDeviceOnce {
 };
 
 // ---- kernel launchers (defined in the .cu files) ------------------------------------------------
+// jets: 0 = single pass (the Hessian pass contracts the second-order jet with mu in the interval kernel);
+//       1 = mu-independent pass over a new iterate: the forward role also carries the second-order rows and STORES the
+//           vectors the (parameter, parameter) Hessian entries are contractions of (DInt::jets); no mu is read;
+//       2 = Hessian pass on an iterate whose jets are stored: only the adjoint role runs (want_hess must be set), the
+//           (parameter, parameter) entries come from launch_hpp_contract.
+enum { DTO_JETS_NONE = 0, DTO_JETS_STORE = 1, DTO_JETS_USE = 2 };
 struct EvalFlags {
     bool want_g, want_jac, want_hess;
+    int jets = DTO_JETS_NONE;
 };
+// (parameter, parameter) block of the compact Hessian from stored jets: hpp = -mu' W, same summation order as the kernels
+void launch_hpp_contract(const DProb& P, int ii, const double* mu, cudaStream_t st, long long* launches);
 void launch_bilinear_generic(const DProb& P, int ii, const double* Z, const double* mu, double* g, double* jac, EvalFlags f,
                              cudaStream_t st, long long* launches);
 bool launch_bilinear_dmma(const DProb& P, int ii, const double* Z, const double* mu, double* g, double* jac, EvalFlags f,
