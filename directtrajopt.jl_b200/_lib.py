@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libdto_b200.so")
 
 DTO_OK, DTO_ERR_INVALID, DTO_ERR_UNSUPPORTED, DTO_ERR_CUDA, DTO_ERR_ALLOC = 0, -1, -2, -3, -4
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 INT_BILINEAR, INT_DERIVATIVE, INT_TDBILINEAR = 1, 2, 3
 OBJ_QUADREG, OBJ_MINTIME, OBJ_KNOT, OBJ_NULL, OBJ_LINREG, OBJ_GLOBAL_KNOT = 1, 2, 3, 4, 5, 6
@@ -90,6 +90,10 @@ SYMBOLS = [
     ("dto_eval_jacobian_product", C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("dto_eval_jacobian_transpose_product", C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("dto_eval_all", C.c_int, [_H, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("dto_upload", C.c_int, [_H, C.c_void_p]),
+    ("dto_cache_stats", C.c_int, [_H, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    ("dto_register_outputs", C.c_int, [_H, C.c_void_p, C.c_void_p]),
+    ("dto_unregister_outputs", C.c_int, [_H]),
     ("dto_eval_all_dev", C.c_int, [_H, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("dto_violation_dev", C.c_int, [_H, C.c_void_p, C.c_void_p]),
     ("dto_synchronize", C.c_int, [_H]),

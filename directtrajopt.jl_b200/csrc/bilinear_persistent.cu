@@ -359,8 +359,6 @@ __device__ __forceinline__ void role_forward(const Ctx<NT>& c, int b, int kk, co
             }
         }
     }
-}
-
     if (c.jets == DTO_JETS_STORE) {
         // the vectors the (parameter, parameter) entries are contractions of, for launch_hpp_contract (same order of
         // summation there: the two passes give the bits of the single pass)
@@ -414,6 +412,8 @@ __device__ __forceinline__ void role_forward(const Ctx<NT>& c, int b, int kk, co
             }
         }
     }
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // EXP, series mode: columns of the identity, MT tiles at a time, through the Taylor series
 // ------------------------------------------------------------------------------------------------------------------

@@ -125,6 +125,14 @@ struct dto_handle {
     // host-pointer path: outputs leave over PCIe while later knot ranges are still being computed
     cudaStream_t copy_stream = nullptr;
     std::vector<cudaEvent_t> chunk_events;
+    cudaEvent_t chunk_events_at(size_t i) {  // created on demand; nullptr on failure
+        while (chunk_events.size() <= i) {
+            cudaEvent_t e = nullptr;
+            if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+            chunk_events.push_back(e);
+        }
+        return chunk_events[i];
+    }
     std::vector<double> pipeline_fracs;  // cumulative interval fractions of the chunk boundaries (empty = no pipelining)
     std::vector<HRun> hess_runs;         // empty: the Hessian is delivered whole
     std::vector<std::pair<long long, long long>> hess_zero_segs;  // structural-zero prefixes of the knot regions
@@ -150,6 +158,15 @@ struct dto_handle {
     bool have_jets = false;    // DInt::jets of every bilinear integrator
     bool jets_ok = false;      // every interval kernel of the problem can keep / use the jets
     long long cache_hits = 0, cache_misses = 0;
+    // ---- registered outputs (dto_register_outputs): the solver's own value arrays, page-locked, structural constants
+    // written once; later callbacks that are handed these pointers move only the value-dependent entries
+    double *reg_jac = nullptr, *reg_hess = nullptr;
+    bool reg_jac_pinned = false, reg_hess_pinned = false;  // page lock taken by this handle
+    bool reg_jac_sparse = false, reg_hess_sparse = false;  // constants are in place
+    int jac_skip_ok = 0;             // length of the constant head of the inner knots' Jacobian columns (0: no common layout)
+    bool fill_threads_ok = false;    // enough host threads to zero-fill an unregistered Hessian buffer faster than PCIe delivers it
+    bool spec_jac_inflight = false;  // a speculative delivery of the Jacobian into reg_jac is on the copy stream
+    bool spec_jac_done = false;      // reg_jac holds the resident iterate's Jacobian (once the copy stream has drained)
 };
 
 #define CUDA_TRY(h, call)                                                                       \
@@ -185,6 +202,7 @@ extern "C" const char* dto_last_error(const dto_handle* h) { return h ? h->err.c
 extern "C" void dto_destroy(dto_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
+    dto_unregister_outputs(h);
     if (h->ipc_peer) cudaIpcCloseMemHandle(h->ipc_peer);
     for (auto& e : h->ev_pool) {
         cudaEventDestroy(e.first);
@@ -811,7 +829,14 @@ extern "C" int dto_create(const dto_problem_desc* d, dto_handle** out) {
         // chunk boundaries of the host-pointer pipeline as cumulative fractions of the intervals; DTO_B200_PIPELINE=0
         // disables it, DTO_B200_PIPELINE=0.1,0.4,0.7 overrides the plan
         const char* env = getenv("DTO_B200_PIPELINE");
-        if (!env) h->pipeline_fracs = {0.1, 0.4, 0.7};
+        if (!env) {
+            // the persistent interval kernel needs many items per warp to fill the FP64 pipe (one forward item alone takes
+            // ~100 us): two ranges; the octet kernel's items are small: four
+            bool persistent = false;
+            for (int i = 0; i < P.n_int; ++i) persistent |= P.in[i].kind == DTO_INT_BILINEAR && P.in[i].variant == DTO_VAR_PERSISTENT;
+            if (persistent) h->pipeline_fracs = {0.5};
+            else h->pipeline_fracs = {0.1, 0.4, 0.7};
+        }
         else if (strcmp(env, "0") != 0) {
             std::string t(env);
             size_t pos = 0;
@@ -887,15 +912,14 @@ extern "C" int dto_create(const dto_problem_desc* d, dto_handle** out) {
             // than the bus it relieves (one thread writes ~10 GB/s), so the whole array is delivered instead
             int nth = (int)std::min<unsigned>(4, std::max(1u, std::thread::hardware_concurrency() / 2));
             if (const char* e2 = getenv("DTO_B200_HOST_THREADS")) nth = std::max(1, std::min(32, atoi(e2)));
-            if (zeros * 2 < P.nnz_hess_local || h->hess_runs.size() > 64 || nth < 3) {
+            if (zeros * 2 < P.nnz_hess_local || h->hess_runs.size() > 64) {
                 h->hess_runs.clear();
                 h->hess_zero_segs.clear();
-            } else {
+            } else if (nth >= 3) {  // unregistered buffers need the fill threads; registered ones have their zeros in place
                 h->zero_fill = new (std::nothrow) ZeroFill();
-                if (h->zero_fill) h->zero_fill->start(nth);
-                else {
-                    h->hess_runs.clear();
-                    h->hess_zero_segs.clear();
+                if (h->zero_fill) {
+                    h->zero_fill->start(nth);
+                    h->fill_threads_ok = true;
                 }
             }
         }
@@ -907,8 +931,9 @@ extern "C" int dto_create(const dto_problem_desc* d, dto_handle** out) {
         const char* env = getenv("DTO_B200_SPARSE_D2H");
         const int k0i = P.in[0].kind;
         const long long L = 2LL * P.Dsum, d1 = P.in[0].n;
-        if (d->batch == 1 && P.jac_closed && G == 0 && P.nI >= 3 && (k0i == DTO_INT_BILINEAR || k0i == DTO_INT_DERIVATIVE) &&
-            env && strcmp(env, "2") == 0 && 8 * (L - d1) >= 256) {  // opt-in: 256-byte rows make a slow strided copy
+        if (d->batch == 1 && P.jac_closed && G == 0 && P.nI >= 3 && (k0i == DTO_INT_BILINEAR || k0i == DTO_INT_DERIVATIVE) && 8 * (L - d1) >= 256)
+            h->jac_skip_ok = (int)d1;  // registered Jacobian arrays (dto_register_outputs) get the constant heads once
+        if (h->jac_skip_ok && env && strcmp(env, "2") == 0) {  // unregistered buffers: opt-in (74 000 small memsets per call at c2)
             if (!h->zero_fill) {
                 int nth = 4;
                 if (const char* e2 = getenv("DTO_B200_HOST_THREADS")) nth = std::max(1, std::min(32, atoi(e2)));
@@ -1111,9 +1136,9 @@ static void eval_prologue(dto_handle* h, const DProb& P, const double* dZ, doubl
 }
 
 // Interval kernels, analytic integrators and the Hessian assembler over the active knot range of P.
-static void eval_range(dto_handle* h, const DProb& P, const double* dZ, double sigma, const double* dmu, double* dg, double* djac,
-                       double* dhess, EvalFlags f) {
-    if (!(f.want_g || f.want_jac || f.want_hess)) return;
+static int eval_range(dto_handle* h, const DProb& P, const double* dZ, double sigma, const double* dmu, double* dg, double* djac,
+                      double* dhess, EvalFlags f) {
+    if (!(f.want_g || f.want_jac || f.want_hess)) return DTO_OK;
     bool fused_missed = false;
     for (int i = 0; i < P.n_int; ++i) {
         if (P.in[i].kind == DTO_INT_DERIVATIVE) continue;
@@ -1126,9 +1151,14 @@ static void eval_range(dto_handle* h, const DProb& P, const double* dZ, double s
                 if (!done && P.analytic_fused == i + 1) fused_missed = true;
             }
             if (!done && P.in[i].variant >= DTO_VAR_PERSISTENT && P.in[i].G_stride == 0) done = launch_bilinear_persistent(P, i, dZ, dmu, dg, djac, f, h->stream, &h->launches);
+            if (!done && f.jets != DTO_JETS_NONE) {
+                h->err = "interval kernel cannot keep the forward jets between callbacks (internal)";
+                return DTO_ERR_CUDA;
+            }
             if (!done && P.in[i].variant >= DTO_VAR_DMMA && bilinear_dmma_supported(P.in[i].n, P.in[i].m))
                 done = launch_bilinear_dmma(P, i, dZ, dmu, dg, djac, f, h->stream, &h->launches);
             if (!done) launch_bilinear_generic(P, i, dZ, dmu, dg, djac, f, h->stream, &h->launches);
+            if (f.jets == DTO_JETS_USE) launch_hpp_contract(P, i, dmu, h->stream, &h->launches);
         } else if (P.in[i].kind == DTO_INT_TDBILINEAR) {
             bool done = false;
             if (P.in[i].variant == DTO_VAR_DMMA) done = launch_tdb_dmma(P, i, dZ, dmu, dg, djac, f, h->stream, &h->launches);
@@ -1147,6 +1177,7 @@ static void eval_range(dto_handle* h, const DProb& P, const double* dZ, double s
     }
     if (f.want_hess) launch_hessian_assemble(P, dZ, sigma, dmu, dhess, h->stream, &h->launches);
     if (f.want_hess) launch_global_hessian(P, dZ, sigma, dmu, dhess, nullptr, h->stream, &h->launches);
+    return DTO_OK;
 }
 
 static int check_eval_args(dto_handle* h, const double* dmu, const double* dhess) {
@@ -1167,13 +1198,14 @@ static int run_eval(dto_handle* h, const double* dZ, double sigma, const double*
     int rc = check_eval_args(h, dmu, dhess);
     if (rc != DTO_OK) return rc;
     EvalFlags f{dg != nullptr, djac != nullptr, dhess != nullptr};
-    eval_range(h, P, dZ, sigma, dmu, dg, djac, dhess, f);
+    rc = eval_range(h, P, dZ, sigma, dmu, dg, djac, dhess, f);
+    if (rc != DTO_OK) return rc;
     eval_prologue(h, P, dZ, dJ, dgrad, dg, djac, f);
     CUDA_TRY(h, cudaGetLastError());
     return DTO_OK;
 }
 
-// Every interval kernel of the problem honours DProb::kc0/kc1 (only the persistent bilinear variant does)
+// Every interval kernel of the problem honours DProb::kc0/kc1 (the persistent and octet bilinear variants do)
 static bool range_capable(const dto_handle* h) {
     const DProb& P = h->P;
     if (P.batch != 1 || P.any_cross || P.gl.G > 0) return false;
@@ -1186,6 +1218,8 @@ extern "C" int dto_eval_all_dev(dto_handle* h, const double* dZ, double sigma, c
                                 double* dg, double* djac, double* dhess) {
     if (!h || !dZ) return DTO_ERR_INVALID;
     CUDA_TRY(h, cudaSetDevice(h->device));
+    // scratch shared with the cached callbacks (compact Hessian, jets) is overwritten; caller-owned outputs are not tracked
+    if (dZ != h->dZ) h->have_jets = false;
     return run_eval(h, dZ, sigma, dmu, dJ, dgrad, dg, djac, dhess);
 }
 
@@ -1195,172 +1229,422 @@ extern "C" int dto_synchronize(dto_handle* h) {
     return DTO_OK;
 }
 
-extern "C" int dto_eval_all(dto_handle* h, const double* Z, double sigma, const double* mu, double* J, double* grad, double* g,
-                            double* jac, double* hess) {
+// ---- iterate cache -----------------------------------------------------------------------------------
+// 1: Z is the resident iterate (nothing moved); 0: a new iterate was uploaded (every cached quantity dropped); < 0: error
+static int ensure_iterate(dto_handle* h, const double* Z) {
+    const DProb& P = h->P;
+    const size_t bytes = sizeof(double) * (size_t)P.batch * (size_t)P.n_vars_local;
+    if (h->cache_mode && h->z_valid && memcmp(h->hZpin, Z, bytes) == 0) {
+        ++h->cache_hits;
+        return 1;
+    }
+    ++h->cache_misses;
+    h->have_obj = h->have_g = h->have_jac = h->have_jets = false;
+    h->z_valid = false;
+    h->spec_jac_done = false;
+    if (h->spec_jac_inflight) {  // the previous iterate's Jacobian is still leaving for the registered array
+        CUDA_TRY(h, cudaStreamSynchronize(h->copy_stream));
+        h->spec_jac_inflight = false;
+    }
+    if (h->cache_mode) {
+        memcpy(h->hZpin, Z, bytes);
+        CUDA_TRY(h, cudaMemcpyAsync(h->dZ, h->hZpin, bytes, cudaMemcpyHostToDevice, h->stream));
+        h->z_valid = true;
+    } else {
+        CUDA_TRY(h, cudaMemcpyAsync(h->dZ, Z, bytes, cudaMemcpyHostToDevice, h->stream));
+    }
+    return 0;
+}
+
+extern "C" int dto_cache_stats(const dto_handle* h, int64_t* hits, int64_t* misses) {
+    if (!h || !hits || !misses) return DTO_ERR_INVALID;
+    *hits = h->cache_hits;
+    *misses = h->cache_misses;
+    return DTO_OK;
+}
+
+extern "C" int dto_upload(dto_handle* h, const double* Z) {
     if (!h || !Z) return DTO_ERR_INVALID;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const int rc = ensure_iterate(h, Z);
+    if (rc < 0) return rc;
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return DTO_OK;
+}
+
+// joins the zero-fill workers on every exit path (they write into the caller's buffer)
+struct FillGuard {
+    ZeroFill* z = nullptr;
+    ~FillGuard() {
+        if (z) z->finish();
+    }
+};
+
+// What one host-pointer call computes on the device (`passes`, `comp_obj`) and what it delivers to the caller (the non-null
+// host pointers).  Z (and mu) are already on their way to the device.  A quantity that is delivered but not computed is
+// resident from an earlier callback on the same iterate.  `spec_jac`: the Jacobian computed by this call also goes to the
+// registered array on the copy stream, and the call returns without waiting for it (dto_eval_jacobian on the same iterate
+// with that array only joins the copy).
+static int eval_core(dto_handle* h, double sigma, const EvalFlags* passes, int n_passes, bool comp_obj, double* J, double* grad,
+                     double* g, double* jac, double* hess, bool spec_jac = false) {
     const DProb& P = h->P;
     const size_t B = (size_t)P.batch;
-    if (hess && !h->eval_hessian) {
-        h->err = "evaluator was created with eval_hessian = false";
-        return DTO_ERR_INVALID;
+    bool comp_jac = false, comp_hess = false, comp_g = false;
+    for (int i = 0; i < n_passes; ++i) {
+        comp_g |= passes[i].want_g;
+        comp_jac |= passes[i].want_jac;
+        comp_hess |= passes[i].want_hess;
     }
-    if (hess && !mu) {
-        h->err = "Hessian evaluation needs mu";
-        return DTO_ERR_INVALID;
-    }
-    CUDA_TRY(h, cudaSetDevice(h->device));
-    CUDA_TRY(h, cudaMemcpyAsync(h->dZ, Z, sizeof(double) * B * P.n_vars_local, cudaMemcpyHostToDevice, h->stream));
-    if (hess) CUDA_TRY(h, cudaMemcpyAsync(h->dmu, mu, sizeof(double) * B * P.n_cons_local, cudaMemcpyHostToDevice, h->stream));
+    if (spec_jac) jac = h->reg_jac;
     long long d2h = 8LL * B * ((J ? 1 : 0) + (grad ? P.n_grad_local : 0) + (g ? P.n_cons_local : 0));
-    double* dJ = J ? h->dJ : nullptr;
-    double* dgrad = grad ? h->dgrad : nullptr;
-    double* dg = g ? h->dg : nullptr;
-    double* djac = jac ? h->djac : nullptr;
-    double* dhess = hess ? h->dhess : nullptr;
-    EvalFlags f{dg != nullptr, djac != nullptr, dhess != nullptr};
+    double* dJ = comp_obj ? h->dJ : nullptr;
+    double* dgrad = comp_obj ? h->dgrad : nullptr;
+    EvalFlags fany{comp_g, comp_jac, comp_hess};
+    if (!h->copy_stream) CUDA_TRY(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
 
-    // Large sparse outputs: cut the trajectory into a few knot ranges; the Jacobian columns and Hessian
-    // blocks of a finished range go out on the copy engine while the next range is being computed.
-    const long long out_bytes = 8LL * ((jac ? P.nnz_jac_local : 0) + (hess ? P.nnz_hess_local : 0));
-    const bool pipelined = !h->pipeline_fracs.empty() && (jac || hess) && out_bytes >= (8LL << 20) && P.nI >= 512 && range_capable(h);
-    if (!pipelined) {
-        int rc = run_eval(h, h->dZ, sigma, h->dmu, dJ, dgrad, dg, djac, dhess);
+    // Structural constants stay off the bus: a registered array has them in place (written once by dto_register_outputs);
+    // an unregistered Hessian buffer gets them from the handle's host threads while the GPU computes.
+    const bool reg_h = hess && hess == h->reg_hess && h->reg_hess_sparse;
+    const bool reg_j = jac && jac == h->reg_jac && h->reg_jac_sparse;
+    const bool big = 8LL * ((jac ? P.nnz_jac_local : 0) + (hess ? P.nnz_hess_local : 0)) >= (8LL << 20) && P.nI >= 512;
+    const bool sparse_hess = hess && big && !h->hess_runs.empty() && (reg_h || (h->fill_threads_ok && range_capable(h)));
+    const bool sparse_jac = jac && big && ((reg_j && h->jac_skip_ok > 0) || (h->jac_skip > 0 && h->zero_fill && range_capable(h)));
+    const int jskip = sparse_jac ? (reg_j ? h->jac_skip_ok : h->jac_skip) : 0;
+    const bool fill_h = sparse_hess && !reg_h, fill_j = sparse_jac && !reg_j;
+
+    // Jacobian columns / Hessian regions of the local knots [ka, kb) on stream `st`
+    auto deliver_jac = [&](int ka, int kb, cudaStream_t st) -> int {
+        auto whole = [&](int a, int b2) -> int {
+            if (a >= b2) return DTO_OK;
+            // the columns of the global variables follow the last knot's (evaluator.jl:123)
+            const long long p0 = h->jac_colptr[(size_t)a * P.z], p1 = b2 >= P.nK ? P.nnz_jac_local : h->jac_colptr[(size_t)b2 * P.z];
+            CUDA_TRY(h, cudaMemcpyAsync(jac + p0, h->djac + p0, sizeof(double) * (p1 - p0), cudaMemcpyDeviceToHost, st));
+            d2h += 8LL * (p1 - p0);
+            return DTO_OK;
+        };
+        if (!sparse_jac) return whole(ka, kb);
+        // knot 0 and the last knot whole; inner knots: every column minus its constant head, one strided copy
+        int rc = whole(ka, std::min(kb, 1));
         if (rc != DTO_OK) return rc;
-        if (jac) CUDA_TRY(h, cudaMemcpyAsync(jac, h->djac, sizeof(double) * B * P.nnz_jac_local, cudaMemcpyDeviceToHost, h->stream));
-        if (hess) CUDA_TRY(h, cudaMemcpyAsync(hess, h->dhess, sizeof(double) * B * P.nnz_hess_local, cudaMemcpyDeviceToHost, h->stream));
-        if (hess) d2h += 8LL * B * P.nnz_hess_local;
-        if (jac) d2h += 8LL * B * P.nnz_jac_local;
+        const int a = std::max(ka, 1), b2 = std::min(kb, P.nI);
+        if (a < b2) {
+            const long long Lc = 2LL * P.Dsum, sk = jskip;
+            const long long p0 = h->jac_colptr[(size_t)a * P.z] + sk;
+            CUDA_TRY(h, cudaMemcpy2DAsync(jac + p0, sizeof(double) * Lc, h->djac + p0, sizeof(double) * Lc, sizeof(double) * (Lc - sk),
+                                          (size_t)(b2 - a) * P.z, cudaMemcpyDeviceToHost, st));
+            d2h += 8LL * (Lc - sk) * (b2 - a) * P.z;
+        }
+        return whole(std::max(ka, P.nI), kb);
+    };
+    auto deliver_hess = [&](int ka, int kb, cudaStream_t st) -> int {
+        kb = std::min(kb, P.nOwn);
+        if (ka >= kb) return DTO_OK;
+        if (!sparse_hess) {
+            const long long p0 = hess_knot_base(P, ka), p1 = kb >= P.nOwn ? P.nnz_hess_local : hess_knot_base(P, kb);
+            CUDA_TRY(h, cudaMemcpyAsync(hess + p0, h->dhess + p0, sizeof(double) * (p1 - p0), cudaMemcpyDeviceToHost, st));
+            d2h += 8LL * (p1 - p0);
+            return DTO_OK;
+        }
+        // only the columns >= l0 of every knot of the range: one 2-D copy per run of equal knots
+        for (const HRun& r : h->hess_runs) {
+            const int a = std::max(r.k0, ka), b2 = std::min(r.k0 + r.cnt, kb);
+            if (a >= b2) continue;
+            const long long nc = hess_knot_has_cross(P, a) ? P.z : 0;
+            const long long region = nc * P.z + (long long)P.z * (P.z + 1) / 2;
+            const long long skip = (long long)r.l0 * nc + (long long)r.l0 * (r.l0 + 1) / 2;
+            if (region == skip) continue;
+            const long long p0 = hess_knot_base(P, a) + skip;
+            CUDA_TRY(h, cudaMemcpy2DAsync(hess + p0, sizeof(double) * region, h->dhess + p0, sizeof(double) * region,
+                                          sizeof(double) * (region - skip), (size_t)(b2 - a), cudaMemcpyDeviceToHost, st));
+            d2h += 8LL * (region - skip) * (b2 - a);
+        }
+        return DTO_OK;
+    };
+
+    FillGuard guard;
+    if (fill_h || fill_j) {
+        // host threads write the structural constants into the caller's buffers while the GPU computes
+        const dto_handle* hh = h;
+        double* hz = fill_h ? hess : nullptr;
+        double* jz = fill_j ? jac : nullptr;
+        h->zero_fill->launch([hh, hz, jz](int part, int parts) {
+            const DProb& Q = hh->P;
+            if (hz) {
+                const size_t n = hh->hess_zero_segs.size(), lo = n * part / parts, hi = n * (part + 1) / parts;
+                for (size_t i = lo; i < hi; ++i)
+                    memset(hz + hh->hess_zero_segs[i].first, 0, sizeof(double) * (size_t)hh->hess_zero_segs[i].second);
+            }
+            if (jz) {
+                // head of every column of knots 1..nI-1: [0 .. 1 (row l - x_off) .. 0]
+                const long long nk = Q.nI - 1, k_lo = 1 + nk * part / parts, k_hi = 1 + nk * (part + 1) / parts;
+                const int d1 = hh->jac_skip, xo = Q.in[0].x_off;
+                for (long long kl = k_lo; kl < k_hi; ++kl)
+                    for (int l = 0; l < Q.z; ++l) {
+                        double* c = jz + hh->jac_colptr[(size_t)kl * Q.z + l];
+                        memset(c, 0, sizeof(double) * (size_t)d1);
+                        if (l >= xo && l < xo + d1) c[l - xo] = 1.0;
+                    }
+            }
+        });
+        guard.z = h->zero_fill;  // joined on every exit path below
+    }
+
+    // Large sparse outputs that are computed by this call: cut the trajectory into a few knot ranges; the Jacobian columns
+    // and Hessian blocks of a finished range go out on the copy engine while the next range is being computed.
+    // (`jac` includes the registered array of a speculative delivery)
+    const long long out_bytes = 8LL * ((jac && comp_jac ? P.nnz_jac_local : 0) + (hess && comp_hess ? P.nnz_hess_local : 0));
+    const bool pipelined = !h->pipeline_fracs.empty() && out_bytes >= (8LL << 20) && P.nI >= 512 && range_capable(h) &&
+                           !(n_passes == 1 && passes[0].jets == DTO_JETS_USE);  // the adjoint-only pass is too short to be worth cutting
+    bool used_copy_stream = false;
+    int rc = DTO_OK;
+    // a resident Jacobian asked for (not computed here): right away, beside the computation
+    if (jac && !comp_jac) {
+        if (B == 1) {
+            used_copy_stream = true;
+            if ((rc = deliver_jac(0, P.nK, h->copy_stream)) != DTO_OK) return rc;
+        } else {
+            CUDA_TRY(h, cudaMemcpyAsync(jac, h->djac, sizeof(double) * B * P.nnz_jac_local, cudaMemcpyDeviceToHost, h->stream));
+            d2h += 8LL * B * P.nnz_jac_local;
+        }
+    }
+    if (!pipelined) {
+        for (int i = 0; i < n_passes; ++i)
+            if ((rc = eval_range(h, P, h->dZ, sigma, h->dmu, h->dg, h->djac, h->dhess, passes[i])) != DTO_OK) return rc;
+        eval_prologue(h, P, h->dZ, dJ, dgrad, h->dg, h->djac, fany);
+        CUDA_TRY(h, cudaGetLastError());
+        if (B == 1) {
+            cudaStream_t jst = h->stream;
+            if (spec_jac && comp_jac) {  // the speculative copy must not hold up this call's own outputs
+                CUDA_TRY(h, cudaEventRecord(h->chunk_events_at(0), h->stream));
+                CUDA_TRY(h, cudaStreamWaitEvent(h->copy_stream, h->chunk_events_at(0), 0));
+                jst = h->copy_stream;
+                used_copy_stream = true;
+            }
+            if (jac && comp_jac && (rc = deliver_jac(0, P.nK, jst)) != DTO_OK) return rc;
+            if (hess && (rc = deliver_hess(0, P.nOwn, h->stream)) != DTO_OK) return rc;
+        } else {
+            if (jac && comp_jac) CUDA_TRY(h, cudaMemcpyAsync(jac, h->djac, sizeof(double) * B * P.nnz_jac_local, cudaMemcpyDeviceToHost, h->stream));
+            if (hess) CUDA_TRY(h, cudaMemcpyAsync(hess, h->dhess, sizeof(double) * B * P.nnz_hess_local, cudaMemcpyDeviceToHost, h->stream));
+            if (hess) d2h += 8LL * B * P.nnz_hess_local;
+            if (jac && comp_jac) d2h += 8LL * B * P.nnz_jac_local;
+        }
     } else {
-        if (!h->copy_stream) CUDA_TRY(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        used_copy_stream = true;
         std::vector<int> bounds{0};
         for (double fr : h->pipeline_fracs) {
             const int k = (int)(fr * P.nI);
             if (k > bounds.back() && k < P.nI) bounds.push_back(k);
         }
         bounds.push_back(P.nK);
-        while (h->chunk_events.size() + 1 < bounds.size()) {
-            cudaEvent_t e;
-            CUDA_TRY(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-            h->chunk_events.push_back(e);
-        }
-        const bool sparse_hess = hess && !h->hess_runs.empty();
-        const bool sparse_jac = jac && h->jac_skip > 0;
-        if (sparse_hess || sparse_jac) {
-            // host threads write the structural constants into the caller's buffers while the GPU computes
-            const dto_handle* hh = h;
-            double* hz = sparse_hess ? hess : nullptr;
-            double* jz = sparse_jac ? jac : nullptr;
-            h->zero_fill->launch([hh, hz, jz](int part, int parts) {
-                const DProb& Q = hh->P;
-                if (hz) {
-                    const size_t n = hh->hess_zero_segs.size(), lo = n * part / parts, hi = n * (part + 1) / parts;
-                    for (size_t i = lo; i < hi; ++i)
-                        memset(hz + hh->hess_zero_segs[i].first, 0, sizeof(double) * (size_t)hh->hess_zero_segs[i].second);
-                }
-                if (jz) {
-                    // head of every column of knots 1..nI-1: [0 .. 1 (row l - x_off) .. 0]
-                    const long long nk = Q.nI - 1, k_lo = 1 + nk * part / parts, k_hi = 1 + nk * (part + 1) / parts;
-                    const int d1 = hh->jac_skip, xo = Q.in[0].x_off;
-                    for (long long kl = k_lo; kl < k_hi; ++kl)
-                        for (int l = 0; l < Q.z; ++l) {
-                            double* c = jz + hh->jac_colptr[(size_t)kl * Q.z + l];
-                            memset(c, 0, sizeof(double) * (size_t)d1);
-                            if (l >= xo && l < xo + d1) c[l - xo] = 1.0;
-                        }
-                }
-            });
-        }
-        eval_prologue(h, P, h->dZ, dJ, dgrad, dg, djac, f);  // knot-constraint entries land before any column leaves
+        const bool jac_now = jac && comp_jac, hess_now = hess && comp_hess;
+        eval_prologue(h, P, h->dZ, dJ, dgrad, h->dg, h->djac, fany);  // knot-constraint entries land before any column leaves
         DProb Pr = P;
         for (size_t c = 0; c + 1 < bounds.size(); ++c) {
             Pr.kc0 = bounds[c];
             Pr.kc1 = bounds[c + 1];
-            eval_range(h, Pr, h->dZ, sigma, h->dmu, dg, djac, dhess, f);
-            CUDA_TRY(h, cudaEventRecord(h->chunk_events[c], h->stream));
-            CUDA_TRY(h, cudaStreamWaitEvent(h->copy_stream, h->chunk_events[c], 0));
-            if (jac && !sparse_jac) {
-                // columns of knots [kc0, kc1): their own-interval rows were written by this range, the
-                // previous-interval rows of knot kc0 by the range before
-                const long long p0 = h->jac_colptr[(size_t)Pr.kc0 * P.z], p1 = h->jac_colptr[(size_t)Pr.kc1 * P.z];
-                CUDA_TRY(h, cudaMemcpyAsync(jac + p0, h->djac + p0, sizeof(double) * (p1 - p0), cudaMemcpyDeviceToHost, h->copy_stream));
-                d2h += 8LL * (p1 - p0);
+            for (int i = 0; i < n_passes; ++i)
+                if ((rc = eval_range(h, Pr, h->dZ, sigma, h->dmu, h->dg, h->djac, h->dhess, passes[i])) != DTO_OK) return rc;
+            cudaEvent_t ev = h->chunk_events_at(c);
+            if (!ev) {
+                h->err = "cudaEventCreate failed";
+                return DTO_ERR_CUDA;
             }
-            if (sparse_jac) {
-                // knot 0 and the last knot whole; inner knots: every column minus its constant head, one strided copy
-                auto whole = [&](int ka, int kb2) -> int {
-                    if (ka >= kb2) return DTO_OK;
-                    const long long p0 = h->jac_colptr[(size_t)ka * P.z], p1 = h->jac_colptr[(size_t)kb2 * P.z];
-                    CUDA_TRY(h, cudaMemcpyAsync(jac + p0, h->djac + p0, sizeof(double) * (p1 - p0), cudaMemcpyDeviceToHost, h->copy_stream));
-                    d2h += 8LL * (p1 - p0);
-                    return DTO_OK;
-                };
-                int rc = whole(Pr.kc0, std::min(Pr.kc1, 1));
-                if (rc != DTO_OK) return rc;
-                const int ka = std::max(Pr.kc0, 1), kb2 = std::min(Pr.kc1, P.nI);
-                if (ka < kb2) {
-                    const long long Lc = 2LL * P.Dsum, sk = h->jac_skip;
-                    const long long p0 = h->jac_colptr[(size_t)ka * P.z] + sk;
-                    CUDA_TRY(h, cudaMemcpy2DAsync(jac + p0, sizeof(double) * Lc, h->djac + p0, sizeof(double) * Lc, sizeof(double) * (Lc - sk),
-                                                  (size_t)(kb2 - ka) * P.z, cudaMemcpyDeviceToHost, h->copy_stream));
-                    d2h += 8LL * (Lc - sk) * (kb2 - ka) * P.z;
-                }
-                rc = whole(std::max(Pr.kc0, P.nI), Pr.kc1);
-                if (rc != DTO_OK) return rc;
-            }
-            if (hess && !sparse_hess) {
-                const long long p0 = hess_knot_base(P, Pr.kc0), p1 = hess_knot_base(P, std::min(Pr.kc1, P.nOwn));
-                CUDA_TRY(h, cudaMemcpyAsync(hess + p0, h->dhess + p0, sizeof(double) * (p1 - p0), cudaMemcpyDeviceToHost, h->copy_stream));
-                d2h += 8LL * (p1 - p0);
-            }
-            if (sparse_hess) {
-                // only the columns >= l0 of every knot of the range: one 2-D copy per run of equal knots
-                const int ka = Pr.kc0, kb2 = std::min(Pr.kc1, P.nOwn);
-                for (const HRun& r : h->hess_runs) {
-                    const int a = std::max(r.k0, ka), b2 = std::min(r.k0 + r.cnt, kb2);
-                    if (a >= b2) continue;
-                    const long long nc = hess_knot_has_cross(P, a) ? P.z : 0;
-                    const long long region = nc * P.z + (long long)P.z * (P.z + 1) / 2;
-                    const long long skip = (long long)r.l0 * nc + (long long)r.l0 * (r.l0 + 1) / 2;
-                    if (region == skip) continue;
-                    const long long p0 = hess_knot_base(P, a) + skip;
-                    CUDA_TRY(h, cudaMemcpy2DAsync(hess + p0, sizeof(double) * region, h->dhess + p0, sizeof(double) * region,
-                                                  sizeof(double) * (region - skip), (size_t)(b2 - a), cudaMemcpyDeviceToHost, h->copy_stream));
-                    d2h += 8LL * (region - skip) * (b2 - a);
-                }
-            }
+            CUDA_TRY(h, cudaEventRecord(ev, h->stream));
+            CUDA_TRY(h, cudaStreamWaitEvent(h->copy_stream, ev, 0));
+            // columns of knots [kc0, kc1): their own-interval rows were written by this range, the previous-interval rows
+            // of knot kc0 by the range before
+            if (jac_now && (rc = deliver_jac(Pr.kc0, Pr.kc1, h->copy_stream)) != DTO_OK) return rc;
+            if (hess_now && (rc = deliver_hess(Pr.kc0, Pr.kc1, h->copy_stream)) != DTO_OK) return rc;
         }
-        // everything is enqueued: the calling thread writes its share of the structural zeros while the GPU works
-        if (sparse_hess || sparse_jac) h->zero_fill->finish();
         CUDA_TRY(h, cudaGetLastError());
     }
     if (J) CUDA_TRY(h, cudaMemcpyAsync(J, h->dJ, sizeof(double) * B, cudaMemcpyDeviceToHost, h->stream));
     if (grad) CUDA_TRY(h, cudaMemcpyAsync(grad, h->dgrad, sizeof(double) * B * P.n_grad_local, cudaMemcpyDeviceToHost, h->stream));
     if (g) CUDA_TRY(h, cudaMemcpyAsync(g, h->dg, sizeof(double) * B * P.n_cons_local, cudaMemcpyDeviceToHost, h->stream));
+    // everything is enqueued: the calling thread writes its share of the structural zeros while the GPU works
+    if (guard.z) {
+        guard.z->finish();
+        guard.z = nullptr;
+    }
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-    if (pipelined) CUDA_TRY(h, cudaStreamSynchronize(h->copy_stream));
+    if (spec_jac) h->spec_jac_inflight = true;
+    else if (used_copy_stream || h->spec_jac_inflight) {
+        CUDA_TRY(h, cudaStreamSynchronize(h->copy_stream));
+        h->spec_jac_inflight = false;
+    }
     h->last_d2h_bytes = d2h;
+    return DTO_OK;
+}
+
+// One fused pass over one iterate (benchmark/benchmarks.jl:23-38 times the five callbacks on one iterate; a solver calls
+// them separately: see the single callbacks below).
+extern "C" int dto_eval_all(dto_handle* h, const double* Z, double sigma, const double* mu, double* J, double* grad, double* g,
+                            double* jac, double* hess) {
+    if (!h || !Z) return DTO_ERR_INVALID;
+    const DProb& P = h->P;
+    int rc = check_eval_args(h, mu, hess);
+    if (rc != DTO_OK) return rc;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    if ((rc = ensure_iterate(h, Z)) < 0) return rc;
+    // the fused pass recomputes what it is asked for and leaves the callbacks' cache empty (its Hessian pass overwrites
+    // the compact second derivatives with this call's mu)
+    h->have_obj = h->have_g = h->have_jac = h->have_jets = false;
+    if (hess) CUDA_TRY(h, cudaMemcpyAsync(h->dmu, mu, sizeof(double) * (size_t)P.batch * P.n_cons_local, cudaMemcpyHostToDevice, h->stream));
+    EvalFlags f{g != nullptr, jac != nullptr, hess != nullptr};
+    rc = eval_core(h, sigma, &f, 1, J || grad, J, grad, g, jac, hess);
+    if (rc == DTO_OK) {
+        h->have_obj = h->z_valid && (J || grad);
+        h->have_g = h->z_valid && g;
+        h->have_jac = h->z_valid && jac;
+    }
+    return rc;
+}
+
+// The five callbacks as a solver calls them: separately, usually on one iterate (f, grad f, g, jac g, then the Hessian
+// with the new multipliers).  The first callback that needs the interval kernels on a NEW iterate runs ONE mu-independent
+// pass (residual + Jacobian; the forward role also stores the second-order vectors of its jet); later callbacks on the
+// same iterate only copy, and the Hessian callback runs the adjoint role, contracts the stored jets with mu and assembles.
+static int eval_callback(dto_handle* h, const double* Z, double sigma, const double* mu, double* J, double* grad, double* g,
+                         double* jac, double* hess) {
+    if (!h || !Z) return DTO_ERR_INVALID;
+    const DProb& P = h->P;
+    int rc = check_eval_args(h, mu, hess);
+    if (rc != DTO_OK) return rc;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    if ((rc = ensure_iterate(h, Z)) < 0) return rc;
+    if (!h->z_valid) {  // cache off: every callback is its own pass
+        if (hess) CUDA_TRY(h, cudaMemcpyAsync(h->dmu, mu, sizeof(double) * (size_t)P.batch * P.n_cons_local, cudaMemcpyHostToDevice, h->stream));
+        EvalFlags f{g != nullptr, jac != nullptr, hess != nullptr};
+        return eval_core(h, sigma, &f, 1, J || grad, J, grad, g, jac, hess);
+    }
+    if (jac && jac == h->reg_jac && h->have_jac && h->spec_jac_done && !J && !grad && !g && !hess) {
+        // the Jacobian of this iterate went to the registered array while the constraint callback computed it
+        if (h->spec_jac_inflight) {
+            CUDA_TRY(h, cudaStreamSynchronize(h->copy_stream));
+            h->spec_jac_inflight = false;
+        }
+        h->last_d2h_bytes = 0;
+        return DTO_OK;
+    }
+    EvalFlags passes[2];
+    int np = 0;
+    const bool comp_obj = (J || grad) && !h->have_obj;
+    const bool eager = h->cache_mode == 1;
+    const bool use_jets = hess && h->jets_ok;
+    bool need_g = g && !h->have_g, need_jac = jac && !h->have_jac;
+    const bool need_jets = use_jets && !h->have_jets;
+    if (need_g || need_jac || need_jets) {
+        EvalFlags f1{need_g, need_jac, false};
+        if (eager || need_jets) {
+            f1.want_g = f1.want_jac = true;
+            f1.jets = h->jets_ok ? DTO_JETS_STORE : DTO_JETS_NONE;
+        }
+        passes[np++] = f1;
+    }
+    if (hess) {
+        CUDA_TRY(h, cudaMemcpyAsync(h->dmu, mu, sizeof(double) * (size_t)P.batch * P.n_cons_local, cudaMemcpyHostToDevice, h->stream));
+        EvalFlags f2{false, false, true};
+        f2.jets = use_jets ? DTO_JETS_USE : DTO_JETS_NONE;
+        passes[np++] = f2;
+    }
+    // a Jacobian that is computed without being asked for goes to the registered array on the side
+    const bool spec = !jac && h->reg_jac != nullptr && np > 0 && passes[0].want_jac && P.batch == 1;
+    rc = eval_core(h, sigma, passes, np, comp_obj, J, grad, g, jac, hess, spec);
+    if (rc != DTO_OK) {
+        h->have_obj = h->have_g = h->have_jac = h->have_jets = false;
+        return rc;
+    }
+    if (spec) h->spec_jac_done = true;
+    if (jac && jac == h->reg_jac) h->spec_jac_done = true;
+    if (comp_obj) h->have_obj = true;
+    for (int i = 0; i < np; ++i) {
+        h->have_g |= passes[i].want_g;
+        h->have_jac |= passes[i].want_jac;
+        h->have_jets |= passes[i].jets == DTO_JETS_STORE;
+    }
     return DTO_OK;
 }
 
 extern "C" int dto_eval_objective(dto_handle* h, const double* Z, double* J) {
     if (!J) return DTO_ERR_INVALID;
-    return dto_eval_all(h, Z, 0.0, nullptr, J, nullptr, nullptr, nullptr, nullptr);
+    return eval_callback(h, Z, 0.0, nullptr, J, nullptr, nullptr, nullptr, nullptr);
 }
 extern "C" int dto_eval_gradient(dto_handle* h, const double* Z, double* grad) {
     if (!grad) return DTO_ERR_INVALID;
-    return dto_eval_all(h, Z, 0.0, nullptr, nullptr, grad, nullptr, nullptr, nullptr);
+    return eval_callback(h, Z, 0.0, nullptr, nullptr, grad, nullptr, nullptr, nullptr);
 }
 extern "C" int dto_eval_constraint(dto_handle* h, const double* Z, double* g) {
     if (!g) return DTO_ERR_INVALID;
-    return dto_eval_all(h, Z, 0.0, nullptr, nullptr, nullptr, g, nullptr, nullptr);
+    return eval_callback(h, Z, 0.0, nullptr, nullptr, nullptr, g, nullptr, nullptr);
 }
 extern "C" int dto_eval_jacobian(dto_handle* h, const double* Z, double* vals) {
     if (!vals) return DTO_ERR_INVALID;
-    return dto_eval_all(h, Z, 0.0, nullptr, nullptr, nullptr, nullptr, vals, nullptr);
+    return eval_callback(h, Z, 0.0, nullptr, nullptr, nullptr, nullptr, vals, nullptr);
 }
 extern "C" int dto_eval_hessian(dto_handle* h, const double* Z, double sigma, const double* mu, double* vals) {
     if (!vals) return DTO_ERR_INVALID;
-    return dto_eval_all(h, Z, sigma, mu, nullptr, nullptr, nullptr, nullptr, vals);
+    return eval_callback(h, Z, sigma, mu, nullptr, nullptr, nullptr, nullptr, vals);
+}
+
+// ---- registered outputs ------------------------------------------------------------------------------
+static void unpin(bool& pinned, double*& p) {
+    if (pinned && p) {
+        cudaHostUnregister(p);
+        cudaGetLastError();
+    }
+    pinned = false;
+    p = nullptr;
+}
+
+extern "C" int dto_unregister_outputs(dto_handle* h) {
+    if (!h) return DTO_ERR_INVALID;
+    cudaSetDevice(h->device);
+    if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
+    h->spec_jac_inflight = h->spec_jac_done = false;
+    unpin(h->reg_jac_pinned, h->reg_jac);
+    unpin(h->reg_hess_pinned, h->reg_hess);
+    h->reg_jac_sparse = h->reg_hess_sparse = false;
+    return DTO_OK;
+}
+
+extern "C" int dto_register_outputs(dto_handle* h, double* jac_vals, double* hess_vals) {
+    if (!h) return DTO_ERR_INVALID;
+    const DProb& P = h->P;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    dto_unregister_outputs(h);
+    if (P.batch != 1) {
+        h->err = "dto_register_outputs: one problem per handle (batch == 1)";
+        return DTO_ERR_UNSUPPORTED;
+    }
+    auto pin = [&](double* p, long long n, bool& pinned) {
+        const cudaError_t e = cudaHostRegister(p, sizeof(double) * (size_t)n, cudaHostRegisterPortable);
+        pinned = e == cudaSuccess;
+        cudaGetLastError();  // already page-locked by the caller (or not lockable): the copies still work
+    };
+    if (jac_vals) {
+        pin(jac_vals, P.nnz_jac_local, h->reg_jac_pinned);
+        h->reg_jac = jac_vals;
+        if (h->jac_skip_ok > 0) {
+            // head of every column of the inner knots: the previous-interval block of the first integrator, [0 .. 1 .. 0]
+            const int d1 = h->jac_skip_ok, xo = P.in[0].x_off;
+            for (long long kl = 1; kl < P.nI; ++kl)
+                for (int l = 0; l < P.z; ++l) {
+                    double* c = jac_vals + h->jac_colptr[(size_t)kl * P.z + l];
+                    memset(c, 0, sizeof(double) * (size_t)d1);
+                    if (l >= xo && l < xo + d1) c[l - xo] = 1.0;
+                }
+            h->reg_jac_sparse = true;
+        }
+    }
+    if (hess_vals && h->eval_hessian) {
+        pin(hess_vals, P.nnz_hess_local, h->reg_hess_pinned);
+        h->reg_hess = hess_vals;
+        if (!h->hess_runs.empty()) {
+            for (const auto& sgm : h->hess_zero_segs) memset(hess_vals + sgm.first, 0, sizeof(double) * (size_t)sgm.second);
+            h->reg_hess_sparse = true;
+        }
+    }
+    return DTO_OK;
 }
 
 // Products straight from the series for problems made of persistent-variant bilinear integrators, derivative
@@ -1395,7 +1679,10 @@ static int jac_product(dto_handle* h, const double* Z, const double* w, double* 
     }
     const size_t nw = transpose ? (size_t)P.n_cons_local : (size_t)P.n_vars_local;
     const size_t ny = transpose ? (size_t)P.n_vars_local : (size_t)P.n_cons_local;
-    CUDA_TRY(h, cudaMemcpyAsync(h->dZ, Z, sizeof(double) * B * P.n_vars_local, cudaMemcpyHostToDevice, h->stream));
+    {
+        const int rc = ensure_iterate(h, Z);
+        if (rc < 0) return rc;
+    }
     CUDA_TRY(h, cudaMemcpyAsync(h->dw, w, sizeof(double) * B * nw, cudaMemcpyHostToDevice, h->stream));
     bool done = false;
     if (matrix_free_capable(h)) {
@@ -1419,8 +1706,11 @@ static int jac_product(dto_handle* h, const double* Z, const double* w, double* 
                 return DTO_ERR_ALLOC;
             }
         }
-        int rc = run_eval(h, h->dZ, 0.0, nullptr, nullptr, nullptr, nullptr, h->djac, nullptr);
-        if (rc != DTO_OK) return rc;
+        if (!h->have_jac) {
+            int rc = run_eval(h, h->dZ, 0.0, nullptr, nullptr, nullptr, nullptr, h->djac, nullptr);
+            if (rc != DTO_OK) return rc;
+            h->have_jac = h->z_valid;
+        }
         launch_jac_product(P, h->djac, h->d_rows0, h->d_cols0, h->dw, h->dy, transpose, h->stream, &h->launches);
     }
     CUDA_TRY(h, cudaGetLastError());

@@ -292,13 +292,19 @@ class Evaluator:
         self._out(H, self.batch * self.nnz_hessian)
         _lib.check(self._lib.dto_eval_hessian(self._h, Z.ctypes.data, float(sigma), mu.ctypes.data, H.ctypes.data), self._h)
 
+    def _w(self, w, n):
+        w = _f64(w).reshape(-1)
+        if w.size != n:
+            raise ValueError(f"w has {w.size} entries, expected {n}")
+        return w
+
     def eval_constraint_jacobian_product(self, y, x, w):
-        x, w = self._z(x), _f64(w).reshape(-1)
+        x, w = self._z(x), self._w(w, self.batch * self.n_vars)
         self._out(y, self.batch * self.n_constraints)
         _lib.check(self._lib.dto_eval_jacobian_product(self._h, x.ctypes.data, w.ctypes.data, y.ctypes.data), self._h)
 
     def eval_constraint_jacobian_transpose_product(self, y, x, w):
-        x, w = self._z(x), _f64(w).reshape(-1)
+        x, w = self._z(x), self._w(w, self.batch * self.n_constraints)
         self._out(y, self.batch * self.n_vars)
         _lib.check(self._lib.dto_eval_jacobian_transpose_product(self._h, x.ctypes.data, w.ctypes.data, y.ctypes.data), self._h)
 
@@ -307,10 +313,41 @@ class Evaluator:
         Z = self._z(Z)
         mu_p = None
         if mu is not None:
-            mu = _f64(mu).reshape(-1)
+            mu = self._w(mu, self.batch * self.n_constraints)
             mu_p = mu.ctypes.data
+        n_grad = self.shard_layout.z_end - self.shard_layout.z_begin + self.global_dim
+        for out, n in ((J, 1), (grad, n_grad), (g, self.n_constraints), (jac, self.nnz_jacobian), (hess, self.nnz_hessian)):
+            if out is not None:
+                self._out(out, self.batch * n)
         p = lambda a: None if a is None else a.ctypes.data
         _lib.check(self._lib.dto_eval_all(self._h, Z.ctypes.data, float(sigma), mu_p, p(J), p(grad), p(g), p(jac), p(hess)), self._h)
+
+    def upload(self, Z):
+        """Make ``Z`` the resident iterate without evaluating anything (returns after the copy has completed)."""
+        Z = self._z(Z)
+        _lib.check(self._lib.dto_upload(self._h, Z.ctypes.data), self._h)
+
+    def cache_stats(self):
+        """(hits, misses) of the iterate cache since creation."""
+        a, b = C.c_int64(), C.c_int64()
+        _lib.check(self._lib.dto_cache_stats(self._h, C.byref(a), C.byref(b)), self._h)
+        return a.value, b.value
+
+    def register_outputs(self, jac=None, hess=None):
+        """``dto_register_outputs``: page-lock the solver's own value arrays and write their structural constants once;
+        callbacks that are handed these arrays afterwards move only the value-dependent entries.  The arrays must
+        stay alive and must only be read by the caller until ``unregister_outputs`` / ``close``."""
+        if jac is not None:
+            self._out(jac, self.nnz_jacobian)
+        if hess is not None:
+            self._out(hess, self.nnz_hessian)
+        self._registered = (jac, hess)  # keep them alive
+        p = lambda a: None if a is None else a.ctypes.data
+        _lib.check(self._lib.dto_register_outputs(self._h, p(jac), p(hess)), self._h)
+
+    def unregister_outputs(self):
+        _lib.check(self._lib.dto_unregister_outputs(self._h), self._h)
+        self._registered = None
 
     def eval_all_dev(self, dZ, sigma=1.0, dmu=0, dJ=0, dgrad=0, dg=0, djac=0, dhess=0):
         """Device-pointer variant: arguments are raw device addresses (e.g. ``tensor.data_ptr()``);

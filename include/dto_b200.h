@@ -56,7 +56,7 @@
 extern "C" {
 #endif
 
-#define DTO_B200_ABI_VERSION 2
+#define DTO_B200_ABI_VERSION 3
 
 typedef struct dto_handle dto_handle;
 
@@ -229,6 +229,29 @@ int dto_eval_jacobian_transpose_product(dto_handle* h, const double* Z, const do
 /* One fused pass over one iterate: any output pointer may be NULL to skip that quantity. */
 int dto_eval_all(dto_handle* h, const double* Z, double sigma, const double* mu, double* J, double* grad,
                  double* g, double* jac_vals, double* hess_vals);
+
+/* Iterate cache.  The reference copies Z into its cached trajectory in EVERY callback (src/solvers/evaluator.jl:474-482) and
+ * the solvers call the five callbacks separately on one iterate (src/solvers/ipopt_solver/solver.jl:85).  The handle
+ * keeps a page-locked copy of the iterate that is resident on the device: a callback whose Z equals it (memcmp) skips the
+ * upload and re-uses what earlier callbacks computed.  The first callback that needs the interval kernels on a NEW
+ * iterate runs one mu-independent pass (residual + Jacobian + the second-order vectors of the forward jet); the
+ * Hessian callback then runs only the adjoint recurrences, contracts the stored vectors with mu and assembles.
+ * Results are bit-identical to dto_eval_all.  DTO_B200_ITERATE_CACHE=0 disables the cache, =lazy computes only what each
+ * callback asks for.  dto_upload makes Z the resident iterate without evaluating anything (and returns after the
+ * copy has completed: on knot-range shards, the point after which a neighbour may read this rank's knots). */
+int dto_upload(dto_handle* h, const double* Z);
+int dto_cache_stats(const dto_handle* h, int64_t* hits, int64_t* misses);
+/* Optional: tell the handle where the solver keeps its Jacobian / Hessian value arrays (either may be NULL; batch == 1).
+ * The arrays are page-locked (cudaHostRegister) and their structural constants -- Hessian entries no term of the
+ * problem can touch, the identity/zero head of the Jacobian columns (d r_{k-1}/d z_k of a bilinear or derivative
+ * integrator) -- are written ONCE, here.  Later callbacks that are handed these pointers move only the value-dependent
+ * entries (c2: 27 of 72 MB), with no host threads involved, and the Jacobian a constraint callback computes on a new
+ * iterate starts leaving for the registered array at once (dto_eval_jacobian on the same iterate then only joins the
+ * copy).  Contract: between dto_register_outputs and dto_unregister_outputs / dto_destroy the caller only READS the arrays
+ * (what Ipopt and MadNLP do with the value arrays of MOI.eval_constraint_jacobian / eval_hessian_lagrangian), and the
+ * Jacobian array may be written by any callback. */
+int dto_register_outputs(dto_handle* h, double* jac_vals, double* hess_vals);
+int dto_unregister_outputs(dto_handle* h);
 
 /* ---- device-pointer callbacks: enqueue on dto_stream(h), no host synchronisation ---- */
 int dto_eval_all_dev(dto_handle* h, const double* dZ, double sigma, const double* dmu, double* dJ, double* dgrad,

@@ -16,7 +16,7 @@ using NamedTrajectories
 using DirectTrajOpt
 
 const LIB = get(ENV, "DTO_B200_LIB", joinpath(@__DIR__, "..", "directtrajopt.jl_b200", "lib", "libdto_b200.so"))
-const ABI_VERSION = Cint(2)
+const ABI_VERSION = Cint(3)
 
 # ---- mirror of the C descriptor structs (include/dto_b200.h) -------------------------------------
 struct IntegratorDesc
