@@ -97,9 +97,11 @@ SYMBOLS = [
     ("dto_eval_all_dev", C.c_int, [_H, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("dto_violation_dev", C.c_int, [_H, C.c_void_p, C.c_void_p]),
     ("dto_synchronize", C.c_int, [_H]),
-    ("dto_halo_export", C.c_int, [_H, C.c_void_p]),
-    ("dto_halo_import", C.c_int, [_H, C.c_void_p]),
-    ("dto_halo_attach", C.c_int, [_H, _H]),
+    ("dto_shard_export", C.c_int, [_H, C.c_void_p]),
+    ("dto_shard_link", C.c_int, [_H, C.c_int, C.c_int, C.c_void_p]),
+    ("dto_shard_link_local", C.c_int, [C.POINTER(_H), C.c_int]),
+    ("dto_upload_dev", C.c_int, [_H, C.c_void_p]),
+    ("dto_allreduce_scalars_dev", C.c_int, [_H, C.c_void_p, C.c_void_p]),
     ("dto_local_Z", C.c_void_p, [_H]),
     ("dto_launch_count", C.c_int64, [_H]),
     ("dto_last_download_bytes", C.c_int64, [_H]),

@@ -119,7 +119,15 @@ struct dto_handle {
            *dpartials = nullptr, *dviol = nullptr, *dw = nullptr, *dy = nullptr;
     int* d_row_is_eq = nullptr;
     long long *d_rows0 = nullptr, *d_cols0 = nullptr;
-    void* ipc_peer = nullptr;
+    // ---- links between knot-range shards (shard_link.cu): exchange windows of this shard and of its peers
+    XWin* xwin = nullptr;                 // own window (device memory, exportable through CUDA IPC)
+    XWin* peer_win[DTO_MAX_RANKS] = {};   // every rank's window as seen from this device (own entry = xwin)
+    bool peer_ipc[DTO_MAX_RANKS] = {};    // mapping opened with cudaIpcOpenMemHandle (closed in dto_destroy)
+    XWin** d_peer_win = nullptr;          // device copy of peer_win
+    int link_rank = -1, link_world = 0;   // < 0: not linked
+    unsigned long long epoch = 0;         // iterates uploaded since the link was made
+    unsigned long long waited_epoch = 0;  // the halo of this iterate has been waited for
+    unsigned long long scal_seq = 0;
     long long launches = 0;
     long long last_d2h_bytes = 0;
     // host-pointer path: outputs leave over PCIe while later knot ranges are still being computed
@@ -203,7 +211,8 @@ extern "C" void dto_destroy(dto_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     dto_unregister_outputs(h);
-    if (h->ipc_peer) cudaIpcCloseMemHandle(h->ipc_peer);
+    for (int r = 0; r < DTO_MAX_RANKS; ++r)
+        if (h->peer_ipc[r] && h->peer_win[r]) cudaIpcCloseMemHandle(h->peer_win[r]);
     for (auto& e : h->ev_pool) {
         cudaEventDestroy(e.first);
         cudaEventDestroy(e.second);
@@ -1192,11 +1201,15 @@ static int check_eval_args(dto_handle* h, const double* dmu, const double* dhess
     return DTO_OK;
 }
 
+static int prepare_halo(dto_handle* h);
+static int check_link_errors(dto_handle* h);
+
 static int run_eval(dto_handle* h, const double* dZ, double sigma, const double* dmu, double* dJ, double* dgrad, double* dg,
                     double* djac, double* dhess) {
-    const DProb& P = h->P;
     int rc = check_eval_args(h, dmu, dhess);
     if (rc != DTO_OK) return rc;
+    if ((rc = prepare_halo(h)) != DTO_OK) return rc;
+    const DProb& P = h->P;
     EvalFlags f{dg != nullptr, djac != nullptr, dhess != nullptr};
     rc = eval_range(h, P, dZ, sigma, dmu, dg, djac, dhess, f);
     if (rc != DTO_OK) return rc;
@@ -1226,15 +1239,16 @@ extern "C" int dto_eval_all_dev(dto_handle* h, const double* dZ, double sigma, c
 extern "C" int dto_synchronize(dto_handle* h) {
     if (!h) return DTO_ERR_INVALID;
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-    return DTO_OK;
+    return check_link_errors(h);
 }
 
 // ---- iterate cache -----------------------------------------------------------------------------------
 // 1: Z is the resident iterate (nothing moved); 0: a new iterate was uploaded (every cached quantity dropped); < 0: error
-static int ensure_iterate(dto_handle* h, const double* Z) {
+static int publish_iterate(dto_handle* h);
+static int ensure_iterate(dto_handle* h, const double* Z, bool force = false) {
     const DProb& P = h->P;
     const size_t bytes = sizeof(double) * (size_t)P.batch * (size_t)P.n_vars_local;
-    if (h->cache_mode && h->z_valid && memcmp(h->hZpin, Z, bytes) == 0) {
+    if (!force && h->cache_mode && h->z_valid && memcmp(h->hZpin, Z, bytes) == 0) {
         ++h->cache_hits;
         return 1;
     }
@@ -1253,7 +1267,8 @@ static int ensure_iterate(dto_handle* h, const double* Z) {
     } else {
         CUDA_TRY(h, cudaMemcpyAsync(h->dZ, Z, bytes, cudaMemcpyHostToDevice, h->stream));
     }
-    return 0;
+    const int rc = publish_iterate(h);
+    return rc < 0 ? rc : 0;
 }
 
 extern "C" int dto_cache_stats(const dto_handle* h, int64_t* hits, int64_t* misses) {
@@ -1266,10 +1281,22 @@ extern "C" int dto_cache_stats(const dto_handle* h, int64_t* hits, int64_t* miss
 extern "C" int dto_upload(dto_handle* h, const double* Z) {
     if (!h || !Z) return DTO_ERR_INVALID;
     CUDA_TRY(h, cudaSetDevice(h->device));
-    const int rc = ensure_iterate(h, Z);
+    // linked shards count iterates in lockstep: every dto_upload is a new iterate on every rank, changed or not
+    const int rc = ensure_iterate(h, Z, h->link_rank >= 0);
     if (rc < 0) return rc;
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     return DTO_OK;
+}
+
+extern "C" int dto_upload_dev(dto_handle* h, const double* dZ) {
+    if (!h || !dZ) return DTO_ERR_INVALID;
+    const DProb& P = h->P;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    h->have_obj = h->have_g = h->have_jac = h->have_jets = false;
+    h->z_valid = false;  // the host copy no longer describes the resident iterate
+    if (dZ != h->dZ)
+        CUDA_TRY(h, cudaMemcpyAsync(h->dZ, dZ, sizeof(double) * (size_t)P.batch * (size_t)P.n_vars_local, cudaMemcpyDeviceToDevice, h->stream));
+    return publish_iterate(h);
 }
 
 // joins the zero-fill workers on every exit path (they write into the caller's buffer)
@@ -1287,6 +1314,10 @@ struct FillGuard {
 // with that array only joins the copy).
 static int eval_core(dto_handle* h, double sigma, const EvalFlags* passes, int n_passes, bool comp_obj, double* J, double* grad,
                      double* g, double* jac, double* hess, bool spec_jac = false) {
+    {
+        const int rc0 = prepare_halo(h);
+        if (rc0 != DTO_OK) return rc0;
+    }
     const DProb& P = h->P;
     const size_t B = (size_t)P.batch;
     bool comp_jac = false, comp_hess = false, comp_g = false;
@@ -1473,7 +1504,7 @@ static int eval_core(dto_handle* h, double sigma, const EvalFlags* passes, int n
         h->spec_jac_inflight = false;
     }
     h->last_d2h_bytes = d2h;
-    return DTO_OK;
+    return check_link_errors(h);
 }
 
 // One fused pass over one iterate (benchmark/benchmarks.jl:23-38 times the five callbacks on one iterate; a solver calls
@@ -1733,51 +1764,169 @@ extern "C" int dto_violation_dev(dto_handle* h, const double* dg, double* dviol)
     return DTO_OK;
 }
 
-// ---- halo over peer memory ---------------------------------------------------------------------------
+// ---- links between knot-range shards ---------------------------------------------------------------------
 extern "C" double* dto_local_Z(dto_handle* h) { return h ? h->dZ : nullptr; }
 
-extern "C" int dto_halo_export(dto_handle* h, void* out64) {
+static size_t xwin_bytes(const dto_handle* h) { return sizeof(XWin) + sizeof(double) * 2 * (size_t)h->P.z; }
+
+static int ensure_xwin(dto_handle* h) {
+    if (h->xwin) return DTO_OK;
+    void* p = nullptr;
+    CUDA_TRY(h, cudaMalloc(&p, xwin_bytes(h)));  // its own allocation: the IPC handle exposes nothing else
+    h->allocs.push_back(p);
+    CUDA_TRY(h, cudaMemset(p, 0, xwin_bytes(h)));
+    h->xwin = (XWin*)p;
+    return DTO_OK;
+}
+
+extern "C" int dto_shard_export(dto_handle* h, void* out64) {
     if (!h || !out64) return DTO_ERR_INVALID;
-    cudaIpcMemHandle_t mh;
     CUDA_TRY(h, cudaSetDevice(h->device));
-    CUDA_TRY(h, cudaIpcGetMemHandle(&mh, h->dZ));
+    int rc = ensure_xwin(h);
+    if (rc != DTO_OK) return rc;
+    cudaIpcMemHandle_t mh;
+    CUDA_TRY(h, cudaIpcGetMemHandle(&mh, h->xwin));
     static_assert(sizeof(mh) == 64, "cudaIpcMemHandle_t is 64 bytes");
     memcpy(out64, &mh, 64);
     return DTO_OK;
 }
 
-extern "C" int dto_halo_import(dto_handle* h, const void* in64) {
-    if (!h || !in64) return DTO_ERR_INVALID;
-    if (h->P.nK == h->P.nOwn) {
-        h->err = "the last shard has no right halo";
-        return DTO_ERR_INVALID;
+static int finish_link(dto_handle* h, int rank, int world) {
+    h->link_rank = rank;
+    h->link_world = world;
+    h->epoch = h->waited_epoch = h->scal_seq = 0;
+    h->z_valid = false;  // the next callback uploads (and publishes) whatever it is given
+    if (!h->d_peer_win) {
+        void* p = nullptr;
+        CUDA_TRY(h, cudaMalloc(&p, sizeof(XWin*) * DTO_MAX_RANKS));
+        h->allocs.push_back(p);
+        h->d_peer_win = (XWin**)p;
     }
-    cudaIpcMemHandle_t mh;
-    memcpy(&mh, in64, 64);
-    CUDA_TRY(h, cudaSetDevice(h->device));
-    void* p = nullptr;
-    CUDA_TRY(h, cudaIpcOpenMemHandle(&p, mh, cudaIpcMemLazyEnablePeerAccess));
-    h->ipc_peer = p;
-    h->P.halo = (const double*)p;  // the neighbour's first owned knot
+    CUDA_TRY(h, cudaMemcpy(h->d_peer_win, h->peer_win, sizeof(XWin*) * DTO_MAX_RANKS, cudaMemcpyHostToDevice));
     return DTO_OK;
 }
 
-extern "C" int dto_halo_attach(dto_handle* h, dto_handle* right) {
-    if (!h || !right) return DTO_ERR_INVALID;
-    if (h->P.nK == h->P.nOwn) {
-        h->err = "the last shard has no right halo";
+static void drop_links(dto_handle* h) {
+    for (int r = 0; r < DTO_MAX_RANKS; ++r) {
+        if (h->peer_ipc[r] && h->peer_win[r]) cudaIpcCloseMemHandle(h->peer_win[r]);
+        h->peer_ipc[r] = false;
+        h->peer_win[r] = nullptr;
+    }
+    cudaGetLastError();
+    h->link_rank = -1;
+    h->link_world = 0;
+    h->P.halo = nullptr;
+}
+
+extern "C" int dto_shard_link(dto_handle* h, int rank, int world, const void* handles64) {
+    if (!h || !handles64 || world < 1 || world > DTO_MAX_RANKS || rank < 0 || rank >= world) return DTO_ERR_INVALID;
+    if (!h->sharded) {
+        h->err = "dto_shard_link: the handle is not a knot-range shard";
         return DTO_ERR_INVALID;
     }
-    if (right->device != h->device) {
-        CUDA_TRY(h, cudaSetDevice(h->device));
-        cudaError_t e = cudaDeviceEnablePeerAccess(right->device, 0);
-        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
-            h->err = std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e);
-            return DTO_ERR_CUDA;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    int rc = ensure_xwin(h);
+    if (rc != DTO_OK) return rc;
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    drop_links(h);  // a second link closes the first mappings
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) {
+            h->peer_win[r] = h->xwin;
+            continue;
         }
-        cudaGetLastError();
+        cudaIpcMemHandle_t mh;
+        memcpy(&mh, (const char*)handles64 + 64 * (size_t)r, 64);
+        void* p = nullptr;
+        CUDA_TRY(h, cudaIpcOpenMemHandle(&p, mh, cudaIpcMemLazyEnablePeerAccess));
+        h->peer_win[r] = (XWin*)p;
+        h->peer_ipc[r] = true;
     }
-    h->P.halo = right->dZ;
+    return finish_link(h, rank, world);
+}
+
+extern "C" int dto_shard_link_local(dto_handle* const* hs, int world) {
+    if (!hs || world < 1 || world > DTO_MAX_RANKS) return DTO_ERR_INVALID;
+    for (int r = 0; r < world; ++r) {
+        if (!hs[r] || !hs[r]->sharded) return DTO_ERR_INVALID;
+        cudaSetDevice(hs[r]->device);
+        int rc = ensure_xwin(hs[r]);
+        if (rc != DTO_OK) return rc;
+        cudaStreamSynchronize(hs[r]->stream);
+        drop_links(hs[r]);
+    }
+    for (int r = 0; r < world; ++r) {
+        dto_handle* h = hs[r];
+        CUDA_TRY(h, cudaSetDevice(h->device));
+        for (int p = 0; p < world; ++p) {
+            h->peer_win[p] = hs[p]->xwin;
+            if (hs[p]->device != h->device) {
+                cudaError_t e = cudaDeviceEnablePeerAccess(hs[p]->device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+                    h->err = std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e);
+                    return DTO_ERR_CUDA;
+                }
+                cudaGetLastError();
+            }
+        }
+        int rc = finish_link(h, r, world);
+        if (rc != DTO_OK) return rc;
+    }
+    return DTO_OK;
+}
+
+// A new iterate is on its way into dZ (stream order): acknowledge the right neighbour's previous knot, push this shard's
+// first knot to the left neighbour.
+static int publish_iterate(dto_handle* h) {
+    if (h->link_rank < 0) return DTO_OK;
+    ++h->epoch;
+    XWin* left = h->link_rank > 0 ? h->peer_win[h->link_rank - 1] : nullptr;
+    XWin* right = h->link_rank + 1 < h->link_world ? h->peer_win[h->link_rank + 1] : nullptr;
+    if (left || right) launch_shard_publish(h->xwin, left, right, h->dZ, h->P.z, h->epoch, h->stream, &h->launches);
+    CUDA_TRY(h, cudaGetLastError());
+    return DTO_OK;
+}
+
+// Before the first kernel of an iterate that reads the halo knot: wait (on the device) until the right neighbour's push
+// of this iterate has landed in this shard's window, and point the kernels at that slot.
+static int prepare_halo(dto_handle* h) {
+    if (h->link_rank < 0 || h->link_rank + 1 >= h->link_world) return DTO_OK;
+    if (h->epoch == 0) {
+        h->err = "linked shard: upload an iterate first (dto_upload / dto_upload_dev / any host-pointer callback)";
+        return DTO_ERR_INVALID;
+    }
+    if (h->waited_epoch != h->epoch) {
+        launch_shard_wait(h->xwin, h->epoch, h->stream, &h->launches);
+        h->waited_epoch = h->epoch;
+    }
+    h->P.halo = h->xwin->halo + (size_t)(h->epoch & 1) * h->P.z;  // address arithmetic on a device pointer (no dereference)
+    return DTO_OK;
+}
+
+static int check_link_errors(dto_handle* h) {
+    if (h->link_rank < 0) return DTO_OK;
+    unsigned long long e = 0;
+    CUDA_TRY(h, cudaMemcpyAsync(&e, &h->xwin->err, sizeof(e), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (e != 0) {
+        h->err = e == 1 ? "shard link: the left neighbour never released the halo slot (timeout)"
+                        : (e == 2 ? "shard link: the right neighbour's knot of this iterate never arrived (timeout); every rank must upload every iterate"
+                                  : "shard link: scalar exchange timed out");
+        cudaMemsetAsync(&h->xwin->err, 0, sizeof(e), h->stream);
+        return DTO_ERR_CUDA;
+    }
+    return DTO_OK;
+}
+
+extern "C" int dto_allreduce_scalars_dev(dto_handle* h, double* dJ, double* dviol) {
+    if (!h || !dJ || !dviol) return DTO_ERR_INVALID;
+    if (h->link_rank < 0) {
+        h->err = "dto_allreduce_scalars_dev: the shard is not linked";
+        return DTO_ERR_INVALID;
+    }
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    ++h->scal_seq;
+    launch_scalar_exchange(h->xwin, h->d_peer_win, h->link_rank, h->link_world, h->scal_seq, dJ, dviol, h->stream, &h->launches);
+    CUDA_TRY(h, cudaGetLastError());
     return DTO_OK;
 }
 

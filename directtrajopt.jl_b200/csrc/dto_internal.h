@@ -138,6 +138,23 @@ __host__ __device__ inline long long hess_knot_base(const DProb& P, int kl) {
 }
 __host__ __device__ inline bool hess_knot_has_cross(const DProb& P, int kl) { return kl > 0 || P.first_has_cross; }
 
+// Exchange window of a knot-range shard: device memory its neighbours map (CUDA IPC, or directly in one process).  See
+// shard_link.cu for the protocol.
+#define DTO_MAX_RANKS 16
+struct XWin {
+    unsigned long long halo_epoch;  // written by the RIGHT neighbour: halo[epoch & 1] holds its first knot of iterate `epoch`
+    unsigned long long ack;         // written by the LEFT neighbour: it no longer reads this shard's knot of iterates <= ack
+    unsigned long long err;         // a wait timed out (1: acknowledgement, 2: halo, 3: scalar exchange)
+    unsigned long long pad;
+    double scal[2][DTO_MAX_RANKS][4];  // [seq & 1][rank] = {objective, violation, seq (as u64), -}
+    double halo[2];                    // really [2][z]: allocated with the window
+};
+void launch_shard_publish(XWin* own, XWin* left, XWin* right, const double* first_knot, int z, unsigned long long epoch, cudaStream_t st,
+                          long long* launches);
+void launch_shard_wait(XWin* own, unsigned long long epoch, cudaStream_t st, long long* launches);
+void launch_scalar_exchange(XWin* own, XWin* const* peers, int rank, int world, unsigned long long seq, double* J, double* viol,
+                            cudaStream_t st, long long* launches);
+
 // variants of the bilinear kernel
 enum { DTO_VAR_GENERIC = 0, DTO_VAR_DMMA = 1, DTO_VAR_PERSISTENT = 2, DTO_VAR_OCTET = 3 };
 

@@ -395,16 +395,33 @@ class Evaluator:
         _lib.check(self._lib.dto_shard_maps(self._h, i64(r), i64(j), i64(hh)), self._h)
         return r, j, hh
 
-    def halo_export(self):
+    def shard_export(self):
+        """64-byte CUDA-IPC handle of this shard's exchange window."""
         buf = C.create_string_buffer(64)
-        _lib.check(self._lib.dto_halo_export(self._h, buf), self._h)
+        _lib.check(self._lib.dto_shard_export(self._h, buf), self._h)
         return buf.raw
 
-    def halo_import(self, raw):
-        _lib.check(self._lib.dto_halo_import(self._h, C.create_string_buffer(raw, 64)), self._h)
+    def shard_link(self, rank, world, handles):
+        """Map the exchange windows of all ``world`` shards (``handles``: their ``shard_export()`` in rank order)."""
+        raw = b"".join(bytes(x) for x in handles)
+        if len(raw) != 64 * world:
+            raise ValueError("need one 64-byte handle per rank")
+        _lib.check(self._lib.dto_shard_link(self._h, int(rank), int(world), C.create_string_buffer(raw, len(raw))), self._h)
 
-    def halo_attach(self, right):
-        _lib.check(self._lib.dto_halo_attach(self._h, right._h), self._h)
+    @staticmethod
+    def shard_link_local(evaluators):
+        """Link several shards that live in this process (rank order)."""
+        lib = _lib.load()
+        arr = (C.c_void_p * len(evaluators))(*[e._h for e in evaluators])
+        rc = lib.dto_shard_link_local(arr, len(evaluators))
+        if rc != _lib.DTO_OK:
+            raise _lib.DtoError(rc, "; ".join(lib.dto_last_error(e._h).decode() for e in evaluators))
+
+    def upload_dev(self, dZ):
+        _lib.check(self._lib.dto_upload_dev(self._h, dZ), self._h)
+
+    def allreduce_scalars_dev(self, dJ, dviol):
+        _lib.check(self._lib.dto_allreduce_scalars_dev(self._h, dJ, dviol), self._h)
 
     @property
     def local_Z_ptr(self):

@@ -3,13 +3,16 @@
   partitioning A (independent problems, BASELINE config c5): ``split_batch`` gives each rank a contiguous
       block of problems; no communication on the data path at all.
   partitioning B (one long trajectory, config c4): ``ShardedEvaluator`` gives rank r the contiguous knot
-      range ``knot_ranges(N, world)[r]``.  Every interval needs knots k and k+1, so a rank reads ONE halo
-      knot (z doubles) from its right neighbour -- straight out of the neighbour's HBM through a CUDA-IPC
-      mapped peer pointer inside the evaluation kernels (NVLink P2P; no copy kernel, no collective).
-      The only collective is the all-reduce of two scalars: the objective (sum) and the constraint
-      violation (max), over ``torch.distributed`` (NCCL on GPUs, gloo in the CPU tests).
+      range ``knot_ranges(N, world)[r]``.  Every interval needs knots k and k+1, so a rank needs ONE halo
+      knot (z doubles) of its right neighbour.  Linked shards (``peer_halo``) move it over NVLink P2P inside the
+      evaluation stream: after uploading an iterate a rank pushes its first knot into the left neighbour's exchange
+      window (CUDA-IPC mapped HBM) and flags it; the neighbour's kernels wait for the flag on the device
+      (csrc/shard_link.cu).  Protocol: every rank calls ``upload`` (or ``upload_dev``) once per iterate.
+      The two scalars every rank needs -- objective (sum) and constraint violation (max) -- go through the same
+      windows (``allreduce_scalars_dev``: one small kernel per rank, no collective library) or, as the
+      fallback / in the CPU tests, through ``torch.distributed`` (NCCL on GPUs, gloo on CPU).
 
-``torch.distributed`` is plumbing only: handle exchange, barrier and the two-scalar reduction.
+``torch.distributed`` is plumbing only: handle exchange, barrier and the fallback reduction.
 """
 from __future__ import annotations
 
@@ -66,17 +69,23 @@ class ShardedEvaluator:
         self.z_end = self.k1 * self.z
         self.z_halo_end = min(self.k1 + 1, prob.trajectory.N) * self.z
         self.peer_halo = False
-        if peer_halo and world > 1 and dist is not None and hasattr(self.local, "halo_export"):
-            # every rank publishes the IPC handle of its resident Z; rank r maps rank r+1's
+        if peer_halo and world > 1 and dist is not None and hasattr(self.local, "shard_export"):
+            # every rank publishes the IPC handle of its exchange window and maps everybody else's
             handles = [None] * world
-            dist.all_gather_object(handles, self.local.halo_export())
-            if rank + 1 < world:
-                self.local.halo_import(handles[rank + 1])
+            dist.all_gather_object(handles, self.local.shard_export())
+            self.local.shard_link(rank, world, handles)
             self.peer_halo = True
 
     def local_slice(self, Z):
         """This rank's input slice of the global primal vector (owned knots + the one-knot right halo)."""
         return np.ascontiguousarray(Z[self.z_begin:self.z_halo_end])
+
+    def upload(self, Z):
+        """Make this rank's slice of the global ``Z`` the resident iterate (and push the first knot to the left
+        neighbour when the shards are linked).  Every rank calls this once per iterate."""
+        Zloc = self.local_slice(Z)
+        self.local.upload(Zloc)
+        return Zloc
 
     def reduce_scalars(self, J_local: float, viol_local: float, device=None):
         """All-reduce (objective: sum, violation: max) -- the only collective of the sharded path."""

@@ -260,15 +260,30 @@ int dto_eval_all_dev(dto_handle* h, const double* dZ, double sigma, const double
 int dto_violation_dev(dto_handle* h, const double* dg, double* dviol);
 int dto_synchronize(dto_handle* h);
 
-/* ---- knot-range sharding: one-knot halo over NVLink peer memory ---- */
-/* 64-byte cudaIpcMemHandle_t of this shard's device Z buffer (knots k0..k1+1). */
-int dto_halo_export(dto_handle* h, void* ipc_handle_64B);
-/* Map the RIGHT neighbour's Z buffer; afterwards the evaluation kernels read knot k1+1 straight from
- * the peer's HBM (ld.global on a mapped peer pointer) instead of from the local halo slot. */
-int dto_halo_import(dto_handle* h, const void* ipc_handle_64B);
-/* in-process variant (several handles, one process): peer = right neighbour's handle */
-int dto_halo_attach(dto_handle* h, dto_handle* right_neighbour);
-/* device pointer of this shard's local Z buffer ([z_begin, z_halo_end) of the global Z) */
+/* ---- knot-range sharding: one-knot halo and the two scalars over NVLink peer memory ----
+ * An unlinked shard reads its right halo knot from the caller's own slice of Z ([z_begin, z_halo_end)): no cross-rank
+ * traffic, no ordering requirement.  LINKED shards (one per rank of a single box; CUDA IPC across processes) exchange
+ * through windows in each other's HBM instead, inside the evaluation stream:
+ *   - after uploading iterate e a shard pushes its first knot into the left neighbour's window and publishes e there;
+ *     the left neighbour's kernels of iterate e wait for that flag on the device and read the knot from the window.  The
+ *     reader acknowledges when it moves on, so a rank runs at most one iterate ahead of the neighbour reading its knot.
+ *   - dto_allreduce_scalars_dev: objective (sum) and violation (max) of all shards with one kernel per rank that
+ *     stores into every peer's window and spins on its own (rank-ordered sum: identical bits on every rank; no NCCL).
+ * Protocol: EVERY rank uploads EVERY iterate exactly once, with dto_upload (host Z slice) or dto_upload_dev (device);
+ * callbacks are then called with that same Z (iterate-cache hits) or through the _dev entry points on dto_local_Z.
+ * A wait that sees no progress for 20 s fails the evaluation with DTO_ERR_CUDA instead of hanging. */
+/* 64-byte cudaIpcMemHandle_t of this shard's exchange window */
+int dto_shard_export(dto_handle* h, void* ipc_handle_64B);
+/* map the windows of all `world` shards (handles64 = world x 64 bytes in rank order; the own entry is ignored) */
+int dto_shard_link(dto_handle* h, int rank, int world, const void* handles64);
+/* several shards in ONE process (tests, one-process multi-device drivers): handles in rank order */
+int dto_shard_link_local(dto_handle* const* handles, int world);
+/* a new iterate that already lives on the device: copies it into the resident buffer (unless dZ == dto_local_Z) and
+ * publishes it to the neighbours; enqueues on dto_stream(h) without synchronising */
+int dto_upload_dev(dto_handle* h, const double* dZ);
+/* in place: dJ[0] <- sum over shards, dviol[0] <- max over shards; enqueues on dto_stream(h) */
+int dto_allreduce_scalars_dev(dto_handle* h, double* dJ, double* dviol);
+/* device pointer of this shard's resident Z buffer ([z_begin, z_halo_end) of the global Z) */
 double* dto_local_Z(dto_handle* h);
 
 /* ---- instrumentation ---- */

@@ -1,6 +1,6 @@
 """Multi-problem batches (BASELINE config c5) and knot-range shards with a one-knot halo (config c4),
-exercised on ONE GPU: several handles in one process, the halo read through dto_halo_attach (the same
-code path as a mapped peer pointer)."""
+exercised on ONE GPU: several handles in one process, linked with dto_shard_link_local (the same exchange-window
+protocol as CUDA-IPC mapped peers: halo pushed into the neighbour's window, scalars exchanged through the windows)."""
 import numpy as np
 import pytest
 
@@ -86,8 +86,7 @@ def test_knot_range_shards_reassemble_the_whole_problem(builder, cuts, peer_halo
     Jw, gradw, gw, jacw, hessw = all_outputs(whole, Z, sigma, mu)
     shards = [dto.Evaluator(prob, shard=c) for c in cuts]
     if peer_halo:
-        for left, right in zip(shards[:-1], shards[1:]):
-            left.halo_attach(right)
+        dto.Evaluator.shard_link_local(shards)
     J = 0.0
     grad = np.full_like(gradw, np.nan)
     g, jac, hess = np.full_like(gw, np.nan), np.full_like(jacw, np.nan), np.full_like(hessw, np.nan)
@@ -100,7 +99,7 @@ def test_knot_range_shards_reassemble_the_whole_problem(builder, cuts, peer_halo
         Zloc = Z[L.z_begin:L.z_halo_end].copy()
         if peer_halo and L.z_halo_end > L.z_end:
             Zloc[L.z_end - L.z_begin:] = np.nan  # the local halo slot must not be read
-        sh.eval_objective(Zloc)  # uploads the shard's Z
+        sh.upload(Zloc)  # uploads the shard's Z (linked shards: pushes the first knot into the left neighbour's window)
     for sh in shards:
         L = sh.shard_layout
         Zloc = Z[L.z_begin:L.z_halo_end].copy()
@@ -138,3 +137,58 @@ def test_violation_reduction():
     ev.synchronize()
     assert dv.item() == ref
     ev.close()
+
+
+def test_linked_shards_follow_a_changing_iterate():
+    """Solver-loop pattern on linked shards: every iterate is uploaded once on every shard, the halo knot of THAT iterate
+    reaches the left neighbour through the exchange window (the local halo slot holds NaN), the five callbacks run on
+    cache hits, and objective / violation are reduced through the windows.  Several iterates, so the double-buffered
+    halo slots and the acknowledgements are exercised."""
+    import torch
+
+    prob = pt.scaled_problem(N=26, state_dim=8, n_controls=2, generator_scale=0.4)
+    cuts = [(1, 7), (8, 8), (9, 20), (21, 26)]
+    rng = np.random.default_rng(8)
+    whole = dto.Evaluator(prob)
+    shards = [dto.Evaluator(prob, shard=c) for c in cuts]
+    dto.Evaluator.shard_link_local(shards)
+    Z0 = prob.trajectory.datavec
+    lo, _ = whole.constraint_bounds()
+    for it in range(5):
+        Z = Z0 + 0.02 * rng.standard_normal(Z0.size)
+        mu = rng.random(whole.n_constraints)
+        Jw, gradw, gw, jacw, hessw = all_outputs(whole, Z, 1.1, mu)
+        locs = []
+        for sh in shards:  # phase 1: every shard uploads the iterate
+            L = sh.shard_layout
+            Zloc = Z[L.z_begin:L.z_halo_end].copy()
+            if L.z_halo_end > L.z_end:
+                Zloc[L.z_end - L.z_begin:] = np.nan
+            sh.upload(Zloc)
+            locs.append(Zloc)
+        g, jac, hess = np.full_like(gw, np.nan), np.full_like(jacw, np.nan), np.full_like(hessw, np.nan)
+        dJs, dVs = [], []
+        for sh, Zloc in zip(shards, locs):  # phase 2: the five callbacks, separately
+            rows, jpos, hpos = sh.shard_maps()
+            gl, jl, hl = np.empty(sh.n_constraints), np.empty(sh.nnz_jacobian), np.empty(sh.nnz_hessian)
+            J = sh.eval_objective(Zloc)
+            sh.eval_constraint(gl, Zloc)
+            sh.eval_constraint_jacobian(jl, Zloc)
+            sh.eval_hessian_lagrangian(hl, Zloc, 1.1, mu[rows])
+            g[rows], jac[jpos], hess[hpos] = gl, jl, hl
+            l2, _ = sh.constraint_bounds()
+            viol = float(np.where(l2 == 0, np.abs(gl), np.maximum(gl, 0)).max()) if gl.size else 0.0
+            dJs.append(torch.tensor([J], dtype=torch.float64, device="cuda"))
+            dVs.append(torch.tensor([viol], dtype=torch.float64, device="cuda"))
+        assert np.array_equal(g, gw) and np.array_equal(jac, jacw) and np.array_equal(hess, hessw), it
+        torch.cuda.synchronize()
+        for sh, dJ, dV in zip(shards, dJs, dVs):  # the scalar exchange: all ranks enqueue, then all synchronise
+            sh.allreduce_scalars_dev(dJ.data_ptr(), dV.data_ptr())
+        for sh in shards:
+            sh.synchronize()
+        vw = np.where(lo == 0, np.abs(gw), np.maximum(gw, 0)).max()
+        tot = [float(t.item()) for t in dJs]
+        assert all(t == tot[0] for t in tot) and abs(tot[0] - Jw[0]) <= 1e-13 * max(1.0, abs(Jw[0]))
+        assert all(float(v.item()) == vw for v in dVs)
+    for e in shards + [whole]:
+        e.close()

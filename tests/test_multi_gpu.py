@@ -1,6 +1,7 @@
-"""Two-process NCCL run of the knot-range sharding on two GPUs of one box: the halo knot is read from the
-right neighbour's HBM through a CUDA-IPC mapped pointer, the scalars are all-reduced over NCCL, and the
-reassembled outputs equal the single-GPU evaluation bit for bit.  Skipped on boxes with fewer than 2 GPUs
+"""Two-process run of the knot-range sharding on two GPUs of one box: the halo knot of every iterate reaches the left
+neighbour through a CUDA-IPC mapped exchange window (pushed over NVLink, flagged, waited for on the device), the
+scalars are reduced both through the windows and over NCCL, and the reassembled outputs equal the single-GPU
+evaluation bit for bit, for several iterates in a row.  Skipped on boxes with fewer than 2 GPUs
 (the same logic runs single-GPU in test_batch_shard_gpu.py and on CPU in test_sharding_gloo.py)."""
 import os
 import socket
@@ -38,20 +39,29 @@ def _worker(rank, world, port, q):
     rows, jpos, hpos = ev.shard_maps()
     mu_all = np.random.default_rng(1).random(int(rows.max()) + 1 if rank == world - 1 else 10**6)[: 10**6]
     mu_all = np.random.default_rng(1).random(2 * 40 * 16 + 40 * 2 + 10)
-    Zloc = sh.local_slice(Z)
-    if sh.peer_halo and sh.z_halo_end > sh.z_end:
-        Zloc = Zloc.copy()
-        Zloc[sh.z_end - sh.z_begin:] = np.nan  # must come from the peer, not from the local halo slot
-    ev.eval_objective(Zloc)  # make the shard's Z resident
-    dist.barrier()
-    J = np.empty(1)
-    grad = np.empty(sh.z_end - sh.z_begin)
-    g, jac, hess = np.empty(ev.n_constraints), np.empty(ev.nnz_jacobian), np.empty(ev.nnz_hessian)
-    ev.eval_all(Zloc, 1.2, mu_all[rows], J, grad, g, jac, hess)
-    lo, _ = ev.constraint_bounds()
-    viol = float(np.where(lo == 0, np.abs(g), np.maximum(g, 0)).max())
-    Jt, vt = sh.reduce_scalars(float(J[0]), viol, device=torch.device("cuda", rank))
-    q.put((rank, rows, jpos, hpos, sh.z_begin, sh.z_end, grad, g, jac, hess, Jt, vt))
+    res = []
+    for it in range(3):  # three iterates: nothing but the exchange windows orders the ranks between upload and evaluation
+        Zi = Z + 0.01 * it
+        Zloc = sh.local_slice(Zi)
+        if sh.peer_halo and sh.z_halo_end > sh.z_end:
+            Zloc = Zloc.copy()
+            Zloc[sh.z_end - sh.z_begin:] = np.nan  # must come from the peer, not from the local halo slot
+        ev.upload(Zloc)
+        J = np.empty(1)
+        grad = np.empty(sh.z_end - sh.z_begin)
+        g, jac, hess = np.empty(ev.n_constraints), np.empty(ev.nnz_jacobian), np.empty(ev.nnz_hessian)
+        ev.eval_all(Zloc, 1.2, mu_all[rows], J, grad, g, jac, hess)
+        lo, _ = ev.constraint_bounds()
+        viol = float(np.where(lo == 0, np.abs(g), np.maximum(g, 0)).max())
+        Jt, vt = sh.reduce_scalars(float(J[0]), viol, device=torch.device("cuda", rank))
+        dJ = torch.tensor([float(J[0])], dtype=torch.float64, device=torch.device("cuda", rank))
+        dV = torch.tensor([viol], dtype=torch.float64, device=torch.device("cuda", rank))
+        torch.cuda.synchronize()
+        ev.allreduce_scalars_dev(dJ.data_ptr(), dV.data_ptr())
+        ev.synchronize()
+        assert abs(dJ.item() - Jt) <= 1e-13 * max(1.0, abs(Jt)) and dV.item() == vt
+        res.append((grad, g, jac, hess, Jt, vt))
+    q.put((rank, rows, jpos, hpos, sh.z_begin, sh.z_end, res))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -80,17 +90,19 @@ def test_two_gpu_knot_shards_with_ipc_halo():
     whole = dto.Evaluator(prob, device=0)
     mu_all = np.random.default_rng(1).random(2 * 40 * 16 + 40 * 2 + 10)
     mu = mu_all[: whole.n_constraints]
-    J = np.empty(1)
-    grad, g = np.empty(whole.n_vars), np.empty(whole.n_constraints)
-    jac, hess = np.empty(whole.nnz_jacobian), np.empty(whole.nnz_hessian)
-    whole.eval_all(Z, 1.2, mu, J, grad, g, jac, hess)
-    grad2, g2, jac2, hess2 = [np.full_like(a, np.nan) for a in (grad, g, jac, hess)]
-    for rank, rows, jpos, hpos, zb, ze, gr, gg, jj, hh, Jt, vt in res:
-        grad2[zb:ze], g2[rows], jac2[jpos], hess2[hpos] = gr, gg, jj, hh
-        assert abs(Jt - J[0]) <= 1e-12 * max(1, abs(J[0]))
-        lo, _ = whole.constraint_bounds()
-        assert vt == np.where(lo == 0, np.abs(g), np.maximum(g, 0)).max()
-    assert np.array_equal(grad2, grad) and np.array_equal(g2, g) and np.array_equal(jac2, jac) and np.array_equal(hess2, hess)
+    for it in range(3):
+        J = np.empty(1)
+        grad, g = np.empty(whole.n_vars), np.empty(whole.n_constraints)
+        jac, hess = np.empty(whole.nnz_jacobian), np.empty(whole.nnz_hessian)
+        whole.eval_all(Z + 0.01 * it, 1.2, mu, J, grad, g, jac, hess)
+        grad2, g2, jac2, hess2 = [np.full_like(a, np.nan) for a in (grad, g, jac, hess)]
+        for rank, rows, jpos, hpos, zb, ze, per_it in res:
+            gr, gg, jj, hh, Jt, vt = per_it[it]
+            grad2[zb:ze], g2[rows], jac2[jpos], hess2[hpos] = gr, gg, jj, hh
+            assert abs(Jt - J[0]) <= 1e-12 * max(1, abs(J[0]))
+            lo, _ = whole.constraint_bounds()
+            assert vt == np.where(lo == 0, np.abs(g), np.maximum(g, 0)).max()
+        assert np.array_equal(grad2, grad) and np.array_equal(g2, g) and np.array_equal(jac2, jac) and np.array_equal(hess2, hess)
 
 
 def test_one_process_two_devices():
