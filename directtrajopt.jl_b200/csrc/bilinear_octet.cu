@@ -190,7 +190,9 @@ __global__ void __launch_bounds__(NT == 1 ? 256 : 128)
             return id < nItems;
         }
     };
-    const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    // CTA-minor numbering of the warps: the octets of a partial last round spread over all SMs (a few warps each, running
+    // at their latency bound) instead of filling the first SMs (12 500 intervals per rank on eight GPUs are 1.32 rounds)
+    const long long warp0 = (long long)(threadIdx.x >> 5) * gridDim.x + blockIdx.x;
     const long long nWarps = (long long)gridDim.x * (blockDim.x >> 5);
 
     for (long long oct = warp0; oct < nOct; oct += nWarps) {

@@ -360,6 +360,30 @@ extern "C" int dto_create(const dto_problem_desc* d, dto_handle** out) {
             I.D = dev_upload(h, s.D, nn * s.n_carrier);
             I.omega_d = dev_upload(h, s.omega_d, s.n_carrier);
             I.phi_d = dev_upload(h, s.phi_d, s.n_carrier);
+            {
+                // 1-norms that bound ||G(u, t)||_1 for the per-interval macro-step count (tdb_item_steps)
+                auto norm1 = [&](const double* M) {
+                    double best = 0.0;
+                    for (int c = 0; c < s.x_dim; ++c) {
+                        double sum = 0.0;
+                        for (int r = 0; r < s.x_dim; ++r) sum += fabs(M[(size_t)c * s.x_dim + r]);
+                        best = std::max(best, sum);
+                    }
+                    return best;
+                };
+                std::vector<double> bn((size_t)std::max(s.u_dim, 1), 0.0);
+                I.tdb_gnorm = norm1(s.G);
+                I.tdb_wmax = 0.0;
+                for (int i = 0; i < s.u_dim; ++i) {
+                    bn[i] = norm1(s.A + (size_t)i * nn) + norm1(s.B + (size_t)i * nn);
+                    I.tdb_wmax = std::max(I.tdb_wmax, fabs(s.omega[i]));
+                }
+                for (int j = 0; j < s.n_carrier; ++j) {
+                    I.tdb_gnorm += norm1(s.D + (size_t)j * nn);
+                    I.tdb_wmax = std::max(I.tdb_wmax, fabs(s.omega_d[j]));
+                }
+                I.tdb_bnorm = dev_upload(h, bn.data(), bn.size());
+            }
             if (s.x_dim % 8 == 0 && s.x_dim <= 64) {
                 // swizzled row-major copies for the tensor-core variant (layout of dmma_tiles.cuh)
                 const int nd = s.x_dim;

@@ -19,7 +19,10 @@ struct DInt {
     int kind, x_off, n, u_off, m, t_off, order, n_carrier;
     int doff;           // sum of x_dim of the integrators before this one
     int hs_stride;      // doubles of compact Hessian scratch per interval
-    int steps;          // tdbilinear RK steps
+    int steps;          // tdbilinear: minimum number of macro steps per interval (the kernels raise it per interval, tdb_item_steps)
+    double tdb_gnorm;   // tdbilinear: ||G0||_1 + sum_j ||D_j||_1
+    double tdb_wmax;    // tdbilinear: largest carrier frequency |w_i|, |wd_j|
+    const double* tdb_bnorm;  // tdbilinear: [m] ||A_i||_1 + ||B_i||_1
     int variant;        // kernel variant chosen on the host
     long long row_off;  // local row of this integrator's first residual
     long long G_stride;
@@ -112,6 +115,23 @@ struct DProb {
     DObj ob[DTO_MAX_OBJ];
     DCon co[DTO_MAX_CON];
 };
+
+// Macro steps of one tdbilinear interval.  The extrapolation scheme (8 columns of the modified midpoint rule, order 16) is
+// accurate to ~1e-13 per macro step while theta = |dt| (||G(u, .)||_1 bound + carrier frequency) stays below 1: the error of
+// a macro step of size theta behaves like theta^17 / prod_j (2j)^2 ~ theta^17 1e-14.  The reference controls its error by
+// adaptive Tsit5 steps (time_dependent_bilinear_integrator.jl:117-127); here the step count follows the iterate.
+// Same arithmetic in every kernel (role CTAs of one interval must agree).
+__device__ inline int tdb_item_steps(const DInt& I, const double* zk, const double* zk1, int dt_off) {
+    double g = I.tdb_gnorm;
+    for (int i = 0; i < I.m; ++i) {
+        const double u0 = fabs(zk[I.u_off + i]), u1 = I.order == 1 ? fabs(zk1[I.u_off + i]) : u0;
+        g += fmax(u0, u1) * I.tdb_bnorm[i];
+    }
+    const double theta = fabs(zk[dt_off]) * (g + I.tdb_wmax);
+    int s = I.steps;
+    if (theta > (double)s && theta < 1e8) s = (int)ceil(theta);  // NaN / absurd iterates keep the minimum
+    return s < 256 ? s : 256;
+}
 
 // Jacobian position helpers (local numbering) --------------------------------------------------
 // column of local knot kl (0-based), component l: [I1 prev | I1 own | I2 prev | I2 own | ... | constraints]

@@ -209,7 +209,7 @@ __device__ void rhs(int role, const Ctx& C, const Scal& S, const Tables& T, cons
 
 __global__ void __launch_bounds__(kThreads) tdb_kernel(DProb P, int ii, const double* __restrict__ Z, const double* __restrict__ mu,
                                                        double* __restrict__ g, double* __restrict__ jac, int want_jac, int want_hess,
-                                                       int K, int steps) {
+                                                       int K) {
     extern __shared__ double sm[];
     const DInt& I = P.in[ii];
     const int n = I.n, m = I.m, z = P.z, tid = threadIdx.x, nt = blockDim.x;
@@ -219,6 +219,7 @@ __global__ void __launch_bounds__(kThreads) tdb_kernel(DProb P, int ii, const do
     const double* zk = Z + (long long)b * P.n_vars_local + (long long)kl * z;
     const double* zk1 = zk + z;
     if (P.halo != nullptr && kl + 1 == P.nK - 1) zk1 = P.halo;
+    const int steps = tdb_item_steps(I, zk, zk1, P.dt_off);
 
     Ctx C;
     C.n = n;
@@ -411,8 +412,7 @@ void launch_tdb(const DProb& P, int ii, const double* Z, const double* mu, doubl
     }
     const int K = 8;
     dim3 grid((unsigned)(P.nI * P.batch), 1 + (f.want_jac ? 1 : 0) + (f.want_hess ? 1 : 0));
-    tdb_kernel<<<grid, kThreads, smem, st>>>(P, ii, Z, mu, f.want_g ? g : nullptr, jac, f.want_jac ? 1 : 0, f.want_hess ? 1 : 0, K,
-                                            I.steps);
+    tdb_kernel<<<grid, kThreads, smem, st>>>(P, ii, Z, mu, f.want_g ? g : nullptr, jac, f.want_jac ? 1 : 0, f.want_hess ? 1 : 0, K);
     ++*launches;
 }
 

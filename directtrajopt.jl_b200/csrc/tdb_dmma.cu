@@ -289,7 +289,7 @@ __device__ __forceinline__ void assemble_generators(double* Gf, double* Ga, cons
 template <int NT, int MAXW>
 __global__ void __launch_bounds__(MAXW * 32, 1)
     tdb_dmma_kernel(DProb P, int ii, const double* __restrict__ Z, const double* __restrict__ mu, double* __restrict__ g,
-                    double* __restrict__ jac, int want_jac, int want_hess, int K, int steps, int TF, int TE, int TA, int split, int nbs,
+                    double* __restrict__ jac, int want_jac, int want_hess, int K, int TF, int TE, int TA, int split, int nbs,
                     double* __restrict__ scratch) {
     extern __shared__ __align__(16) double sm[];
     constexpr int n = 8 * NT, nn = n * n, FR = NT * 2 * 32;  // FR: doubles of one tile in per-lane fragment order
@@ -387,6 +387,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
     const double* zk = Z + (long long)b * P.n_vars_local + (long long)kl * z;
     const double* zk1 = zk + z;
     if (P.halo != nullptr && kl + 1 == P.nK - 1) zk1 = P.halo;
+    const int steps = tdb_item_steps(I, zk, zk1, P.dt_off);  // macro steps of THIS interval
     __syncthreads();  // the previous item's tables and scalars are dead
     const long long mu_off = (long long)b * P.n_cons_local + I.row_off + (long long)kl * n;
 
@@ -765,7 +766,7 @@ struct NodeIter {
 
 template <int NT>
 __global__ void __launch_bounds__(8 * 32, 1)
-    tdb_exp_kernel(DProb P, int ii, const double* __restrict__ Z, double* __restrict__ jac, int K, int steps, int TE, int nbs,
+    tdb_exp_kernel(DProb P, int ii, const double* __restrict__ Z, double* __restrict__ jac, int K, int TE, int nbs,
                    double* __restrict__ scratch) {
     extern __shared__ __align__(16) double sm[];
     constexpr int n = 8 * NT, nn = n * n, FR = NT * 2 * 32;
@@ -813,6 +814,7 @@ __global__ void __launch_bounds__(8 * 32, 1)
         const double* zk1 = zk + z;
         if (P.halo != nullptr && kl + 1 == P.nK - 1) zk1 = P.halo;
         const double dts = zk[P.dt_off];
+        const int steps = tdb_item_steps(I, zk, zk1, P.dt_off);  // the same count as the forward/adjoint CTA of this interval
         __syncthreads();  // previous item done with both generators and the scalars
         if (active) {
 #pragma unroll
@@ -972,16 +974,16 @@ void launch_nt_w(const DProb& P, int ii, const double* Z, const double* mu, doub
     const int ctas = std::min(P.nI * P.batch, I.tdb_scratch_ctas / 2);  // persistent: one CTA per SM
     if (!pl.split) {
         kern<<<ctas, pl.warps * 32, pl.smem, st>>>(P, ii, Z, mu, f.want_g ? g : nullptr, jac, f.want_jac ? 1 : 0, f.want_hess ? 1 : 0, 8,
-                                                   I.steps, pl.TF, pl.TE, pl.TA, 0, pl.nbs, I.tdb_scratch);
+                                                   pl.TF, pl.TE, pl.TA, 0, pl.nbs, I.tdb_scratch);
         return;
     }
     // split interval: forward + adjoint tiles in one kernel, the propagator tiles in the double-buffered one
     kern<<<ctas, std::min(MAXW, std::max(pl.TF + pl.TA + 3, 4)) * 32, pl.smem, st>>>(P, ii, Z, mu, f.want_g ? g : nullptr, jac, f.want_jac ? 1 : 0,
-                                                                    f.want_hess ? 1 : 0, 8, I.steps, pl.TF, 0, pl.TA, 0, pl.nbs, I.tdb_scratch);
+                                                                    f.want_hess ? 1 : 0, 8, pl.TF, 0, pl.TA, 0, pl.nbs, I.tdb_scratch);
     const int n = I.n, nbasis = 2 * I.m + I.n_carrier;
     const size_t fixed = (2 * (size_t)n * n + 2 * sizeof(Scal) / sizeof(double) + 12) * sizeof(double);
     const int nbs = (int)std::min<size_t>(nbasis, (226 * 1024 - fixed) / ((size_t)n * n * sizeof(double)));
-    tdb_exp_kernel<NT><<<ctas, std::max(pl.TE, 4) * 32, fixed + (size_t)nbs * n * n * sizeof(double), st>>>(P, ii, Z, jac, 8, I.steps, pl.TE, nbs,
+    tdb_exp_kernel<NT><<<ctas, std::max(pl.TE, 4) * 32, fixed + (size_t)nbs * n * n * sizeof(double), st>>>(P, ii, Z, jac, 8, pl.TE, nbs,
                                                                                                        I.tdb_scratch);
 }
 

@@ -107,3 +107,39 @@ def test_trajectory_layout_is_knot_major():
     assert Z.size == traj.dim * traj.N
     assert np.array_equal(Z[traj.dim : 2 * traj.dim], traj.data[:, 1])
     assert traj[2].timestep == traj.data[traj.components["dt"].start, 1]
+
+
+def _build_c_smoke(tmp_path):
+    import shutil
+    import subprocess
+
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    lib_dir = os.path.join(ROOT, "directtrajopt.jl_b200", "lib")
+    exe = str(tmp_path / "c_abi_smoke")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "c_abi_smoke.c"),
+                    "-L", lib_dir, "-ldto_b200", "-lm", f"-Wl,-rpath,{lib_dir}", "-o", exe], check=True)
+    return exe
+
+
+def test_plain_c_consumer_links_and_fails_loudly_without_a_device(tmp_path):
+    """tests/c_abi_smoke.c: a C99 program builds the descriptor by hand and calls the ABI -- no Python, no C++.  Without a
+    CUDA device dto_create must fail with DTO_ERR_CUDA (exit code 77: there is no CPU fallback); with one, the closed-form
+    checks must pass (exit code 0)."""
+    import subprocess
+
+    import torch
+
+    exe = _build_c_smoke(tmp_path)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == (0 if torch.cuda.is_available() else 77), r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+def test_plain_c_consumer_on_the_gpu(tmp_path):
+    import subprocess
+
+    exe = _build_c_smoke(tmp_path)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "worst abs error" in r.stdout

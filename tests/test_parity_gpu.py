@@ -342,6 +342,29 @@ def test_c3_full_size_sampled_intervals():
     ev.close()
 
 
+@pytest.mark.parametrize("n,dt", [(8, 1.5), (6, 2.0), (16, 0.8)])
+def test_tdbilinear_large_steps(n, dt):
+    """Large |dt| (||G|| + carrier frequency): the kernels choose the number of macro steps per interval from the iterate
+    (tdb_item_steps: theta ~ 3..8 here, i.e. several macro steps) instead of silently losing accuracy with one
+    (the reference's Tsit5 adapts its steps the same way, time_dependent_bilinear_integrator.jl:117-127)."""
+    rng = np.random.default_rng(17)
+    prob = pt.carrier_problem(N=4, state_dim=n, n_drives=2, spline_order=1, dt=dt)
+    spec = prob.to_spec()
+    ev = dto.Evaluator(prob)
+    Z0 = prob.trajectory.vec()
+    Z = Z0 + 0.02 * rng.standard_normal(Z0.size)
+    jst, hst = orc.jacobian_structure(spec, Z0), orc.hessian_structure(spec, Z0)
+    mu = rng.random(ev.n_constraints)
+    g, J, H = np.empty(ev.n_constraints), np.empty(ev.nnz_jacobian), np.empty(ev.nnz_hessian)
+    ev.eval_all(Z, 1.0, mu, None, None, g, J, H)
+    assert relerr(g, orc.eval_constraint(spec, Z)) <= TDB_TOL
+    Jref = orc.eval_constraint_jacobian(spec, Z, jst)
+    assert relerr(J, Jref) <= TDB_TOL and blocks.jac_block_relerr(spec, jst, J, Jref) <= 10 * TDB_TOL
+    Href = orc.eval_hessian_lagrangian(spec, Z, 1.0, mu, hst)
+    assert relerr(H, Href) <= 10 * TDB_TOL
+    ev.close()
+
+
 def test_tdbilinear_variants_agree(monkeypatch):
     """The tensor-core variant of K7 and the CUDA-core variant integrate the same equations with the same
     extrapolation scheme: they must agree far below the parity tolerance (and the dispatch must pick them)."""
