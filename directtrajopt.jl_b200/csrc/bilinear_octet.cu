@@ -139,7 +139,7 @@ __device__ __forceinline__ void mul_t(Mat<NT>& out, const Mat<NT>& V, const Mat<
 template <int NT, int M, bool PP>
 __global__ void __launch_bounds__(NT == 1 ? 256 : 128)
     bilinear_octet_kernel(DProb P, int ii, const double* __restrict__ Z, const double* __restrict__ mu, double* __restrict__ g,
-                          double* __restrict__ jac, int want_jac, int want_hess, int jets) {
+                          double* __restrict__ jac, int want_jac, int want_hess, int jets, int split) {
     constexpr int n = 8 * NT, nn = n * n, J = 1 + M + M * (M + 1) / 2;
     extern __shared__ __align__(16) double sm[];
     const DInt& I = P.in[ii];
@@ -195,7 +195,19 @@ __global__ void __launch_bounds__(NT == 1 ? 256 : 128)
     const long long warp0 = (long long)(threadIdx.x >> 5) * gridDim.x + blockIdx.x;
     const long long nWarps = (long long)gridDim.x * (blockDim.x >> 5);
 
-    for (long long oct = warp0; oct < nOct; oct += nWarps) {
+    // Work units.  Normally one octet = one unit (forward, adjoint and propagator phases back to back in one warp).  When a
+    // launch has only a few rounds of octets per warp (a knot-range shard on eight GPUs: 1.3 rounds), the duration of one
+    // unit -- latency-bound, the same with two or eight warps on the SM -- quantises the kernel time; `split` makes every
+    // phase of an octet its own unit (longest first), a third of the granularity.
+    int phases[3], nPh = 0;
+    if (jets != DTO_JETS_USE) phases[nPh++] = 0;  // forward
+    if (want_jac) phases[nPh++] = 1;              // propagator + constant columns (+ derivative integrators)
+    if (want_hess) phases[nPh++] = 2;             // adjoint
+    const long long nUnits = split ? nOct * nPh : nOct;
+    for (long long unit = warp0; unit < nUnits; unit += nWarps) {
+        const long long oct = split ? unit % nOct : unit;
+        const int ph = split ? phases[unit / nOct] : -1;
+        const bool do_fwd = ph < 0 || ph == 0, do_exp = ph < 0 || ph == 1, do_adj = ph < 0 || ph == 2;
         int b, kk;
         const bool valid = locate(oct, row8, b, kk);
         if constexpr (PP) {  // this problem's generators
@@ -240,7 +252,7 @@ __global__ void __launch_bounds__(NT == 1 ? 256 : 128)
         const bool deriv = want_jac || second;
 
         // =========================== FWD ===========================
-        if (jets != DTO_JETS_USE) {
+        if (jets != DTO_JETS_USE && do_fwd) {
             Tile<NT> F[J], term[J];
 #pragma unroll
             for (int j = 0; j < J; ++j) tzero(F[j]);
@@ -418,7 +430,7 @@ __global__ void __launch_bounds__(NT == 1 ? 256 : 128)
         }
 
         // =========================== ADJ ===========================
-        if (want_hess) {
+        if (want_hess && do_adj) {
             Tile<NT> F[1 + M], term[1 + M];
 #pragma unroll
             for (int j = 0; j <= M; ++j) tzero(F[j]);
@@ -481,7 +493,7 @@ __global__ void __launch_bounds__(NT == 1 ? 256 : 128)
         // =========================== EXP: -E block, one interval at a time (rows = columns of E) ===========================
         // zero and identity columns (everything except the x, u, dt columns of the own knot), all eight intervals at once:
         // the four lanes of a row write the 8 NT rows of their interval's column
-        if (want_jac && valid) {
+        if (want_jac && valid && do_exp) {
             const long long prev_off = jac_prev_off(P, kk + 1, I.doff);
             for (int l = 0; l < 2 * z; ++l) {
                 if (l < z) {
@@ -501,13 +513,13 @@ __global__ void __launch_bounds__(NT == 1 ? 256 : 128)
             }
         }
         const bool fused = P.analytic_fused == ii + 1;  // this kernel also writes the derivative integrators' rows
-        if (fused && !want_jac && g != nullptr) {
+        if (fused && !want_jac && g != nullptr && do_fwd) {
             for (int r = 0; r < 8; ++r) {
                 int br, kr;
                 if (locate(oct, r, br, kr)) analytic_interval(P, Z, g, nullptr, br, kr, lane, 32);
             }
         }
-        if (want_jac) {
+        if (want_jac && do_exp) {
             for (int r = 0; r < 8; ++r) {
                 int br, kr;
                 if (!locate(oct, r, br, kr)) break;
@@ -655,8 +667,13 @@ bool launch_octet_pp(const DProb& P, int ii, const double* Z, const double* mu, 
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
     const long long nIc = std::min(P.kc1, P.nI) - P.kc0, items = (long long)P.batch * nIc;
     const long long octs = PP ? (long long)P.batch * ((nIc + 7) / 8) : (items + 7) / 8, wpc = threads / 32;
-    const int grid = (int)std::max<long long>(1, std::min<long long>((long long)sms * per_sm, (octs + wpc - 1) / wpc));
-    kern<<<grid, threads, smem, st>>>(P, ii, Z, mu, f.want_g ? g : nullptr, jac, f.want_jac ? 1 : 0, f.want_hess ? 1 : 0, f.jets);
+    const int nPh = (f.jets != DTO_JETS_USE ? 1 : 0) + (f.want_jac ? 1 : 0) + (f.want_hess ? 1 : 0);
+    const long long resident = (long long)sms * per_sm * wpc;  // warps in flight
+    const char* env = getenv("DTO_B200_OCTET_SPLIT");           // A/B switch: 0 = never, 1 = always
+    const bool split = nPh > 1 && (env ? env[0] == '1' : octs < 6 * resident);
+    const long long units = split ? octs * nPh : octs;
+    const int grid = (int)std::max<long long>(1, std::min<long long>((long long)sms * per_sm, (units + wpc - 1) / wpc));
+    kern<<<grid, threads, smem, st>>>(P, ii, Z, mu, f.want_g ? g : nullptr, jac, f.want_jac ? 1 : 0, f.want_hess ? 1 : 0, f.jets, split ? 1 : 0);
     ++*launches;
     return true;
 }
