@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libdto_b200.so")
+# DTO_B200_LIB: another build of the same library (e.g. the instrumented one of tools/build_profile_lib.sh)
+LIB_PATH = os.environ.get("DTO_B200_LIB") or os.path.join(HERE, "lib", "libdto_b200.so")
 
 DTO_OK, DTO_ERR_INVALID, DTO_ERR_UNSUPPORTED, DTO_ERR_CUDA, DTO_ERR_ALLOC = 0, -1, -2, -3, -4
 ABI_VERSION = 3

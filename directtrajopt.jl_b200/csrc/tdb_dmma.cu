@@ -32,129 +32,194 @@ constexpr int kMaxC = 4;      // carriers
 constexpr int kMaxCols = 10;  // extrapolation columns
 constexpr int kMaxWarpsT = 16;  // 16 warps x 128 registers (the allocation granularity makes 13..16 warps cost the same)
 
-struct Scal {  // per-evaluation scalars at time tau
-    double dt, tau, w0, w1;
-    double u[kMaxM], c[kMaxM], s[kMaxM], om[kMaxM];
-    double e[kMaxC], es[kMaxC], omd[kMaxC];
+struct Scal {  // what the generator assembly needs at one node
+    double dt;
+    double u[kMaxM], c[kMaxM], s[kMaxM];
+    double e[kMaxC];
+    double pad_;
 };
 
 struct Ctx {
     int n, m, nc, order, np;
 };
 
-__device__ void make_scal(const DInt& I, const double* zk, const double* zk1, int dt_off, double tau, Scal& S) {
-    S.dt = zk[dt_off];
-    S.tau = tau;
-    const double t = zk[I.t_off] + tau * S.dt;
-    S.w0 = I.order == 1 ? 1.0 - tau : 1.0;
-    S.w1 = I.order == 1 ? tau : 0.0;
+// Node values NV[]: every coupling coefficient of the jet recurrence is  NV[i1] NV[i2] + NV[i3] NV[i4]  (times the step
+// factor) with indices that depend only on the (row, slot, table) position, not on the node.  One array per node, written
+// by the lane that evaluates the node's sines and cosines.
+enum { NV_ONE = 0, NV_ZERO, NV_DT, NV_DTTAU, NV_2TAU, NV_DTTAU2, NV_W0, NV_W1, NV_DTW0, NV_DTW1, NV_W0DTTAU, NV_W1DTTAU, NV_BASE };
+// per drive i, 8 values at NV_BASE + 8 i:  C_i = (c, s);  C_i' = w (-s, c);  dG/dt part u w (-s, c);  d2G/dt2 part -u w^2 (c, s)
+enum { ND_C = 0, ND_S, ND_CP_A, ND_CP_B, ND_GT_A, ND_GT_B, ND_GTT_A, ND_GTT_B };
+// per carrier j, 2 values at NV_BASE + 8 m + 2 j:  dG/dt part -wd sin,  d2G/dt2 part -wd^2 cos
+__host__ __device__ inline int nv_count(int m, int nc) { return NV_BASE + 8 * m + 2 * nc; }
+
+__device__ void make_scal(const DInt& I, const double* zk, const double* zk1, int dt_off, double tau, Scal& S, double* nv) {
+    const double dt = zk[dt_off];
+    S.dt = dt;
+    const double t = zk[I.t_off] + tau * dt;
+    const double w0 = I.order == 1 ? 1.0 - tau : 1.0, w1 = I.order == 1 ? tau : 0.0;
+    if (nv != nullptr) {
+        nv[NV_ONE] = 1.0;
+        nv[NV_ZERO] = 0.0;
+        nv[NV_DT] = dt;
+        nv[NV_DTTAU] = dt * tau;
+        nv[NV_2TAU] = 2.0 * tau;
+        nv[NV_DTTAU2] = dt * tau * tau;
+        nv[NV_W0] = w0;
+        nv[NV_W1] = w1;
+        nv[NV_DTW0] = dt * w0;
+        nv[NV_DTW1] = dt * w1;
+        nv[NV_W0DTTAU] = w0 * dt * tau;
+        nv[NV_W1DTTAU] = w1 * dt * tau;
+    }
     for (int i = 0; i < I.m; ++i) {
         const double u0 = zk[I.u_off + i], u1 = I.order == 1 ? zk1[I.u_off + i] : u0;
-        S.u[i] = S.w0 * u0 + S.w1 * u1;
-        S.om[i] = I.omega[i];
-        sincos(I.omega[i] * t + I.phi[i], &S.s[i], &S.c[i]);
+        const double u = w0 * u0 + w1 * u1, om = I.omega[i];
+        double sn, cs;
+        sincos(om * t + I.phi[i], &sn, &cs);
+        S.u[i] = u;
+        S.c[i] = cs;
+        S.s[i] = sn;
+        if (nv != nullptr) {
+            double* d = nv + NV_BASE + 8 * i;
+            d[ND_C] = cs;
+            d[ND_S] = sn;
+            d[ND_CP_A] = -om * sn;
+            d[ND_CP_B] = om * cs;
+            d[ND_GT_A] = u * om * (-sn);
+            d[ND_GT_B] = u * om * cs;
+            d[ND_GTT_A] = -u * om * om * cs;
+            d[ND_GTT_B] = -u * om * om * sn;
+        }
     }
     for (int j = 0; j < I.n_carrier; ++j) {
-        S.omd[j] = I.omega_d[j];
-        sincos(I.omega_d[j] * t + I.phi_d[j], &S.es[j], &S.e[j]);
+        const double omd = I.omega_d[j];
+        double es, ec;
+        sincos(omd * t + I.phi_d[j], &es, &ec);
+        S.e[j] = ec;
+        if (nv != nullptr) {
+            nv[NV_BASE + 8 * I.m + 2 * j] = -omd * es;
+            nv[NV_BASE + 8 * I.m + 2 * j + 1] = -omd * omd * ec;
+        }
     }
 }
 
-// ---- parameter couplings as linear combinations of table rows ------------------------------------------------
+// ---- parameter couplings ------------------------------------------------------------------------------------------
 // Tables (shared memory): T_0[v] = G Z_v (before the dt factor), T_{1+i}[v] = A_i Z_v, T_{1+m+i}[v] = B_i Z_v,
-// T_{1+2m+j}[v] = D_j Z_v.  Every coupling term of a row is  sum_t coef[t] * T_t[v'] ; the coefficients depend on
-// the node (tau) but not on the state index, so a lane builds them once per right-hand side (in registers:
-// fixed slots, statically indexed) and then streams the table rows.
-struct Coef {
-    double g, a[kMaxM], b[kMaxM], d[kMaxC];
-};
-__device__ __forceinline__ void coef_zero(Coef& c) {
-    c.g = 0.0;
-#pragma unroll
-    for (int i = 0; i < kMaxM; ++i) c.a[i] = c.b[i] = 0.0;
-#pragma unroll
-    for (int j = 0; j < kMaxC; ++j) c.d[j] = 0.0;
-}
-__device__ __forceinline__ void coef_scale(Coef& c, double f) {
-    c.g *= f;
-#pragma unroll
-    for (int i = 0; i < kMaxM; ++i) {
-        c.a[i] *= f;
-        c.b[i] *= f;
+// T_{1+2m+j}[v] = D_j Z_v.  The coupling of a row is  sum_t coef[t] * T_t[source row]  with, per (row, slot):
+//   first-order row a:  slot 0 = dM/dtheta_a            (source row 0 = x)
+//   pair row (a, b):    slot 0 = M_a (2 M_a if a == b)  (source row 1 + b)
+//                       slot 1 = M_b                    (source row 1 + a, a != b)
+//                       slot 2 = M_ab                   (source row 0)
+// M = dt G(u(tau), t_k + tau dt), theta = [u_k (m), u_{k+1} (m, order 1), dt, t_k];  dG/dt, d2G/dt2 act on the carriers.
+// coef_indices() gives the NV indices of entry t of one of those matrices' coefficient vectors:
+//   value = NV[i1] NV[i2] + NV[i3] NV[i4]      (packed i1 | i2 << 8 | i3 << 16 | i4 << 24)
+enum { AT_ZERO = 0, AT_EG, AT_GT, AT_GTT, AT_C, AT_CP };
+__device__ __forceinline__ int atom_index(int atom, int i, int t, int m) {  // NV index of component t of an atom
+    if (atom == AT_ZERO) return NV_ZERO;
+    if (atom == AT_EG) return t == 0 ? NV_ONE : NV_ZERO;
+    if (t == 0) return NV_ZERO;
+    if (t <= 2 * m) {
+        const bool isb = t > m;
+        const int it = isb ? t - 1 - m : t - 1;
+        const int base = NV_BASE + 8 * it;
+        if (atom == AT_GT) return base + (isb ? ND_GT_B : ND_GT_A);
+        if (atom == AT_GTT) return base + (isb ? ND_GTT_B : ND_GTT_A);
+        if (it != i) return NV_ZERO;
+        if (atom == AT_C) return base + (isb ? ND_S : ND_C);
+        return base + (isb ? ND_CP_B : ND_CP_A);
     }
-#pragma unroll
-    for (int j = 0; j < kMaxC; ++j) c.d[j] *= f;
+    const int j = t - 1 - 2 * m;
+    if (atom == AT_GT) return NV_BASE + 8 * m + 2 * j;
+    if (atom == AT_GTT) return NV_BASE + 8 * m + 2 * j + 1;
+    return NV_ZERO;
 }
-// coef += scale * dG/dt = scale * [sum_i u_i w_i (-s_i A_i + c_i B_i) - sum_j wd_j es_j D_j]
-__device__ __forceinline__ void add_Gt(Coef& c, const Scal& S, const Ctx& C, double scale) {
-#pragma unroll
-    for (int i = 0; i < kMaxM; ++i)
-        if (i < C.m) {
-            c.a[i] += scale * S.u[i] * S.om[i] * (-S.s[i]);
-            c.b[i] += scale * S.u[i] * S.om[i] * S.c[i];
-        }
-#pragma unroll
-    for (int j = 0; j < kMaxC; ++j)
-        if (j < C.nc) c.d[j] += scale * (-S.omd[j] * S.es[j]);
-}
-// coef += scale * d2G/dt2
-__device__ __forceinline__ void add_Gtt(Coef& c, const Scal& S, const Ctx& C, double scale) {
-#pragma unroll
-    for (int i = 0; i < kMaxM; ++i)
-        if (i < C.m) {
-            const double f = -scale * S.u[i] * S.om[i] * S.om[i];
-            c.a[i] += f * S.c[i];
-            c.b[i] += f * S.s[i];
-        }
-#pragma unroll
-    for (int j = 0; j < kMaxC; ++j)
-        if (j < C.nc) c.d[j] += -scale * S.omd[j] * S.omd[j] * S.e[j];
-}
-// coef += dM/dtheta_a, M = dt G(u(tau), t_k + tau dt), theta = [u_k (m), u_{k+1} (m, order 1), dt, t_k]
-__device__ __forceinline__ void add_Ma(Coef& c, const Scal& S, const Ctx& C, int a) {
+// dM/dtheta_a -> (atom A, scalar A, atom B, scalar B, drive index)
+__device__ __forceinline__ void terms_Ma(const Ctx& C, int a, int& aA, int& sA, int& aB, int& sB, int& drive) {
     const int nu = C.np - 2;
-    if (a < nu) {
-        const int ia = a % C.m;
-        const double w = S.dt * (a < C.m ? S.w0 : S.w1);
-#pragma unroll
-        for (int i = 0; i < kMaxM; ++i)
-            if (i == ia) {
-                c.a[i] += w * S.c[i];
-                c.b[i] += w * S.s[i];
-            }
-    } else if (a == nu) {
-        c.g += 1.0;
-        add_Gt(c, S, C, S.dt * S.tau);
-    } else {
-        add_Gt(c, S, C, S.dt);
+    aA = aB = AT_ZERO;
+    sA = sB = NV_ZERO;
+    drive = 0;
+    if (a < nu) {  // dt w C_i
+        drive = a % C.m;
+        aA = AT_C;
+        sA = a < C.m ? NV_DTW0 : NV_DTW1;
+    } else if (a == nu) {  // G + dt tau dG/dt
+        aA = AT_EG;
+        sA = NV_ONE;
+        aB = AT_GT;
+        sB = NV_DTTAU;
+    } else {  // dt dG/dt
+        aA = AT_GT;
+        sA = NV_DT;
     }
 }
-// coef += d2M/(dtheta_a dtheta_b), a <= b
-__device__ __forceinline__ void add_Mab(Coef& c, const Scal& S, const Ctx& C, int a, int b) {
+// d2M/(dtheta_a dtheta_b), a <= b
+__device__ __forceinline__ void terms_Mab(const Ctx& C, int a, int b, int& aA, int& sA, int& aB, int& sB, int& drive) {
     const int nu = C.np - 2;
+    aA = aB = AT_ZERO;
+    sA = sB = NV_ZERO;
+    drive = 0;
     if (b < nu) return;  // u-u
     if (a < nu) {
-        const int ia = a % C.m;
-        const double w = a < C.m ? S.w0 : S.w1;
-        // b == dt: w (C_i + dt tau C_i');  b == t: dt w C_i',  C_i = c A + s B, C_i' = om (-s A + c B)
-        const double f0 = b == nu ? w : 0.0, f1 = b == nu ? w * S.dt * S.tau : S.dt * w;
-#pragma unroll
-        for (int i = 0; i < kMaxM; ++i)
-            if (i == ia) {
-                c.a[i] += f0 * S.c[i] + f1 * S.om[i] * (-S.s[i]);
-                c.b[i] += f0 * S.s[i] + f1 * S.om[i] * S.c[i];
-            }
+        drive = a % C.m;
+        const bool k0 = a < C.m;
+        if (b == nu) {  // w (C_i + dt tau C_i')
+            aA = AT_C;
+            sA = k0 ? NV_W0 : NV_W1;
+            aB = AT_CP;
+            sB = k0 ? NV_W0DTTAU : NV_W1DTTAU;
+        } else {  // dt w C_i'
+            aA = AT_CP;
+            sA = k0 ? NV_DTW0 : NV_DTW1;
+        }
         return;
     }
-    if (a == nu && b == nu) {
-        add_Gt(c, S, C, 2.0 * S.tau);
-        add_Gtt(c, S, C, S.dt * S.tau * S.tau);
-    } else if (a == nu) {
-        add_Gt(c, S, C, 1.0);
-        add_Gtt(c, S, C, S.dt * S.tau);
-    } else {
-        add_Gtt(c, S, C, S.dt);
+    if (a == nu && b == nu) {  // 2 tau dG/dt + dt tau^2 d2G/dt2
+        aA = AT_GT;
+        sA = NV_2TAU;
+        aB = AT_GTT;
+        sB = NV_DTTAU2;
+    } else if (a == nu) {  // dG/dt + dt tau d2G/dt2
+        aA = AT_GT;
+        sA = NV_ONE;
+        aB = AT_GTT;
+        sB = NV_DTTAU;
+    } else {  // dt d2G/dt2
+        aA = AT_GTT;
+        sA = NV_DT;
     }
+}
+
+// NV indices of coefficient-table entry `en` = ((row * 3 + slot) * KCr + t): packed i1 | i2 << 8 | i3 << 16 | i4 << 24, and
+// whether the entry carries the factor 2 of a diagonal pair.  Rows [0, nrowsF) are the forward rows 1.., then np adjoint rows.
+__device__ int coef_entry(const Ctx& C, int KCr, int nrowsF, int en, bool& twice) {
+    const int t = en % KCr, it = en / KCr, slot = it % 3, r = it / 3, np = C.np;
+    int aA = AT_ZERO, sA = NV_ZERO, aB = AT_ZERO, sB = NV_ZERO, drive = 0;
+    twice = false;
+    if (r < nrowsF) {
+        const int v = r + 1;
+        if (v <= np) {
+            if (slot == 0) terms_Ma(C, v - 1, aA, sA, aB, sB, drive);
+        } else {
+            int pp = v - 1 - np, a = 0;
+            while (a < np && pp >= np - a) {
+                pp -= np - a;
+                ++a;
+            }
+            const int bb = a + pp;
+            if (slot == 0) {
+                terms_Ma(C, a, aA, sA, aB, sB, drive);
+                twice = a == bb;
+            } else if (slot == 1) {
+                if (a != bb) terms_Ma(C, bb, aA, sA, aB, sB, drive);
+            } else {
+                terms_Mab(C, a, bb, aA, sA, aB, sB, drive);
+            }
+        }
+    } else if (slot == 0) {
+        terms_Ma(C, r - nrowsF, aA, sA, aB, sB, drive);
+    }
+    return atom_index(aA, drive, t, C.m) | (sA << 8) | (atom_index(aB, drive, t, C.m) << 16) | (sB << 24);
 }
 
 // D += cf * row   (this lane's states 8 nt + 2q + {0,1})
@@ -168,24 +233,6 @@ __device__ __forceinline__ void axpy_row(double (&D)[1][NT][2], double cf, const
         D[0][nt][1] = fma(cf, x.y, D[0][nt][1]);
     }
 }
-// D += sum_t coef[t] * T_t[row]  (tables are [t][rows][stride])
-template <int NT>
-__device__ __forceinline__ void apply_terms(double (&D)[1][NT][2], const Coef& c, const Ctx& C, const double* tab, int rows, int stride,
-                                            int row, int q) {
-    const double* base = tab + (size_t)row * stride + 2 * q;
-    const size_t ts = (size_t)rows * stride;
-    axpy_row<NT>(D, c.g, base);
-#pragma unroll
-    for (int i = 0; i < kMaxM; ++i)
-        if (i < C.m) {
-            axpy_row<NT>(D, c.a[i], base + (1 + i) * ts);
-            axpy_row<NT>(D, c.b[i], base + (1 + C.m + i) * ts);
-        }
-#pragma unroll
-    for (int j = 0; j < kMaxC; ++j)
-        if (j < C.nc) axpy_row<NT>(D, c.d[j], base + (1 + 2 * C.m + j) * ts);
-}
-
 enum { W_FWD = 0, W_EXP = 1, W_ADJ = 2, W_IDLE = 3 };
 
 #ifdef DTO_TDB_PROFILE
@@ -219,6 +266,50 @@ __device__ __forceinline__ void mma_tile(double (&out)[1][NT][2], const double (
     }
 }
 
+// R += s * (V * M') for one tile, by output halves: only half a tile of accumulators is live beside the two state tiles
+// (previous and current vector of the midpoint rule), so that 16 warps fit the register file without spills.  The raw
+// products go to `tab` (this lane's row of a coupling table, 8 doubles apart per n-tile) when `to_tab` is set.
+template <int NT>
+__device__ __forceinline__ void mma_tile_axpy(double (&R)[1][NT][2], const double (&v)[1][NT][2], const double* __restrict__ M, double s, int lane,
+                                              double* __restrict__ tab, bool to_tab) {
+    constexpr int n = 8 * NT, NH = (NT + 1) / 2;
+    const int row8 = lane >> 2;
+    const int d = (NT % 2 == 0) ? ((row8 & 1) << 3) : 0;
+    const double* base = M + row8 * n + 2 * (lane & 3);
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        double acc[NH][2];
+#pragma unroll
+        for (int x = 0; x < NH; ++x) acc[x][0] = acc[x][1] = 0.0;
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+            const int off = 8 * t + ((t & 1) ? -d : d);
+            double2 bf[NH];
+#pragma unroll
+            for (int x = 0; x < NH; ++x)
+                if (half * NH + x < NT) bf[x] = *reinterpret_cast<const double2*>(base + 8 * (half * NH + x) * n + off);
+#pragma unroll
+            for (int x = 0; x < NH; ++x)
+                if (half * NH + x < NT) dmma(acc[x][0], acc[x][1], v[0][t][0], bf[x].x);
+#pragma unroll
+            for (int x = 0; x < NH; ++x)
+                if (half * NH + x < NT) dmma(acc[x][0], acc[x][1], v[0][t][1], bf[x].y);
+        }
+#pragma unroll
+        for (int x = 0; x < NH; ++x) {
+            const int nt = half * NH + x;
+            if (nt < NT) {
+                if (to_tab) {
+                    tab[8 * nt] = acc[x][0];
+                    tab[8 * nt + 1] = acc[x][1];
+                }
+                R[0][nt][0] = fma(s, acc[x][0], R[0][nt][0]);
+                R[0][nt][1] = fma(s, acc[x][1], R[0][nt][1]);
+            }
+        }
+    }
+}
+
 // basis matrix b (0..2m+nc-1) of the swizzled row-major copies
 __device__ __forceinline__ const double* basis_global(const DInt& I, int b, int nn) {
     if (b < I.m) return I.Asw + (size_t)b * nn;
@@ -233,7 +324,7 @@ __device__ __forceinline__ const double* basis_global(const DInt& I, int b, int 
 // the stores to Gf/Ga would otherwise force the compiler to re-read them from shared memory per element.
 template <int NT, bool CACHED, int MM, int CC>
 __device__ __forceinline__ void assemble_generators(double* Gf, double* Ga, const double* Bs, const DInt& I, const Scal& Sf, const Scal& Sa,
-                                                    int m, int nc, bool want_adj, int warp, int nwarps, int lane) {
+                                                    int m, int nc, bool want_adj, int b0, int b1, int lane) {
     constexpr int n = 8 * NT, nn = n * n;
     const double* gA = I.Asw;
     const double* gB = I.Bsw;
@@ -253,7 +344,7 @@ __device__ __forceinline__ void assemble_generators(double* Gf, double* Ga, cons
     }
     // two adjacent columns per thread (16-byte loads and stores; a swizzled pair stays adjacent): an 8 x 8 block of
     // the matrix per warp pass
-    for (int blk = warp; blk < nn / 64; blk += nwarps) {
+    for (int blk = b0; blk < b1; ++blk) {
         const int r = (blk / NT) * 8 + (lane >> 2), c = (blk % NT) * 8 + 2 * (lane & 3);
         const int p = sw<NT>(r, c);
         const double2 g0 = *reinterpret_cast<const double2*>(Gf + p);  // the drift entries, prefetched by this very thread
@@ -332,15 +423,64 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
     Scal* scal = reinterpret_cast<Scal*>(Ga + nn);            // [2 buffers][forward, adjoint]
     double* pub0 = reinterpret_cast<double*>(scal + 4);       // leading forward tile in fragment order
     double* lam = pub0 + FR;                                  // lambda (n)
-    // table rows are n + 2 doubles apart: the couplings read a different row per lane group, and this stride
-    // spreads the 32 16-byte reads of one LDS.128 evenly over the banks
-    constexpr int TS = n + 2;
+    // table rows are TS doubles apart    // (n + 4: the 8-byte B-fragment reads of the coupling product -- 4 table rows x 8 states per k-step -- and the 16-byte
+    // C-fragment stores that fill the tables both spread evenly over the banks)
+    constexpr int TS = n + 4;
     double* PG = lam + n;                                     // [8][TS]   G Z_v (before the dt factor)
     double* Pb = PG + 8 * TS;                                 // [nbasis][8][TS]
     double* PGa = Pb + (size_t)nbasis * 8 * TS;               // [n]       G' lambda
     double* PT = PGa + n;                                     // [nbasis][n] basis' lambda
     double* wk = PT + (size_t)nbasis * n;                     // [kMaxCols] extrapolation weights
-    double* Bs = wk + kMaxCols + (kMaxCols & 1);              // the first nbs basis matrices, cached for the CTA's lifetime
+    // coupling coefficients of the current node, built ONCE per right-hand side (one (row, slot) per thread, during the
+    // product phase) instead of by every lane of every forward row: [forward rows 1.. | adjoint rows][3 slots][KCr]
+    const int KCr = 1 + 2 * m + nc;
+    double* CT = wk + kMaxCols + (kMaxCols & 1);
+    const int ctRows = (nvecF > 1 ? nvecF - 1 : 0) + (TA > 0 ? np : 0);
+    double* NV = CT + ((size_t)ctRows * 3 * KCr + 1) / 2 * 2;   // [2 buffers][forward, adjoint][NVn] node values
+    const int NVn = (nv_count(m, nc) + 1) / 2 * 2;
+    double* Bs = NV + 4 * (size_t)NVn;                           // cached basis matrices
+    // Coupling GEMM of the forward tiles (phase 3): per k-step this lane's A element comes from CT[ctoff] (or is zero) and
+    // its B elements from table row boff; both are fixed for the kernel's lifetime -> packed once: ctoff | boff << 13.
+    constexpr int kPackedKS = 10, kNoCoef = 0x1FFF;
+    const int nsrc = 1 + np, Kdim = KCr * nsrc;
+    const bool packed = Kdim <= 4 * kPackedKS;
+    int pk[kPackedKS];
+#pragma unroll
+    for (int ks = 0; ks < kPackedKS; ++ks) {
+        const int k = 4 * ks + q, kc = k < Kdim ? k : Kdim - 1;
+        const int t = kc / nsrc, vs = kc - t * nsrc;
+        const int v = 8 * tile + row8;
+        int slot = -1;
+        if (role == W_FWD && v >= 1 && v < nvecF && k < Kdim) {
+            if (v <= np) slot = vs == 0 ? 0 : -1;
+            else if (vs == 1 + pair_b) slot = 0;
+            else if (vs == 1 + pair_a) slot = 1;  // only reached when a != b
+            else if (vs == 0) slot = 2;
+        }
+        pk[ks] = (slot >= 0 ? ((v - 1) * 3 + slot) * KCr + t : kNoCoef) | (((t * 8 + vs) * TS) << 13);
+    }
+    // Coefficient-table entries this lane rebuilds at every node: the rows of its own tile (forward warps) or the adjoint
+    // rows (adjoint warp), entries ct_lo + lane + 32 j.  Their NV indices never change: decoded once, kept packed.
+    constexpr int kEntPerLane = 4;
+    const int nrowsF = couple ? nvecF - 1 : 0;
+    int ct_lo = 0, ct_hi = 0;  // [ct_lo, ct_hi) entries of CT
+    if (role == W_FWD && couple) {
+        ct_lo = (8 * tile == 0 ? 0 : 8 * tile - 1) * 3 * KCr;
+        ct_hi = min(8 * tile + 7, nrowsF) * 3 * KCr;
+    } else if (role == W_ADJ) {
+        ct_lo = nrowsF * 3 * KCr;
+        ct_hi = (nrowsF + np) * 3 * KCr;
+    }
+    const bool ct_packed = ct_hi - ct_lo <= 32 * kEntPerLane;
+    int ctd[kEntPerLane];
+    int ct_twice = 0;
+#pragma unroll
+    for (int j = 0; j < kEntPerLane; ++j) {
+        const int en = ct_lo + lane + 32 * j;
+        bool tw = false;
+        ctd[j] = en < ct_hi ? coef_entry(C, KCr, nrowsF, en, tw) : 0;
+        ct_twice |= tw ? 1 << j : 0;
+    }
     if (threadIdx.x < kMaxCols) {
         // w_k = prod_{l != k} n_k^2 / (n_k^2 - n_l^2), n_k = 2(k+1)
         const int k = threadIdx.x;
@@ -364,14 +504,19 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
     // Who assembles G: all warps, except that forward-tile warps with parameter couplings are exempt when at least
     // three other warps exist -- their coupling phase is the long one, and the assembly of node q+1 by the others
     // then overlaps it.  (aw, na) = this warp's index among the assemblers and their number; aw < 0: not one.
-    int aw = warp, na = nwarps;
-    if (TF > 0 && (want_hess || want_jac) && nwarps - TF >= 3) {
-        aw = warp >= TF ? warp - TF : -1;
-        na = nwarps - TF;
+    // Who assembles G: every warp takes a contiguous run of 8 x 8 blocks; forward-tile warps with parameter couplings take
+    // half a share when at least three other warps exist -- they arrive late from the coupling phase of the previous node,
+    // while the others start right after the second barrier.  [ab0, ab1) = this warp's blocks.
+    int ab0, ab1;
+    {
+        const bool light = TF > 0 && (want_hess || want_jac) && nwarps - TF >= 3;
+        const int wF = light ? 1 : 2, total = TF * wF + (nwarps - TF) * 2, nblk = nn / 64;
+        const int before = warp < TF ? warp * wF : TF * wF + (warp - TF) * 2;
+        ab0 = nblk * before / total;
+        ab1 = nblk * (before + (warp < TF ? wF : 2)) / total;
     }
     auto prefetch_drift = [&]() {
-        if (aw < 0) return;
-        for (int blk = aw; blk < nn / 64; blk += na) {
+        for (int blk = ab0; blk < ab1; ++blk) {
             const int p = sw<NT>((blk / NT) * 8 + (lane >> 2), (blk % NT) * 8 + 2 * (lane & 3));
             const unsigned dst = (unsigned)__cvta_generic_to_shared(Gf + p);
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(I.Grm + p) : "memory");
@@ -406,11 +551,13 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
                 if (role != W_IDLE) Y0S[(nt * 2 + j) * 32 + lane] = val;
             }
     }
-    if (warp == scal_warp && lane < 2) make_scal(I, zk, zk1, P.dt_off, lane == 0 ? 0.0 : 1.0, scal[lane]);
+    if (warp == scal_warp && lane < 2) make_scal(I, zk, zk1, P.dt_off, lane == 0 ? 0.0 : 1.0, scal[lane], NV + (size_t)lane * NVn);
     prefetch_drift();
     __syncthreads();
 
-    double Zp[1][NT][2], Zc[1][NT][2], D[1][NT][2];
+    // Midpoint rule with TWO state tiles: Zp (z_{q-1}) is updated in place to z_{q+1} = z_{q-1} + 2h f(z_q) -- product and
+    // couplings accumulate straight into it -- and then the two tiles trade names.
+    double Zp[1][NT][2], Zc[1][NT][2];
     int e = 0;  // right-hand sides evaluated so far (parity selects the scalar buffer)
     for (int ms = 0; ms < steps; ++ms) {
         const double H = 1.0 / steps, s0 = ms * H;
@@ -437,15 +584,41 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
 #ifdef DTO_TDB_PROFILE
                 long long tp1 = clock64();
 #endif
-                if (aw < 0) {
-                } else if (nbs == nbasis && m <= 2 && nc == 0) assemble_generators<NT, true, 2, 0>(Gf, Ga, Bs, I, Sf, Sa, m, nc, TA > 0, aw, na, lane);
-                else if (nbs == nbasis) assemble_generators<NT, true, kMaxM, kMaxC>(Gf, Ga, Bs, I, Sf, Sa, m, nc, TA > 0, aw, na, lane);
-                else assemble_generators<NT, false, kMaxM, kMaxC>(Gf, Ga, Bs, I, Sf, Sa, m, nc, TA > 0, aw, na, lane);
+                if (nbs == nbasis && m <= 2 && nc == 0) assemble_generators<NT, true, 2, 0>(Gf, Ga, Bs, I, Sf, Sa, m, nc, TA > 0, ab0, ab1, lane);
+                else if (nbs == nbasis) assemble_generators<NT, true, kMaxM, kMaxC>(Gf, Ga, Bs, I, Sf, Sa, m, nc, TA > 0, ab0, ab1, lane);
+                else assemble_generators<NT, false, kMaxM, kMaxC>(Gf, Ga, Bs, I, Sf, Sa, m, nc, TA > 0, ab0, ab1, lane);
                 if (role == W_FWD && tile == 0 && couple) {
 #pragma unroll
                     for (int nt = 0; nt < NT; ++nt) {
                         pub0[(nt * 2) * 32 + lane] = Zc[0][nt][0];
                         pub0[(nt * 2 + 1) * 32 + lane] = Zc[0][nt][1];
+                    }
+                }
+                // step factor of this node: z_1 = z_0 + h f(z_0); z_{q+1} = z_{q-1} + 2h f(z_q); smoothing uses z_{n-1} + h f(z_n)
+                const double hs = (qq == 0 || qq == nk) ? h : 2.0 * h;
+                if (ct_hi > ct_lo) {
+                    // Coupling coefficients of this node (times the step factor): CT[en] = hs (NV[i1] NV[i2] + NV[i3] NV[i4]).  Every
+                    // warp rebuilds the rows of ITS OWN tile (it is their only reader: no hazard with a neighbour still in the
+                    // previous node's couplings), here in the assembly phase -- the forward warps do not assemble and the FP64
+                    // pipe is not yet busy with this node's products.
+                    const double* nv = NV + (size_t)((e & 1) * 2 + (role == W_ADJ ? 1 : 0)) * NVn;  // adjoint rows: the reflected node
+                    if (ct_packed) {
+#pragma unroll
+                        for (int j = 0; j < kEntPerLane; ++j) {
+                            const int en = ct_lo + lane + 32 * j;
+                            if (en < ct_hi) {
+                                const int d = ctd[j];
+                                const double va = nv[d & 255] * nv[(d >> 8) & 255];
+                                CT[en] = ((ct_twice >> j) & 1 ? 2.0 * hs : hs) * fma(nv[(d >> 16) & 255], nv[(d >> 24) & 255], va);
+                            }
+                        }
+                    } else {
+                        for (int en = ct_lo + lane; en < ct_hi; en += 32) {
+                            bool tw = false;
+                            const int d = coef_entry(C, KCr, nrowsF, en, tw);
+                            const double va = nv[d & 255] * nv[(d >> 8) & 255];
+                            CT[en] = (tw ? 2.0 * hs : hs) * fma(nv[(d >> 16) & 255], nv[(d >> 24) & 255], va);
+                        }
                     }
                 }
                 if (role == W_ADJ && row8 == 0) {
@@ -470,30 +643,43 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
                     else if (k + 1 < K) sn = s0;
                     else if (ms + 1 < steps) sn = s0 + H;
                     else { has_next = false; sn = 0.0; }
-                    if (has_next) make_scal(I, zk, zk1, P.dt_off, lane == 0 ? sn : 1.0 - sn, scal[((e + 1) & 1) * 2 + lane]);
+                    if (has_next) make_scal(I, zk, zk1, P.dt_off, lane == 0 ? sn : 1.0 - sn, scal[((e + 1) & 1) * 2 + lane],
+                                            NV + (size_t)(((e + 1) & 1) * 2 + lane) * NVn);
                 }
                 // basis' lambda on the FMA pipe, one output per thread, taken from the top of the CTA.  It is a chain of
                 // dependent FMAs fed from shared memory (latency-bound): the two warps of a scheduler run it at
                 // opposite ends of the phase so that it hides behind the other warp's DMMAs.
                 auto adjoint_basis_products = [&]() {
-                    for (int idx = (int)blockDim.x - 1 - (int)threadIdx.x; idx < nbasis * n; idx += blockDim.x) {
-                        const int bi = idx / n, s = idx % n;
-                        const double* Mb = basis_ptr(bi);
-                        double acc0 = 0.0, acc1 = 0.0;
-#pragma unroll 8
-                        for (int kk = 0; kk < n; kk += 2) {
-                            acc0 = fma(Mb[sw<NT>(kk, s)], lam[kk], acc0);
-                            acc1 = fma(Mb[sw<NT>(kk + 1, s)], lam[kk + 1], acc1);
+                    const int nh = nwarps > TF ? ((int)blockDim.x - TF * 32) : (int)blockDim.x;  // the warps without a forward tile, if any
+                    if (nwarps > TF && warp < TF) return;
+                    // two outputs per pass, four partial sums each: eight independent FMA chains of n / 4 links instead of one
+                    // output at a time with two chains of n / 2 (the chains queue behind the other warps' DMMAs on the shared pipe)
+                    for (int idx = (int)blockDim.x - 1 - (int)threadIdx.x; idx < nbasis * n; idx += 2 * nh) {
+                        const int idx2 = idx + nh < nbasis * n ? idx + nh : idx;
+                        const int s1 = idx % n, s2 = idx2 % n;
+                        const double* M1 = basis_ptr(idx / n);
+                        const double* M2 = basis_ptr(idx2 / n);
+                        double a1[4] = {0.0, 0.0, 0.0, 0.0}, a2[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 4
+                        for (int kk = 0; kk < n; kk += 4) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const double l = lam[kk + j];
+                                a1[j] = fma(M1[sw<NT>(kk + j, s1)], l, a1[j]);
+                                a2[j] = fma(M2[sw<NT>(kk + j, s2)], l, a2[j]);
+                            }
                         }
-                        PT[(size_t)bi * n + s] = acc0 + acc1;
+                        PT[idx] = (a1[0] + a1[1]) + (a1[2] + a1[3]);
+                        if (idx2 != idx) PT[idx2] = (a2[0] + a2[1]) + (a2[2] + a2[3]);
                     }
                 };
                 const bool matvec_first = (warp & 4) == 0;
                 if (TA > 0 && matvec_first) adjoint_basis_products();
                 if (couple) {
-                    // basis products of the leading forward tile, one per warp, starting at the propagator warps
+                    // basis products of the leading forward tile, one per warp, starting at the last (idle helper) warps
                     for (int bi = 0; bi < nbasis; ++bi) {
-                        if ((TF + bi) % nwarps != warp) continue;
+                        // one per forward warp (their own product is the only other work they have in this phase), the rest from the top
+                        if ((bi < TF ? bi : nwarps - 1 - (bi - TF) % nwarps) != warp) continue;
                         const double* Mb = basis_ptr(bi);
                         double* out = Pb + (size_t)bi * 8 * TS + (size_t)row8 * TS + 2 * q;
 #pragma unroll
@@ -531,28 +717,17 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
                     }
                 }
                 if (role != W_IDLE) {
-                    frag_zero(D);
-                    mma_tile<NT>(D, Zc, role == W_ADJ ? Ga : Gf, lane);
-                    if (role == W_FWD && tile == 0 && couple) {
+                    if (qq == 0) {
 #pragma unroll
                         for (int nt = 0; nt < NT; ++nt) {
-                            PG[row8 * TS + 8 * nt + 2 * q] = D[0][nt][0];
-                            PG[row8 * TS + 8 * nt + 2 * q + 1] = D[0][nt][1];
+                            Zp[0][nt][0] = Zc[0][nt][0];
+                            Zp[0][nt][1] = Zc[0][nt][1];
                         }
                     }
-                    if (role == W_ADJ && row8 == 0) {
-#pragma unroll
-                        for (int nt = 0; nt < NT; ++nt) {
-                            PGa[8 * nt + 2 * q] = D[0][nt][0];
-                            PGa[8 * nt + 2 * q + 1] = D[0][nt][1];
-                        }
-                    }
-                    const double dts = Sf.dt;
-#pragma unroll
-                    for (int nt = 0; nt < NT; ++nt) {
-                        D[0][nt][0] *= dts;
-                        D[0][nt][1] *= dts;
-                    }
+                    const bool pubG = role == W_FWD && tile == 0 && couple;
+                    const bool pubA = role == W_ADJ && row8 == 0;
+                    double* tab = pubG ? PG + row8 * TS + 2 * q : PGa + 2 * q;
+                    mma_tile_axpy<NT>(Zp, Zc, role == W_ADJ ? Ga : Gf, hs * Sf.dt, lane, tab, pubG || pubA);
                 }
                 if (TA > 0 && !matvec_first) adjoint_basis_products();
 #ifdef DTO_TDB_PROFILE
@@ -567,69 +742,74 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
 #ifdef DTO_TDB_PROFILE
                 long long tc0 = clock64();
 #endif
-                if (role == W_FWD && couple) {
-                    const int v = 8 * tile + row8;
-                    if (v >= 1 && v < nvecF) {
-                        const Scal S = Sf;  // node scalars into registers: the coefficient algebra below is then load-free
-                        Coef cf;
-                        coef_zero(cf);
-                        if (v <= np) {  // first-order row a: (dM/dtheta_a) x
-                            add_Ma(cf, S, C, v - 1);
-                            apply_terms<NT>(D, cf, C, PG, 8, TS, 0, q);
-                        } else {  // pair (a, bb): M_a Z_bb + M_bb Z_a + M_ab x
-                            const int a = pair_a, bb = pair_b;
-                            add_Ma(cf, S, C, a);
-                            if (a == bb) {
-                                coef_scale(cf, 2.0);
-                                apply_terms<NT>(D, cf, C, PG, 8, TS, 1 + a, q);
-                            } else {
-                                apply_terms<NT>(D, cf, C, PG, 8, TS, 1 + bb, q);
-                                coef_zero(cf);
-                                add_Ma(cf, S, C, bb);
-                                apply_terms<NT>(D, cf, C, PG, 8, TS, 1 + a, q);
+                {
+                    if (role == W_FWD && couple) {
+                        // The couplings of a forward tile are one small GEMM on the tensor pipe: Zp[8 rows][n] += W[8][K] T[K][n],
+                        // T = the table rows (k = table t * nsrc + source row vs: G Z_vs, A_i Z_vs, B_i Z_vs, D_j Z_vs for the
+                        // nsrc = 1 + np leading rows), W = this node's coefficients (CT) placed at the (row, source) pairs
+                        // of the jet recurrence: first-order row a <- (x; dM/dtheta_a); pair row (a, b) <- (Z_b; M_a), (Z_a; M_b),
+                        // (x; M_ab).  The accumulators are the state tile itself.
+                        const int v = 8 * tile + row8;
+                        const bool rowact = v >= 1 && v < nvecF;
+                        if (packed) {
+#pragma unroll
+                            for (int ks = 0; ks < kPackedKS; ++ks) {
+                                if (4 * ks < Kdim) {
+                                    const int co = pk[ks] & kNoCoef;
+                                    const double a = co != kNoCoef ? CT[co] : 0.0;
+                                    const double* brow = PG + (pk[ks] >> 13) + row8;
+#pragma unroll
+                                    for (int nt = 0; nt < NT; ++nt) dmma(Zp[0][nt][0], Zp[0][nt][1], a, brow[8 * nt]);
+                                }
                             }
-                            coef_zero(cf);
-                            add_Mab(cf, S, C, a, bb);
-                            apply_terms<NT>(D, cf, C, PG, 8, TS, 0, q);
+                        } else
+                        for (int k0 = 0; k0 < Kdim; k0 += 4) {
+                            const int k = k0 + q;                       // A fragment: column k; B fragment: row k (same lane%4)
+                            const int kc = k < Kdim ? k : Kdim - 1;
+                            const int t = kc / nsrc, vs = kc - t * nsrc;
+                            double a = 0.0;
+                            if (rowact && k < Kdim) {
+                                int slot = -1;
+                                if (v <= np) slot = vs == 0 ? 0 : -1;
+                                else if (vs == 1 + pair_b) slot = 0;
+                                else if (vs == 1 + pair_a) slot = 1;    // only reached when a != b
+                                else if (vs == 0) slot = 2;
+                                if (slot >= 0) a = CT[((size_t)(v - 1) * 3 + slot) * KCr + t];
+                            }
+                            const double* brow = PG + (size_t)(t * 8 + vs) * TS + row8;  // PG and Pb are back to back: table t, row vs
+#pragma unroll
+                            for (int nt = 0; nt < NT; ++nt) dmma(Zp[0][nt][0], Zp[0][nt][1], a, brow[8 * nt]);
                         }
-                    }
-                } else if (role == W_ADJ) {
-                    const int v = row8;
-                    if (v >= 1 && v <= np) {  // d lambda^a = M' lambda^a + (M^a)' lambda
-                        const Scal S = Sa;
-                        Coef cf;
-                        coef_zero(cf);
-                        add_Ma(cf, S, C, v - 1);
-                        apply_terms<NT>(D, cf, C, PGa, 1, n, 0, q);
+                    } else if (role == W_ADJ) {
+                        // d lambda^a = M' lambda^a + (M^a)' lambda: the same small GEMM with K = the tables (G' lambda, basis' lambda)
+                        const bool rowact = row8 >= 1 && row8 <= np;
+                        for (int k0 = 0; k0 < KCr; k0 += 4) {
+                            const int k = k0 + q, kc = k < KCr ? k : KCr - 1;
+                            const double a = rowact && k < KCr ? CT[((size_t)(nrowsF + row8 - 1) * 3) * KCr + k] : 0.0;
+                            const double* brow = PGa + (size_t)kc * n + row8;  // PGa and PT are back to back
+#pragma unroll
+                            for (int nt = 0; nt < NT; ++nt) dmma(Zp[0][nt][0], Zp[0][nt][1], a, brow[8 * nt]);
+                        }
                     }
                 }
 #ifdef DTO_TDB_PROFILE
-                if (lane == 0 && blockIdx.x == 0) g_tdb_prof[blockIdx.y][warp][7] += (unsigned long long)(D[0][0][0] != 12345.678 ? clock64() - tc0 : 0);
+                if (lane == 0 && blockIdx.x == 0) g_tdb_prof[blockIdx.y][warp][7] += (unsigned long long)(Zp[0][0][0] != 12345.678 ? clock64() - tc0 : 0);
 #endif
                 if (role != W_IDLE) {
-                    if (qq == 0) {
+                    if (qq < nk) {  // Zp holds z_{q+1}: the tiles trade names
 #pragma unroll
                         for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
                             for (int j = 0; j < 2; ++j) {
-                                Zp[0][nt][j] = Zc[0][nt][j];
-                                Zc[0][nt][j] = fma(h, D[0][nt][j], Zc[0][nt][j]);
-                            }
-                    } else if (qq < nk) {
-#pragma unroll
-                        for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-                            for (int j = 0; j < 2; ++j) {
-                                const double znew = fma(2.0 * h, D[0][nt][j], Zp[0][nt][j]);
+                                const double znew = Zp[0][nt][j];
                                 Zp[0][nt][j] = Zc[0][nt][j];
                                 Zc[0][nt][j] = znew;
                             }
-                    } else {
+                    } else {  // Gragg smoothing: 1/2 (z_n + z_{n-1} + h f(z_n)), weighted into the extrapolation
 #pragma unroll
                         for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
-                            for (int j = 0; j < 2; ++j)
-                                AccS[(nt * 2 + j) * 32 + lane] += wk[k] * 0.5 * (Zc[0][nt][j] + Zp[0][nt][j] + h * D[0][nt][j]);
+                            for (int j = 0; j < 2; ++j) AccS[(nt * 2 + j) * 32 + lane] += wk[k] * 0.5 * (Zc[0][nt][j] + Zp[0][nt][j]);
                     }
                 }
 #ifdef DTO_TDB_PROFILE
@@ -793,18 +973,19 @@ __global__ void __launch_bounds__(8 * 32, 1)
     }
     for (int i = threadIdx.x; i < nbs * nn; i += blockDim.x) Bs[i] = basis_global(I, i / nn, nn)[i % nn];
     auto prefetch_drift = [&](double* Gd) {
-        for (int blk = warp; blk < nn / 64; blk += nwarps) {
+        for (int blk = (nn / 64) * warp / nwarps; blk < (nn / 64) * (warp + 1) / nwarps; ++blk) {
             const int p = sw<NT>((blk / NT) * 8 + (lane >> 2), (blk % NT) * 8 + 2 * (lane & 3));
             const unsigned dst = (unsigned)__cvta_generic_to_shared(Gd + p);
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(I.Grm + p) : "memory");
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
+    const int eb0 = (nn / 64) * warp / nwarps, eb1 = (nn / 64) * (warp + 1) / nwarps;  // this warp's 8 x 8 blocks of G
     auto assemble = [&](double* Gd, const Scal& S) {
         asm volatile("cp.async.wait_all;" ::: "memory");
-        if (nbs == nbasis && m <= 2 && nc == 0) assemble_generators<NT, true, 2, 0>(Gd, nullptr, Bs, I, S, S, m, nc, false, warp, nwarps, lane);
-        else if (nbs == nbasis) assemble_generators<NT, true, kMaxM, kMaxC>(Gd, nullptr, Bs, I, S, S, m, nc, false, warp, nwarps, lane);
-        else assemble_generators<NT, false, kMaxM, kMaxC>(Gd, nullptr, Bs, I, S, S, m, nc, false, warp, nwarps, lane);
+        if (nbs == nbasis && m <= 2 && nc == 0) assemble_generators<NT, true, 2, 0>(Gd, nullptr, Bs, I, S, S, m, nc, false, eb0, eb1, lane);
+        else if (nbs == nbasis) assemble_generators<NT, true, kMaxM, kMaxC>(Gd, nullptr, Bs, I, S, S, m, nc, false, eb0, eb1, lane);
+        else assemble_generators<NT, false, kMaxM, kMaxC>(Gd, nullptr, Bs, I, S, S, m, nc, false, eb0, eb1, lane);
     };
 
     const int n_items = P.nI * P.batch;
@@ -826,9 +1007,9 @@ __global__ void __launch_bounds__(8 * 32, 1)
         NodeIter ahead{0, 0, 0, steps, K};
         if (warp == nwarps - 1 && lane == 0) {
             NodeIter it = ahead;
-            make_scal(I, zk, zk1, P.dt_off, it.time(), scal[0]);
+            make_scal(I, zk, zk1, P.dt_off, it.time(), scal[0], nullptr);
             it.next();
-            if (it.valid()) make_scal(I, zk, zk1, P.dt_off, it.time(), scal[1]);
+            if (it.valid()) make_scal(I, zk, zk1, P.dt_off, it.time(), scal[1], nullptr);
         }
         ahead.next();
         ahead.next();  // the node whose scalars are computed during right-hand side 0
@@ -896,7 +1077,7 @@ __global__ void __launch_bounds__(8 * 32, 1)
                         }
                     }
                     if (!asm_first && !last) assemble(Gnext, scal[(e + 1) & 1]);  // G of the next node, behind this node's products
-                    if (warp == nwarps - 1 && lane == 0 && ahead.valid()) make_scal(I, zk, zk1, P.dt_off, ahead.time(), scal[e & 1]);
+                    if (warp == nwarps - 1 && lane == 0 && ahead.valid()) make_scal(I, zk, zk1, P.dt_off, ahead.time(), scal[e & 1], nullptr);
                     ahead.next();
                     __syncthreads();
                     if (!last) prefetch_drift(Gcur);  // free now: drift entries of the node after next
@@ -940,7 +1121,9 @@ bool make_plan(const DInt& I, bool want_jac, bool want_hess, Plan& pl) {
     pl.warps = pl.TF + pl.TE + pl.TA;
     if (pl.warps > 8) {
         const int half = std::max(pl.TF + pl.TA, pl.TE);
-        const char* env = getenv("DTO_B200_TDB_SPLIT");  // A/B switch: 0 = one 16-warp CTA (128 registers) instead of two 8-warp CTAs (255 registers)
+        // two kernels of 8-warp CTAs (forward + adjoint tiles / propagator tiles, 255 registers each); DTO_B200_TDB_SPLIT=0 = one
+        // 16-warp CTA at 128 registers (measured slower: 11.1 against 9.2 ms at c3)
+        const char* env = getenv("DTO_B200_TDB_SPLIT");
         const bool allow_split = !(env && env[0] == '0');
         if (half <= 8 && pl.TE > 0 && (allow_split || pl.warps > kMaxWarpsT)) {
             pl.split = 1;
@@ -952,9 +1135,13 @@ bool make_plan(const DInt& I, bool want_jac, bool want_hess, Plan& pl) {
         }
     }
     pl.warps = std::max(pl.warps, 4);  // idle warps still help assembling the generators
+    if (!pl.split && pl.warps > 8) pl.warps = kMaxWarpsT;  // the spare warps take the basis products and the assembly
     const size_t FR = (size_t)(n / 8) * 2 * 32, nbasis = 2 * m + nc;
-    const size_t doubles = 2 * (size_t)n * n + 4 * sizeof(Scal) / sizeof(double) + FR + n + 8 * (n + 2) + nbasis * 8 * (n + 2) + n + nbasis * n + 12;
-    const size_t budget = 226 * 1024;
+    // coupling coefficient table + node values (2 buffers x forward/adjoint)
+    const size_t ct = (((size_t)(nvecF > 1 ? nvecF - 1 : 0) + (want_hess ? np : 0)) * 3 * (1 + 2 * m + nc) + 1) / 2 * 2 +
+                      4 * (((size_t)nv_count(m, nc) + 1) / 2 * 2);
+    const size_t doubles = 2 * (size_t)n * n + 4 * sizeof(Scal) / sizeof(double) + FR + n + 8 * (n + 4) + nbasis * 8 * (n + 4) + n + nbasis * n + 12 + ct;
+    const size_t budget = 227 * 1024 - 64;
     if (doubles * sizeof(double) > budget) return false;
     pl.nbs = (int)std::min<size_t>(nbasis, (budget - doubles * sizeof(double)) / ((size_t)n * n * sizeof(double)));
     pl.smem = (doubles + (size_t)pl.nbs * n * n) * sizeof(double);
