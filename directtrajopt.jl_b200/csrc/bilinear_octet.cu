@@ -24,6 +24,7 @@
 //
 // Math as in bilinear_persistent.cu: jet recurrence of the scaled Taylor series of
 // exp(dt G(u)) x, reference: src/integrators/bilinear_integrator.jl:81 differentiated by ForwardDiff (:111-161).
+#include <math.h>
 #include <stdlib.h>
 
 #include "dto_internal.h"
@@ -137,7 +138,7 @@ __device__ __forceinline__ void mul_t(Mat<NT>& out, const Mat<NT>& V, const Mat<
 // generators straight from global memory (DInt::bfrag, 2 (M+1) NT^2 KB-sized blocks that stay in L1/L2) instead of the
 // CTA's shared copy.
 template <int NT, int M, bool PP>
-__global__ void __launch_bounds__(NT == 1 ? 256 : 128)
+__global__ void __launch_bounds__(NT == 1 ? 256 : 128, (NT == 1 && M <= 2) ? 2 : 1)  // n = 8, m <= 2: 128 registers, two CTAs of 8 warps per SM
     bilinear_octet_kernel(DProb P, int ii, const double* __restrict__ Z, const double* __restrict__ mu, double* __restrict__ g,
                           double* __restrict__ jac, int want_jac, int want_hess, int jets, int split) {
     constexpr int n = 8 * NT, nn = n * n, J = 1 + M + M * (M + 1) / 2;
@@ -190,9 +191,9 @@ __global__ void __launch_bounds__(NT == 1 ? 256 : 128)
             return id < nItems;
         }
     };
-    // CTA-minor numbering of the warps: the octets of a partial last round spread over all SMs (a few warps each, running
-    // at their latency bound) instead of filling the first SMs (12 500 intervals per rank on eight GPUs are 1.32 rounds)
-    const long long warp0 = (long long)(threadIdx.x >> 5) * gridDim.x + blockIdx.x;
+    // CTA-major numbering: the warps of a CTA work on neighbouring octets (a CTA-minor numbering, which would spread a partial
+    // last round over all SMs, costs 20 % at c5: the writes of one SM then scatter over the whole output)
+    const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const long long nWarps = (long long)gridDim.x * (blockDim.x >> 5);
 
     // Work units.  Normally one octet = one unit (forward, adjoint and propagator phases back to back in one warp).  When a
@@ -670,7 +671,11 @@ bool launch_octet_pp(const DProb& P, int ii, const double* Z, const double* mu, 
     const int nPh = (f.jets != DTO_JETS_USE ? 1 : 0) + (f.want_jac ? 1 : 0) + (f.want_hess ? 1 : 0);
     const long long resident = (long long)sms * per_sm * wpc;  // warps in flight
     const char* env = getenv("DTO_B200_OCTET_SPLIT");           // A/B switch: 0 = never, 1 = always
-    const bool split = nPh > 1 && (env ? env[0] == '1' : octs < 6 * resident);
+    // split when it recovers more than a tenth of the launch: idle share of the last round of whole octets against that of
+    // the last round of single phases (a third of the granularity; the split form itself is ~8 % slower per octet)
+    auto idle = [&](double rounds) { return (ceil(rounds) - rounds) / ceil(rounds); };
+    const double rounds = (double)octs / (double)resident;
+    const bool split = nPh > 1 && (env ? env[0] == '1' : idle(rounds) - idle(rounds * nPh) > 0.1);
     const long long units = split ? octs * nPh : octs;
     const int grid = (int)std::max<long long>(1, std::min<long long>((long long)sms * per_sm, (units + wpc - 1) / wpc));
     kern<<<grid, threads, smem, st>>>(P, ii, Z, mu, f.want_g ? g : nullptr, jac, f.want_jac ? 1 : 0, f.want_hess ? 1 : 0, f.jets, split ? 1 : 0);
