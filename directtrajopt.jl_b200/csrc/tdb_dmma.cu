@@ -1134,7 +1134,7 @@ bool make_plan(const DInt& I, bool want_jac, bool want_hess, Plan& pl) {
             if (pl.warps > kMaxWarpsT) return false;
         }
     }
-    pl.warps = std::max(pl.warps, 4);  // idle warps still help assembling the generators
+    pl.warps = std::max(pl.warps, n >= 32 ? 8 : 4);  // idle warps still help assembling the generators (and take the basis mat-vecs)
     if (!pl.split && pl.warps > 8) pl.warps = kMaxWarpsT;  // the spare warps take the basis products and the assembly
     const size_t FR = (size_t)(n / 8) * 2 * 32, nbasis = 2 * m + nc;
     // coupling coefficient table + node values (2 buffers x forward/adjoint)
@@ -1165,7 +1165,7 @@ void launch_nt_w(const DProb& P, int ii, const double* Z, const double* mu, doub
         return;
     }
     // split interval: forward + adjoint tiles in one kernel, the propagator tiles in the double-buffered one
-    kern<<<ctas, std::min(MAXW, std::max(pl.TF + pl.TA + 3, 4)) * 32, pl.smem, st>>>(P, ii, Z, mu, f.want_g ? g : nullptr, jac, f.want_jac ? 1 : 0,
+    kern<<<ctas, std::min(MAXW, std::max(pl.TF + pl.TA + 3, I.n >= 32 ? 8 : 4)) * 32, pl.smem, st>>>(P, ii, Z, mu, f.want_g ? g : nullptr, jac, f.want_jac ? 1 : 0,
                                                                     f.want_hess ? 1 : 0, 8, pl.TF, 0, pl.TA, 0, pl.nbs, I.tdb_scratch);
     const int n = I.n, nbasis = 2 * I.m + I.n_carrier;
     const size_t fixed = (2 * (size_t)n * n + 2 * sizeof(Scal) / sizeof(double) + 12) * sizeof(double);
