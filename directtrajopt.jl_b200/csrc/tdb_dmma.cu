@@ -310,6 +310,54 @@ __device__ __forceinline__ void mma_tile_axpy(double (&R)[1][NT][2], const doubl
     }
 }
 
+// R += s * (V * M) for one tile with M in the forward (row-major, swizzled) layout, i.e. the product with the TRANSPOSE of the
+// matrix mma_tile_axpy would use: B fragments are read by columns (two 8-byte loads per pair of k-steps, 4-way bank conflicts).
+// Only the adjoint tile uses it -- one warp -- in exchange for a generator assembly without the transposed, scattered stores.
+template <int NT>
+__device__ __forceinline__ void mma_tile_axpy_T(double (&R)[1][NT][2], const double (&v)[1][NT][2], const double* __restrict__ M, double s, int lane,
+                                                double* __restrict__ tab, bool to_tab) {
+    constexpr int n = 8 * NT, NH = (NT + 1) / 2;
+    const int row8 = lane >> 2, q = lane & 3;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        double acc[NH][2];
+#pragma unroll
+        for (int x = 0; x < NH; ++x) acc[x][0] = acc[x][1] = 0.0;
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+            const int k0 = 8 * t + 2 * q;  // k-steps (t, 0) and (t, 1) contract over states k0 and k0 + 1: rows of M
+            const double* r0 = M + k0 * n;
+            const double* r1 = r0 + n;
+            double b0[NH], b1[NH];
+#pragma unroll
+            for (int x = 0; x < NH; ++x)
+                if (half * NH + x < NT) {
+                    const int col = 8 * (half * NH + x) + row8;
+                    b0[x] = r0[(NT % 2 == 0) ? col : col];                   // even row: not swizzled
+                    b1[x] = r1[(NT % 2 == 0) ? (col ^ 8) : col];             // odd row: 8-double blocks swapped pairwise
+                }
+#pragma unroll
+            for (int x = 0; x < NH; ++x)
+                if (half * NH + x < NT) dmma(acc[x][0], acc[x][1], v[0][t][0], b0[x]);
+#pragma unroll
+            for (int x = 0; x < NH; ++x)
+                if (half * NH + x < NT) dmma(acc[x][0], acc[x][1], v[0][t][1], b1[x]);
+        }
+#pragma unroll
+        for (int x = 0; x < NH; ++x) {
+            const int nt = half * NH + x;
+            if (nt < NT) {
+                if (to_tab) {
+                    tab[8 * nt] = acc[x][0];
+                    tab[8 * nt + 1] = acc[x][1];
+                }
+                R[0][nt][0] = fma(s, acc[x][0], R[0][nt][0]);
+                R[0][nt][1] = fma(s, acc[x][1], R[0][nt][1]);
+            }
+        }
+    }
+}
+
 // basis matrix b (0..2m+nc-1) of the swizzled row-major copies
 __device__ __forceinline__ const double* basis_global(const DInt& I, int b, int nn) {
     if (b < I.m) return I.Asw + (size_t)b * nn;
@@ -317,7 +365,7 @@ __device__ __forceinline__ const double* basis_global(const DInt& I, int b, int 
     return I.Dsw + (size_t)(b - 2 * I.m) * nn;
 }
 
-// G(tau) -> Gf and G(1 - tau)' -> Ga from the drift entries already sitting in Gf (cp.async) and the basis matrices.
+// G(tau) -> Gf and G(1 - tau) -> Ga (both in the forward layout) from the drift entries already sitting in Gf (cp.async) and the basis matrices.
 // A 4 x 8 block of the matrix per warp pass: few bank conflicts on both the straight and the transposed store.
 // CACHED: every basis matrix is in the shared cache Bs (plain offset arithmetic in the inner loop).  The node's
 // coefficients u_i cos, u_i sin, carrier cos are lifted into registers first (MM drives, CC carriers at most):
@@ -369,10 +417,7 @@ __device__ __forceinline__ void assemble_generators(double* Gf, double* Ga, cons
                 va1 = fma(ae[j], d.y, va1);
             }
         *reinterpret_cast<double2*>(Gf + p) = make_double2(vf0, vf1);
-        if (want_adj) {
-            Ga[sw<NT>(c, r)] = va0;
-            Ga[sw<NT>(c + 1, r)] = va1;
-        }
+        if (want_adj) *reinterpret_cast<double2*>(Ga + p) = make_double2(va0, va1);  // same layout: the adjoint tile reads it by columns
     }
 }
 
@@ -677,13 +722,24 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
                 if (TA > 0 && matvec_first) adjoint_basis_products();
                 if (couple) {
                     // basis products of the leading forward tile, one per warp, starting at the last (idle helper) warps
+                    // one per forward warp (their own product is the only other work they have in this phase), the rest from the
+                    // top.  The scheduler of forward warp 0 also carries the adjoint tile (warp TF): its basis product goes, in two
+                    // output halves, to the next two warps instead (2.5 tile products per scheduler at most instead of 3).
+                    const bool halves0 = TA > 0 && TF >= 2 && nwarps >= TF + 3 && NT >= 2;
                     for (int bi = 0; bi < nbasis; ++bi) {
-                        // one per forward warp (their own product is the only other work they have in this phase), the rest from the top
-                        if ((bi < TF ? bi : nwarps - 1 - (bi - TF) % nwarps) != warp) continue;
+                        int own_half = -1;  // -1: both output halves
+                        if (bi == 0 && halves0) {
+                            if (warp == TF + 1) own_half = 0;
+                            else if (warp == TF + 2) own_half = 1;
+                            else continue;
+                        } else if ((bi < TF ? bi : nwarps - 1 - (bi - TF) % nwarps) != warp) {
+                            continue;
+                        }
                         const double* Mb = basis_ptr(bi);
                         double* out = Pb + (size_t)bi * 8 * TS + (size_t)row8 * TS + 2 * q;
 #pragma unroll
                         for (int half = 0; half < 2; ++half) {
+                            if (own_half >= 0 && half != own_half) continue;
                             constexpr int NH = (NT + 1) / 2;
                             double acc[NH][2];
 #pragma unroll
@@ -727,7 +783,8 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
                     const bool pubG = role == W_FWD && tile == 0 && couple;
                     const bool pubA = role == W_ADJ && row8 == 0;
                     double* tab = pubG ? PG + row8 * TS + 2 * q : PGa + 2 * q;
-                    mma_tile_axpy<NT>(Zp, Zc, role == W_ADJ ? Ga : Gf, hs * Sf.dt, lane, tab, pubG || pubA);
+                    if (role == W_ADJ) mma_tile_axpy_T<NT>(Zp, Zc, Ga, hs * Sf.dt, lane, tab, pubA);
+                    else mma_tile_axpy<NT>(Zp, Zc, Gf, hs * Sf.dt, lane, tab, pubG);
                 }
                 if (TA > 0 && !matvec_first) adjoint_basis_products();
 #ifdef DTO_TDB_PROFILE
