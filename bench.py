@@ -334,6 +334,15 @@ def run_workload(args, workload, steps, warmup, *, rank, world, local_rank, full
                                          np.array_equal(oh.cpu().numpy(), ref_out[2][b * ev.nnz_hessian:(b + 1) * ev.nnz_hessian]))
         one.close()
 
+    if args.no_e2e:
+        if full:
+            sampler.stop_flag.set()
+            sampler.join()
+        if rank == 0:
+            print(json.dumps({"workload": workload, "ms_per_step": dev_ms / steps, "kernel_ms": k1_ms / max(k1_n, 1), "gpu_launches": int(launches),
+                              "note": "--no-e2e: device-resident loop only"}), flush=True)
+        ev.close()
+        return None
     # ---- end-to-end through the host-pointer C ABI ------------------------------------------------
     # Host buffers as a solver holds them: page-locked Z / mu inputs, its own Jacobian / Hessian value arrays registered
     # once with the handle (dto_register_outputs: structural constants written once, value-dependent entries per call).
@@ -513,6 +522,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-register", action="store_true", help="e2e with plain (unregistered) output buffers")
     ap.add_argument("--no-extra", action="store_true", help="skip the embedded c3/c4/c5 runs of the default workload")
+    ap.add_argument("--no-e2e", action="store_true", help="device-resident loop only (profiling: the ncu launch list of one step)")
     ap.add_argument("--scalar-reduce", default="peer", choices=["peer", "nccl"], help="knot shards: objective/violation reduction")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -558,7 +568,7 @@ def main():
         line = run_workload(args, "c2", args.steps, args.warmup, full=True, **kw)
         if rank == 0 and extra:
             line["extra"] = extra
-    if rank == 0:
+    if rank == 0 and line is not None:
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

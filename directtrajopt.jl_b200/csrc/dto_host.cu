@@ -3,6 +3,7 @@
 // (/root/reference/src/solvers/evaluator.jl:99-288), device residency, and the C ABI of
 // include/dto_b200.h.  No torch types, no CPU compute fallback: every value comes from a kernel.
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -173,6 +174,7 @@ struct dto_handle {
     bool reg_jac_sparse = false, reg_hess_sparse = false;  // constants are in place
     int jac_skip_ok = 0;             // length of the constant head of the inner knots' Jacobian columns (0: no common layout)
     bool fill_threads_ok = false;    // enough host threads to zero-fill an unregistered Hessian buffer faster than PCIe delivers it
+    int trace = 0;                   // DTO_B200_TRACE=1: device timeline of every host-pointer call on stderr
     bool spec_jac_inflight = false;  // a speculative delivery of the Jacobian into reg_jac is on the copy stream
     bool spec_jac_done = false;      // reg_jac holds the resident iterate's Jacobian (once the copy stream has drained)
 };
@@ -832,6 +834,7 @@ extern "C" int dto_create(const dto_problem_desc* d, dto_handle** out) {
         return fail_create(h, DTO_ERR_ALLOC, "device allocation failed (work buffers)");
     {
         // iterate cache: DTO_B200_ITERATE_CACHE=0 disables it, =lazy computes only what each callback asks for
+        if (const char* tr = getenv("DTO_B200_TRACE")) h->trace = atoi(tr);
         const char* env = getenv("DTO_B200_ITERATE_CACHE");
         h->cache_mode = env && strcmp(env, "0") == 0 ? 0 : (env && strcmp(env, "lazy") == 0 ? 2 : 1);
         if (h->cache_mode && cudaHostAlloc((void**)&h->hZpin, sizeof(double) * B * (size_t)P.n_vars_local, cudaHostAllocDefault) != cudaSuccess) {
@@ -1331,6 +1334,34 @@ struct FillGuard {
     }
 };
 
+// DTO_B200_TRACE: timestamps (CUDA events) of the stages of one host-pointer call, printed relative to its first event
+struct Tracer {
+    bool on;
+    std::vector<std::pair<const char*, cudaEvent_t>> ev;
+    explicit Tracer(bool o) : on(o) {}
+    void mark(const char* what, cudaStream_t st) {
+        if (!on) return;
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return;
+        cudaEventRecord(e, st);
+        ev.emplace_back(what, e);
+    }
+    ~Tracer() {
+        if (!on || ev.empty()) return;
+        cudaDeviceSynchronize();
+        std::string line = "[dto trace]";
+        for (size_t i = 1; i < ev.size(); ++i) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ev[0].second, ev[i].second);
+            char buf[96];
+            snprintf(buf, sizeof(buf), " %s %.0fus", ev[i].first, ms * 1e3);
+            line += buf;
+        }
+        fprintf(stderr, "%s\n", line.c_str());
+        for (auto& e : ev) cudaEventDestroy(e.second);
+    }
+};
+
 // What one host-pointer call computes on the device (`passes`, `comp_obj`) and what it delivers to the caller (the non-null
 // host pointers).  Z (and mu) are already on their way to the device.  A quantity that is delivered but not computed is
 // resident from an earlier callback on the same iterate.  `spec_jac`: the Jacobian computed by this call also goes to the
@@ -1416,6 +1447,8 @@ static int eval_core(dto_handle* h, double sigma, const EvalFlags* passes, int n
         return DTO_OK;
     };
 
+    Tracer tr(h->trace != 0);
+    tr.mark("start", h->stream);
     FillGuard guard;
     if (fill_h || fill_j) {
         // host threads write the structural constants into the caller's buffers while the GPU computes
@@ -1505,17 +1538,35 @@ static int eval_core(dto_handle* h, double sigma, const EvalFlags* passes, int n
                 return DTO_ERR_CUDA;
             }
             CUDA_TRY(h, cudaEventRecord(ev, h->stream));
+            tr.mark("range-computed", h->stream);
+            if (spec_jac && c + 2 == bounds.size()) {
+                // last range of a speculative delivery: the outputs this call was asked for (a few hundred KB) go to the copy
+                // engine BEFORE the last block of the Jacobian nobody is waiting for yet
+                if (J) CUDA_TRY(h, cudaMemcpyAsync(J, h->dJ, sizeof(double) * B, cudaMemcpyDeviceToHost, h->stream));
+                if (grad) CUDA_TRY(h, cudaMemcpyAsync(grad, h->dgrad, sizeof(double) * B * P.n_grad_local, cudaMemcpyDeviceToHost, h->stream));
+                if (g) CUDA_TRY(h, cudaMemcpyAsync(g, h->dg, sizeof(double) * B * P.n_cons_local, cudaMemcpyDeviceToHost, h->stream));
+                J = grad = g = nullptr;
+                cudaEvent_t ev2 = h->chunk_events_at(bounds.size());
+                if (!ev2) {
+                    h->err = "cudaEventCreate failed";
+                    return DTO_ERR_CUDA;
+                }
+                CUDA_TRY(h, cudaEventRecord(ev2, h->stream));
+                ev = ev2;
+            }
             CUDA_TRY(h, cudaStreamWaitEvent(h->copy_stream, ev, 0));
             // columns of knots [kc0, kc1): their own-interval rows were written by this range, the previous-interval rows
             // of knot kc0 by the range before
             if (jac_now && (rc = deliver_jac(Pr.kc0, Pr.kc1, h->copy_stream)) != DTO_OK) return rc;
             if (hess_now && (rc = deliver_hess(Pr.kc0, Pr.kc1, h->copy_stream)) != DTO_OK) return rc;
+            tr.mark("range-delivered", h->copy_stream);
         }
         CUDA_TRY(h, cudaGetLastError());
     }
     if (J) CUDA_TRY(h, cudaMemcpyAsync(J, h->dJ, sizeof(double) * B, cudaMemcpyDeviceToHost, h->stream));
     if (grad) CUDA_TRY(h, cudaMemcpyAsync(grad, h->dgrad, sizeof(double) * B * P.n_grad_local, cudaMemcpyDeviceToHost, h->stream));
     if (g) CUDA_TRY(h, cudaMemcpyAsync(g, h->dg, sizeof(double) * B * P.n_cons_local, cudaMemcpyDeviceToHost, h->stream));
+    tr.mark("main-stream-done", h->stream);
     // everything is enqueued: the calling thread writes its share of the structural zeros while the GPU works
     if (guard.z) {
         guard.z->finish();
