@@ -80,7 +80,7 @@ __device__ __forceinline__ Series choose_series(double theta) {
         const double ths = theta / s.stages;
         double term = ths;
         int T = 1;
-        while (term > 1.3877787807814457e-17 && T < 60) {
+        while (term > 1.1102230246251565e-16 && T < 60) {  // 2^-53, as series_tables.cuh
             ++T;
             term *= ths / T;
         }

@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(32) bilinear_generic_kernel(DProb P, int ii, c
         s_stages = theta > 4.0 ? (int)ceil(theta * 0.25) : 1;
         double ths = theta / s_stages, term = ths;
         T = 1;
-        while (term > 1.3877787807814457e-17 && T < 60) {
+        while (term > 1.1102230246251565e-16 && T < 60) {  // 2^-53, as series_tables.cuh
             ++T;
             term *= ths / T;
         }

@@ -669,7 +669,7 @@ bool launch_octet_pp(const DProb& P, int ii, const double* Z, const double* mu, 
     const long long nIc = std::min(P.kc1, P.nI) - P.kc0, items = (long long)P.batch * nIc;
     const long long octs = PP ? (long long)P.batch * ((nIc + 7) / 8) : (items + 7) / 8, wpc = threads / 32;
     const int nPh = (f.jets != DTO_JETS_USE ? 1 : 0) + (f.want_jac ? 1 : 0) + (f.want_hess ? 1 : 0);
-    const long long resident = (long long)sms * per_sm * wpc;  // warps in flight
+    const long long resident = (long long)std::max(1, sms - P.reserve_sms) * per_sm * wpc;  // warps in flight
     const char* env = getenv("DTO_B200_OCTET_SPLIT");           // A/B switch: 0 = never, 1 = always
     // split when it recovers more than a tenth of the launch: idle share of the last round of whole octets against that of
     // the last round of single phases (a third of the granularity; the split form itself is ~8 % slower per octet)
@@ -677,7 +677,7 @@ bool launch_octet_pp(const DProb& P, int ii, const double* Z, const double* mu, 
     const double rounds = (double)octs / (double)resident;
     const bool split = nPh > 1 && (env ? env[0] == '1' : idle(rounds) - idle(rounds * nPh) > 0.1);
     const long long units = split ? octs * nPh : octs;
-    const int grid = (int)std::max<long long>(1, std::min<long long>((long long)sms * per_sm, (units + wpc - 1) / wpc));
+    const int grid = (int)std::max<long long>(1, std::min<long long>((long long)std::max(1, sms - P.reserve_sms) * per_sm, (units + wpc - 1) / wpc));
     kern<<<grid, threads, smem, st>>>(P, ii, Z, mu, f.want_g ? g : nullptr, jac, f.want_jac ? 1 : 0, f.want_hess ? 1 : 0, f.jets, split ? 1 : 0);
     ++*launches;
     return true;

@@ -1236,7 +1236,7 @@ bool launch_variant(const DProb& P, int ii, const double* Z, const double* mu, d
     const long long items = (long long)P.batch * (std::min(P.kc1, P.nI) - P.kc0);
     const long long roles = (f.jets != DTO_JETS_USE ? 1 : 0) + (f.want_jac ? 1 : 0) + (f.want_hess ? 1 : 0);
     const long long want_ctas = (items * roles + W - 1) / W;
-    const int grid = (int)std::max<long long>(1, std::min<long long>(sms, want_ctas));
+    const int grid = (int)std::max<long long>(1, std::min<long long>(std::max(1, sms - P.reserve_sms), want_ctas));
     if (cudaMemsetAsync(I.wq, 0, 3 * sizeof(unsigned long long), st) != cudaSuccess) return false;
     // small items (n <= 16) are fetched several at a time: the atomic's round trip is as long as the item itself
     const long long per_warp = items / ((long long)grid * W);

@@ -102,6 +102,7 @@ struct DProb {
     int first_has_cross;  // shard does not start at knot 1: its first knot still owns a cross block
     int any_cross;        // some integrator produces cross-knot Hessian entries (tdbilinear order 1)
     int analytic_fused;   // index+1 of the bilinear integrator whose kernel also writes the derivative integrators' rows (0: analytic_kernel does)
+    int reserve_sms;      // host side: SMs the persistent interval kernels leave free for small kernels running beside them on another stream
     int n_int, n_obj, n_con;
     int Dsum;       // sum of x_dim over integrators
     long long n_vars_local;   // nK * z + global_dim  (stride of one problem in the local Z buffer)
