@@ -106,11 +106,12 @@ struct Ctx {
     double* S2;
     int lane, want_jac, want_hess;
     int jets;          // EvalFlags::jets
+    const double2* plan;  // per-interval series plan (series_plan.cu) or nullptr
 };
 
 // G(u) = G_0 + sum_i u_i G_i in the shared layout; returns ||G(u)||_1 (identical arithmetic in every role)
 template <int NT>
-__device__ __forceinline__ double build_generator(const Ctx<NT>& c, const double (&uu)[kMaxDrives], int m) {
+__device__ __forceinline__ double build_generator(const Ctx<NT>& c, const double (&uu)[kMaxDrives], int m, bool need_norm = true) {
     constexpr int n = 8 * NT, nn = n * n;
     for (int p = c.lane; p < nn; p += 32) {
         double v = c.Gs[p];
@@ -120,6 +121,7 @@ __device__ __forceinline__ double build_generator(const Ctx<NT>& c, const double
         c.Gu[p] = v;
     }
     __syncwarp();
+    if (!need_norm) return 0.0;  // the series plan of this interval is already known (series_plan.cu)
     double cmax = 0.0;
     for (int k = c.lane; k < n; k += 32) {
         double s1 = 0.0;
@@ -127,6 +129,16 @@ __device__ __forceinline__ double build_generator(const Ctx<NT>& c, const double
         cmax = fmax(cmax, s1);
     }
     return warp_max(cmax);
+}
+
+// series plan of interval (b, kk): from the pre-computed plan, else from ||dt G(u)||_1
+template <int NT>
+__device__ __forceinline__ Series interval_series(const Ctx<NT>& c, int b, int kk, double dt, const double (&uu)[kMaxDrives], int m) {
+    if (c.plan != nullptr) {
+        build_generator<NT>(c, uu, m, false);
+        return choose_series(c.plan[(long long)b * c.P->nI + kk]);
+    }
+    return choose_series(fabs(dt) * build_generator<NT>(c, uu, m));
 }
 
 // y_i = G_i' a for every drive on the FP64 FMA pipe (one vector times m matrices would waste 7/8 of a DMMA tile).
@@ -200,7 +212,7 @@ __device__ __forceinline__ void role_forward(const Ctx<NT>& c, int b, int kk, co
     double uu[kMaxDrives];
 #pragma unroll
     for (int i = 0; i < kMaxDrives; ++i) uu[i] = i < m ? zk[I.u_off + i] : 0.0;
-    const Series ser = choose_series(fabs(dt) * build_generator<NT>(c, uu, m));
+    const Series ser = interval_series<NT>(c, b, kk, dt, uu, m);
     const long long mu_off = (long long)b * P.n_cons_local + I.row_off + (long long)kk * n;
     const bool deriv = c.want_jac || c.want_hess || c.jets == DTO_JETS_STORE;
     const double* Gu = c.Gu;
@@ -428,7 +440,7 @@ __device__ __forceinline__ void role_exp_series(const Ctx<NT>& c, int b, int kk)
     double uu[kMaxDrives];
 #pragma unroll
     for (int i = 0; i < kMaxDrives; ++i) uu[i] = i < m ? zk[I.u_off + i] : 0.0;
-    const Series ser = choose_series(fabs(dt) * build_generator<NT>(c, uu, m));
+    const Series ser = interval_series<NT>(c, b, kk, dt, uu, m);
     double* jp = c.jac + (long long)b * P.nnz_jac_local;
     const long long own_off = jac_own_off(P, kk, I.doff, n);
     for (int c0 = 0; c0 < n; c0 += 8 * MT) {
@@ -501,17 +513,26 @@ __device__ __forceinline__ void role_exp_ps(const Ctx<NT>& c, int b, int kk) {
     double uu[kMaxDrives];
 #pragma unroll
     for (int i = 0; i < kMaxDrives; ++i) uu[i] = i < m ? zk[I.u_off + i] : 0.0;
-    const double theta = fabs(dt) * build_generator<NT>(c, uu, m);
+    double theta, alpha;
+    if (c.plan != nullptr) {
+        build_generator<NT>(c, uu, m, false);
+        const double2 pl = c.plan[(long long)b * P.nI + kk];
+        alpha = pl.x;
+        theta = pl.y;
+    } else {
+        theta = alpha = fabs(dt) * build_generator<NT>(c, uu, m);
+    }
     int sq = 0, nb = 1;
     double scale = dt;
     if (theta < 1e8) {
         double th = theta;
         while (th > 1.5) {
             th *= 0.5;
+            alpha *= 0.5;
             scale *= 0.5;
             ++sq;
         }
-        nb = (taylor_terms(th) + 2) / 3;
+        nb = (taylor_terms(fmin(th, alpha)) + 2) / 3;  // polynomial degree from alpha_2(A / 2^sq), squarings from ||A||_1
     }
     double* A = c.Gu;
     for (int p = lane; p < nn; p += 32) A[p] *= scale;
@@ -705,20 +726,25 @@ __device__ __forceinline__ void role_adjoint(const Ctx<NT>& c, int b, int kk) {
 #pragma unroll
     for (int i = 0; i < kMaxDrives; ++i) uu[i] = i < m ? zk[I.u_off + i] : 0.0;
     // ||G(u)||_1 with the arithmetic of build_generator (same series length as the forward role), then G(u)'
-    double cmax = 0.0;
-    for (int k = lane; k < n; k += 32) {
-        double s1 = 0.0;
-        for (int s = 0; s < n; ++s) {
-            const int p = sw<NT>(s, k);
-            double v = c.Gs[p];
+    Series ser;
+    if (c.plan != nullptr) {
+        ser = choose_series(c.plan[(long long)b * P.nI + kk]);
+    } else {
+        double cmax = 0.0;
+        for (int k = lane; k < n; k += 32) {
+            double s1 = 0.0;
+            for (int s = 0; s < n; ++s) {
+                const int p = sw<NT>(s, k);
+                double v = c.Gs[p];
 #pragma unroll
-            for (int i = 0; i < kMaxDrives; ++i)
-                if (i < m) v = fma(uu[i], c.Gs[(1 + i) * nn + p], v);
-            s1 += fabs(v);
+                for (int i = 0; i < kMaxDrives; ++i)
+                    if (i < m) v = fma(uu[i], c.Gs[(1 + i) * nn + p], v);
+                s1 += fabs(v);
+            }
+            cmax = fmax(cmax, s1);
         }
-        cmax = fmax(cmax, s1);
+        ser = choose_series(fabs(dt) * warp_max(cmax));
     }
-    const Series ser = choose_series(fabs(dt) * warp_max(cmax));
     for (int e = lane; e < nn; e += 32) {
         const int r = e / n, col = e % n;  // G(r, col) -> G'(col, r)
         const int p = sw<NT>(r, col);
@@ -846,6 +872,7 @@ __global__ void __launch_bounds__(max_warps<NT>() * 32, 1)
     c.want_jac = want_jac;
     c.want_hess = want_hess;
     c.jets = jets;
+    c.plan = I.plan;
     const bool ps = warp < nE;  // this warp owns the two spare matrices of the Paterson-Stockmeyer propagator
 
     // forward rows: r = mt*8 + row8 : 0 -> x, 1+i -> d/du_i, 1+m+p -> d2/(du_i du_j); where the drive products go
@@ -1145,6 +1172,7 @@ __global__ void __launch_bounds__(max_warps<NT>() * 32, 1)
     c.lane = lane;
     c.want_jac = c.want_hess = 0;
     c.jets = DTO_JETS_NONE;
+    c.plan = nullptr;  // the products are called on their own: no plan of this iterate
     const unsigned long long nItems = (unsigned long long)P.batch * (unsigned long long)P.nI;
     while (true) {
         unsigned long long id0 = 0;

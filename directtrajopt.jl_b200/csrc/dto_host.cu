@@ -857,6 +857,44 @@ extern "C" int dto_create(const dto_problem_desc* d, dto_handle** out) {
             any = true;
             ok = ok && P.in[i].kind == DTO_INT_BILINEAR && P.in[i].variant >= DTO_VAR_PERSISTENT;
         }
+        {
+            // per-interval series plans of the bilinear interval kernels (series_plan.cu); DTO_B200_SERIES_PLAN=0: size the
+            // series from ||dt G(u)||_1 as round 1 did
+            const char* sp = getenv("DTO_B200_SERIES_PLAN");
+            if (!(sp && strcmp(sp, "0") == 0))
+                for (int i = 0; i < P.n_int; ++i) {
+                    DInt& I = P.in[i];
+                    if (I.kind != DTO_INT_BILINEAR || I.variant != DTO_VAR_PERSISTENT) continue;  // n = 8 / 16 (octet): a plan costs what it saves
+                    const dto_integrator_desc& sd = d->integrators[i];
+                    const int n = I.n, nmat = I.m + 1, npairs = nmat * (nmat + 1) / 2;
+                    const size_t nn = (size_t)n * n;
+                    if (sd.G_batch_stride != 0 || series_plan_smem(n, I.m) == 0) continue;  // shared sets that fit shared memory
+                    // symmetrised pair products S_ab = G_a G_b + G_b G_a (S_aa = G_a^2), row-major, from the column-major input
+                    std::vector<double> Sp(npairs * nn);
+                    {
+                        const size_t q = 0;
+                        const double* Gq = sd.G;  // column-major: G_a(r, c) = Gq[a nn + c n + r]
+                        int p = 0;
+                        for (int a = 0; a < nmat; ++a)
+                            for (int bb = a; bb < nmat; ++bb, ++p)
+                                for (int r = 0; r < n; ++r)
+                                    for (int c = 0; c < n; ++c) {
+                                        double v = 0.0;
+                                        for (int k = 0; k < n; ++k) {
+                                            v += Gq[a * nn + (size_t)k * n + r] * Gq[bb * nn + (size_t)c * n + k];
+                                            if (bb != a) v += Gq[bb * nn + (size_t)k * n + r] * Gq[a * nn + (size_t)c * n + k];
+                                        }
+                                        Sp[(q * npairs + p) * nn + (size_t)r * n + c] = v;
+                                    }
+                    }
+                    I.Spair = dev_upload(h, Sp.data(), Sp.size());
+                    I.plan = (const double2*)dev_upload<double>(h, nullptr, 2 * B * (size_t)std::max(P.nI, 1));
+                    if (!I.plan || !I.Spair) {
+                        cudaGetLastError();
+                        I.plan = nullptr;
+                    }
+                }
+        }
         if (ok && any) {
             for (int i = 0; i < P.n_int && ok; ++i) {
                 DInt& I = P.in[i];
@@ -1224,6 +1262,12 @@ static int eval_range(dto_handle* h, const DProb& P, const double* dZ, double si
     return DTO_OK;
 }
 
+// Series plans of the iterate in dZ (whole local trajectory), before the first interval kernel that reads them
+static void launch_plans(dto_handle* h, const DProb& P, const double* dZ) {
+    for (int i = 0; i < P.n_int; ++i)
+        if (P.in[i].kind == DTO_INT_BILINEAR && P.in[i].plan != nullptr) launch_series_plan(P, i, dZ, h->stream, &h->launches);
+}
+
 static int check_eval_args(dto_handle* h, const double* dmu, const double* dhess) {
     if (dhess && !h->eval_hessian) {
         h->err = "evaluator was created with eval_hessian = false";
@@ -1249,6 +1293,7 @@ static int run_eval(dto_handle* h, const double* dZ, double sigma, const double*
     // The objective / gradient kernels are independent of the interval kernels and tiny (launch- and latency-bound): they run
     // on a second stream BESIDE the interval kernel, which leaves one SM free for them (0.7 % of its throughput against
     // ~17 us of serial kernels at c2).
+    if (f.want_g || f.want_jac || f.want_hess) launch_plans(h, P, dZ);
     bool overlap = h->overlap_objective && (dJ || dgrad) && (f.want_g || f.want_jac || f.want_hess) && P.nI >= 256;
     if (overlap && !h->aux_stream) {
         if (cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -1484,6 +1529,8 @@ static int eval_core(dto_handle* h, double sigma, const EvalFlags* passes, int n
 
     Tracer tr(h->trace != 0);
     tr.mark("start", h->stream);
+    // series plans of this iterate (a Hessian pass from stored jets re-uses the plans of the pass that stored them)
+    if ((comp_g || comp_jac || comp_hess) && !(n_passes == 1 && passes[0].jets == DTO_JETS_USE)) launch_plans(h, P, h->dZ);
     FillGuard guard;
     if (fill_h || fill_j) {
         // host threads write the structural constants into the caller's buffers while the GPU computes

@@ -40,6 +40,10 @@ struct DInt {
     //   d2(Ex)/(du_a du_b) (a <= b, row-major over the upper triangle) | G G E x | G_i E x (i < m) | G d(Ex)/du_i (i < m)
     double* jets;
     int jet_stride;
+    // bilinear (persistent / octet variants): per-interval series plan {alpha, theta1} written by series_plan_kernel
+    // before the interval kernels of an iterate (series_plan.cu); nullptr: the kernels size the series from ||dt G(u)||_1
+    const double2* plan;
+    const double* Spair;  // symmetrised pair products G_a G_b + G_b G_a (a <= b, row-major; shared generator sets only)
     unsigned long long* wq;  // bilinear, persistent variant: three work-queue counters (FWD, EXP, ADJ)
 };
 
@@ -221,6 +225,8 @@ bool launch_bilinear_product(const DProb& P, int ii, const double* Z, const doub
                              long long* launches);
 void launch_analytic_product(const DProb& P, const double* Z, const double* w, double* y, bool transpose, cudaStream_t st,
                              long long* launches);
+size_t series_plan_smem(int n, int m);
+bool launch_series_plan(const DProb& P, int ii, const double* Z, cudaStream_t st, long long* launches);
 bool tdb_available();
 bool tdb_dmma_supported(const DInt& I);
 bool launch_tdb_dmma(const DProb& P, int ii, const double* Z, const double* mu, double* g, double* jac, EvalFlags f, cudaStream_t st,
