@@ -253,10 +253,10 @@ def run_workload(args, workload, steps, warmup, *, rank, world, local_rank, full
         ev.eval_all_dev(zp, sigma, dmu.data_ptr(), dJ.data_ptr(), dgrad.data_ptr(), dg.data_ptr(), djac.data_ptr(), dhess.data_ptr())
         if linked:
             # the only exchange of the sharded path besides the halo knot: objective (sum) and violation (max)
-            ev.violation_dev(dg.data_ptr(), dviol.data_ptr())
-            if args.scalar_reduce == "peer":
-                ev.allreduce_scalars_dev(dJ.data_ptr(), dviol.data_ptr())
+            if args.scalar_reduce == "peer":  # violation of the shard's rows + exchange through the peer windows: one kernel
+                ev.shard_scalars_dev(dg.data_ptr(), dJ.data_ptr(), dviol.data_ptr())
             else:
+                ev.violation_dev(dg.data_ptr(), dviol.data_ptr())
                 dist.all_reduce(dJ, op=dist.ReduceOp.SUM)
                 dist.all_reduce(dviol, op=dist.ReduceOp.MAX)
 
@@ -489,7 +489,7 @@ def run_workload(args, workload, steps, warmup, *, rank, world, local_rank, full
         if shard_ok is not None:
             line["shard_matches_single_gpu"] = shard_bad == 0.0
         if linked:
-            line["scalar_reduce"] = "exchange windows over NVLink peer memory (dto_allreduce_scalars_dev)" if args.scalar_reduce == "peer" else "NCCL all_reduce x2"
+            line["scalar_reduce"] = "violation + exchange windows over NVLink peer memory in one kernel (dto_shard_scalars_dev)" if args.scalar_reduce == "peer" else "NCCL all_reduce x2"
         if full:
             line["clocks"] = sampler.summary()
             line["wall_s_timed_region"] = t_wall

@@ -103,6 +103,7 @@ SYMBOLS = [
     ("dto_shard_link_local", C.c_int, [C.POINTER(_H), C.c_int]),
     ("dto_upload_dev", C.c_int, [_H, C.c_void_p]),
     ("dto_allreduce_scalars_dev", C.c_int, [_H, C.c_void_p, C.c_void_p]),
+    ("dto_shard_scalars_dev", C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("dto_local_Z", C.c_void_p, [_H]),
     ("dto_launch_count", C.c_int64, [_H]),
     ("dto_last_download_bytes", C.c_int64, [_H]),

@@ -129,6 +129,8 @@ struct dto_handle {
     unsigned long long epoch = 0;         // iterates uploaded since the link was made
     unsigned long long waited_epoch = 0;  // the halo of this iterate has been waited for
     unsigned long long scal_seq = 0;
+    bool link_ipc = false;                      // linked across processes: the publish kernel also waits for the right neighbour's knot
+    unsigned long long* d_scal_scratch = nullptr;  // {violation bits, arrival counter} of shard_scalars_kernel
     long long launches = 0;
     long long last_d2h_bytes = 0;
     // host-pointer path: outputs leave over PCIe while later knot ranges are still being computed
@@ -1351,7 +1353,7 @@ extern "C" int dto_synchronize(dto_handle* h) {
 
 // ---- iterate cache -----------------------------------------------------------------------------------
 // 1: Z is the resident iterate (nothing moved); 0: a new iterate was uploaded (every cached quantity dropped); < 0: error
-static int publish_iterate(dto_handle* h);
+static int publish_iterate(dto_handle* h, const double* src);
 static int ensure_iterate(dto_handle* h, const double* Z, bool force = false) {
     const DProb& P = h->P;
     const size_t bytes = sizeof(double) * (size_t)P.batch * (size_t)P.n_vars_local;
@@ -1374,7 +1376,7 @@ static int ensure_iterate(dto_handle* h, const double* Z, bool force = false) {
     } else {
         CUDA_TRY(h, cudaMemcpyAsync(h->dZ, Z, bytes, cudaMemcpyHostToDevice, h->stream));
     }
-    const int rc = publish_iterate(h);
+    const int rc = publish_iterate(h, h->dZ);
     return rc < 0 ? rc : 0;
 }
 
@@ -1401,9 +1403,10 @@ extern "C" int dto_upload_dev(dto_handle* h, const double* dZ) {
     CUDA_TRY(h, cudaSetDevice(h->device));
     h->have_obj = h->have_g = h->have_jac = h->have_jets = false;
     h->z_valid = false;  // the host copy no longer describes the resident iterate
+    if (h->link_rank >= 0 && h->link_world > 1) return publish_iterate(h, dZ);  // copy + publish (+ wait) in one kernel
     if (dZ != h->dZ)
         CUDA_TRY(h, cudaMemcpyAsync(h->dZ, dZ, sizeof(double) * (size_t)P.batch * (size_t)P.n_vars_local, cudaMemcpyDeviceToDevice, h->stream));
-    return publish_iterate(h);
+    return publish_iterate(h, h->dZ);
 }
 
 // joins the zero-fill workers on every exit path (they write into the caller's buffer)
@@ -1972,6 +1975,7 @@ static void drop_links(dto_handle* h) {
     cudaGetLastError();
     h->link_rank = -1;
     h->link_world = 0;
+    h->link_ipc = false;
     h->P.halo = nullptr;
 }
 
@@ -1998,6 +2002,7 @@ extern "C" int dto_shard_link(dto_handle* h, int rank, int world, const void* ha
         h->peer_win[r] = (XWin*)p;
         h->peer_ipc[r] = true;
     }
+    h->link_ipc = world > 1;
     return finish_link(h, rank, world);
 }
 
@@ -2031,14 +2036,20 @@ extern "C" int dto_shard_link_local(dto_handle* const* hs, int world) {
     return DTO_OK;
 }
 
-// A new iterate is on its way into dZ (stream order): acknowledge the right neighbour's previous knot, push this shard's
-// first knot to the left neighbour.
-static int publish_iterate(dto_handle* h) {
+// A new iterate is on its way into dZ (stream order; src != dZ: the publish kernel copies it there): acknowledge the right
+// neighbour's previous knot, push this shard's first knot to the left neighbour and -- shards linked across processes -- wait
+// for the right neighbour's knot in the same kernel (every rank has its own host thread, so the spinning kernel cannot keep
+// the neighbour from launching its push; shards linked inside one process wait in prepare_halo instead).
+static int publish_iterate(dto_handle* h, const double* src) {
     if (h->link_rank < 0) return DTO_OK;
     ++h->epoch;
     XWin* left = h->link_rank > 0 ? h->peer_win[h->link_rank - 1] : nullptr;
     XWin* right = h->link_rank + 1 < h->link_world ? h->peer_win[h->link_rank + 1] : nullptr;
-    if (left || right) launch_shard_publish(h->xwin, left, right, h->dZ, h->P.z, h->epoch, h->stream, &h->launches);
+    const long long n = (long long)h->P.batch * h->P.n_vars_local;
+    if (left || right || src != h->dZ) {
+        launch_shard_publish(h->xwin, left, right, h->dZ, src, n, h->P.z, h->epoch, h->link_ipc, h->stream, &h->launches);
+        if (h->link_ipc) h->waited_epoch = h->epoch;
+    }
     CUDA_TRY(h, cudaGetLastError());
     return DTO_OK;
 }
@@ -2083,6 +2094,27 @@ extern "C" int dto_allreduce_scalars_dev(dto_handle* h, double* dJ, double* dvio
     CUDA_TRY(h, cudaSetDevice(h->device));
     ++h->scal_seq;
     launch_scalar_exchange(h->xwin, h->d_peer_win, h->link_rank, h->link_world, h->scal_seq, dJ, dviol, h->stream, &h->launches);
+    CUDA_TRY(h, cudaGetLastError());
+    return DTO_OK;
+}
+
+extern "C" int dto_shard_scalars_dev(dto_handle* h, const double* dg, double* dJ, double* dviol) {
+    if (!h || !dg || !dJ || !dviol) return DTO_ERR_INVALID;
+    if (h->link_rank < 0 || h->P.batch != 1) {
+        h->err = "dto_shard_scalars_dev: the shard is not linked";
+        return DTO_ERR_INVALID;
+    }
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    if (!h->d_scal_scratch) {
+        void* p = nullptr;
+        CUDA_TRY(h, cudaMalloc(&p, 2 * sizeof(unsigned long long)));
+        h->allocs.push_back(p);
+        CUDA_TRY(h, cudaMemsetAsync(p, 0, 2 * sizeof(unsigned long long), h->stream));
+        h->d_scal_scratch = (unsigned long long*)p;
+    }
+    ++h->scal_seq;
+    launch_shard_scalars(h->xwin, h->d_peer_win, h->link_rank, h->link_world, h->scal_seq, h->P.n_cons_local, dg, h->d_row_is_eq,
+                         h->d_scal_scratch, dJ, dviol, h->stream, &h->launches);
     CUDA_TRY(h, cudaGetLastError());
     return DTO_OK;
 }

@@ -174,11 +174,14 @@ struct XWin {
     double scal[2][DTO_MAX_RANKS][4];  // [seq & 1][rank] = {objective, violation, seq (as u64), -}
     double halo[2];                    // really [2][z]: allocated with the window
 };
-void launch_shard_publish(XWin* own, XWin* left, XWin* right, const double* first_knot, int z, unsigned long long epoch, cudaStream_t st,
-                          long long* launches);
+void launch_shard_publish(XWin* own, XWin* left, XWin* right, double* dst, const double* src, long long n, int z,
+                          unsigned long long epoch, bool wait_right, cudaStream_t st, long long* launches);
 void launch_shard_wait(XWin* own, unsigned long long epoch, cudaStream_t st, long long* launches);
 void launch_scalar_exchange(XWin* own, XWin* const* peers, int rank, int world, unsigned long long seq, double* J, double* viol,
                             cudaStream_t st, long long* launches);
+
+void launch_shard_scalars(XWin* own, XWin* const* peers, int rank, int world, unsigned long long seq, long long n_cons, const double* g,
+                          const int* row_is_eq, unsigned long long* scratch, double* J, double* viol, cudaStream_t st, long long* launches);
 
 // variants of the bilinear kernel
 enum { DTO_VAR_GENERIC = 0, DTO_VAR_DMMA = 1, DTO_VAR_PERSISTENT = 2, DTO_VAR_OCTET = 3 };

@@ -423,6 +423,10 @@ class Evaluator:
     def allreduce_scalars_dev(self, dJ, dviol):
         _lib.check(self._lib.dto_allreduce_scalars_dev(self._h, dJ, dviol), self._h)
 
+    def shard_scalars_dev(self, dg, dJ, dviol):
+        """Violation of this shard's residuals ``dg`` and the (sum, max) exchange with the other shards in one kernel."""
+        _lib.check(self._lib.dto_shard_scalars_dev(self._h, dg, dJ, dviol), self._h)
+
     @property
     def local_Z_ptr(self):
         return self._lib.dto_local_Z(self._h)

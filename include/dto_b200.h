@@ -265,8 +265,9 @@ int dto_synchronize(dto_handle* h);
  * traffic, no ordering requirement.  LINKED shards (one per rank of a single box; CUDA IPC across processes) exchange
  * through windows in each other's HBM instead, inside the evaluation stream:
  *   - after uploading iterate e a shard pushes its first knot into the left neighbour's window and publishes e there;
- *     the left neighbour's kernels of iterate e wait for that flag on the device and read the knot from the window.  The
- *     reader acknowledges when it moves on, so a rank runs at most one iterate ahead of the neighbour reading its knot.
+ *     the left neighbour's kernels of iterate e wait for that flag on the device and read the knot from the window (shards
+ *     linked across processes: the upload's own kernel copies, pushes and waits -- one launch).  The reader acknowledges
+ *     when it moves on, so a rank runs at most one iterate ahead of the neighbour reading its knot.
  *   - dto_allreduce_scalars_dev: objective (sum) and violation (max) of all shards with one kernel per rank that
  *     stores into every peer's window and spins on its own (rank-ordered sum: identical bits on every rank; no NCCL).
  * Protocol: EVERY rank uploads EVERY iterate exactly once, with dto_upload (host Z slice) or dto_upload_dev (device);
@@ -283,6 +284,9 @@ int dto_shard_link_local(dto_handle* const* handles, int world);
 int dto_upload_dev(dto_handle* h, const double* dZ);
 /* in place: dJ[0] <- sum over shards, dviol[0] <- max over shards; enqueues on dto_stream(h) */
 int dto_allreduce_scalars_dev(dto_handle* h, double* dJ, double* dviol);
+/* the same with the shard's violation computed from its residuals dg in the SAME kernel (instead of dto_violation_dev +
+ * dto_allreduce_scalars_dev): dJ[0] <- sum over shards of dJ[0], dviol[0] <- max over shards */
+int dto_shard_scalars_dev(dto_handle* h, const double* dg, double* dJ, double* dviol);
 /* device pointer of this shard's resident Z buffer ([z_begin, z_halo_end) of the global Z) */
 double* dto_local_Z(dto_handle* h);
 

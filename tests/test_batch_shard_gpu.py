@@ -167,7 +167,7 @@ def test_linked_shards_follow_a_changing_iterate():
             sh.upload(Zloc)
             locs.append(Zloc)
         g, jac, hess = np.full_like(gw, np.nan), np.full_like(jacw, np.nan), np.full_like(hessw, np.nan)
-        dJs, dVs = [], []
+        dJs, dVs, dGs = [], [], []
         for sh, Zloc in zip(shards, locs):  # phase 2: the five callbacks, separately
             rows, jpos, hpos = sh.shard_maps()
             gl, jl, hl = np.empty(sh.n_constraints), np.empty(sh.nnz_jacobian), np.empty(sh.nnz_hessian)
@@ -180,6 +180,7 @@ def test_linked_shards_follow_a_changing_iterate():
             viol = float(np.where(l2 == 0, np.abs(gl), np.maximum(gl, 0)).max()) if gl.size else 0.0
             dJs.append(torch.tensor([J], dtype=torch.float64, device="cuda"))
             dVs.append(torch.tensor([viol], dtype=torch.float64, device="cuda"))
+            dGs.append(torch.from_numpy(gl).cuda())
         assert np.array_equal(g, gw) and np.array_equal(jac, jacw) and np.array_equal(hess, hessw), it
         torch.cuda.synchronize()
         for sh, dJ, dV in zip(shards, dJs, dVs):  # the scalar exchange: all ranks enqueue, then all synchronise
@@ -190,5 +191,15 @@ def test_linked_shards_follow_a_changing_iterate():
         tot = [float(t.item()) for t in dJs]
         assert all(t == tot[0] for t in tot) and abs(tot[0] - Jw[0]) <= 1e-13 * max(1.0, abs(Jw[0]))
         assert all(float(v.item()) == vw for v in dVs)
+        # the fused form: violation of the shard's residuals + exchange in one kernel (dto_shard_scalars_dev), twice in a row
+        for rep in range(2):
+            dJ2 = [torch.tensor([float(sh.eval_objective(Zloc))], dtype=torch.float64, device="cuda") for sh, Zloc in zip(shards, locs)]
+            dV2 = [torch.full((1,), -1.0, dtype=torch.float64, device="cuda") for _ in shards]
+            torch.cuda.synchronize()
+            for sh, dG, dJ, dV in zip(shards, dGs, dJ2, dV2):
+                sh.shard_scalars_dev(dG.data_ptr(), dJ.data_ptr(), dV.data_ptr())
+            for sh in shards:
+                sh.synchronize()
+            assert all(float(t.item()) == tot[0] for t in dJ2) and all(float(v.item()) == vw for v in dV2)
     for e in shards + [whole]:
         e.close()

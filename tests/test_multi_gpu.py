@@ -60,6 +60,19 @@ def _worker(rank, world, port, q):
         ev.allreduce_scalars_dev(dJ.data_ptr(), dV.data_ptr())
         ev.synchronize()
         assert abs(dJ.item() - Jt) <= 1e-13 * max(1.0, abs(Jt)) and dV.item() == vt
+        # violation + exchange in one kernel, device-resident iterate uploaded through the fused copy + publish + wait kernel
+        dZl = torch.from_numpy(np.nan_to_num(Zloc)).to(torch.device("cuda", rank))
+        dg = torch.from_numpy(g).to(torch.device("cuda", rank))
+        dJ2 = torch.tensor([float(J[0])], dtype=torch.float64, device=torch.device("cuda", rank))
+        dV2 = torch.full((1,), -1.0, dtype=torch.float64, device=torch.device("cuda", rank))
+        torch.cuda.synchronize()
+        ev.upload_dev(dZl.data_ptr())
+        g2 = torch.empty_like(dg)
+        ev.eval_all_dev(ev.local_Z_ptr, 1.2, 0, 0, 0, g2.data_ptr(), 0, 0)
+        ev.shard_scalars_dev(g2.data_ptr(), dJ2.data_ptr(), dV2.data_ptr())
+        ev.synchronize()
+        assert np.array_equal(g2.cpu().numpy(), g)
+        assert dJ2.item() == dJ.item() and dV2.item() == vt
         res.append((grad, g, jac, hess, Jt, vt))
     q.put((rank, rows, jpos, hpos, sh.z_begin, sh.z_end, res))
     dist.barrier()

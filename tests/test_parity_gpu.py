@@ -53,6 +53,18 @@ def zero_drive_problem(n=16, N=4):
                                     dto.BilinearIntegrator(lambda u: G0 + u[0] * np.zeros((n, n)), "x", "u", traj))
 
 
+def nonnormal_problem(n=32, N=6, scale=30.0, m=2):
+    """Strongly non-normal generators (strictly upper-triangular drift, ||dt G||_1 ~ 3 but ||(dt G)^2||^(1/2) far smaller):
+    the series plan (series_plan.cu) shortens the Taylor series the most here."""
+    rng = np.random.default_rng(11)
+    G0 = scale * np.triu(rng.standard_normal((n, n)), 1) / n
+    Gd = [0.2 * rng.standard_normal((n, n)) / np.sqrt(n) for _ in range(m)]
+    traj = dto.NamedTrajectory({"x": rng.standard_normal((n, N)), "u": 0.3 * rng.standard_normal((m, N)), "dt": np.full(N, 0.1)},
+                               timestep="dt", controls=("u", "dt"), bounds={"dt": (0.01, 0.5)})
+    return dto.DirectTrajOptProblem(traj, dto.QuadraticRegularizer("u", traj, 1.0) + dto.MinimumTimeObjective(traj, D=1.0),
+                                    dto.BilinearIntegrator((G0, Gd), "x", "u", traj))
+
+
 PROBLEMS = {
     "readme_c1": lambda: pt.readme_problem(N=50),
     "catalogue": catalogue_problem,
@@ -79,6 +91,8 @@ PROBLEMS = {
     "n32_theta3": lambda: pt.scaled_problem(N=4, state_dim=32, n_controls=3, generator_scale=3.0),
     "n16_theta12": lambda: pt.scaled_problem(N=4, state_dim=16, n_controls=2, generator_scale=12.0),
     "zero_drive_n16": zero_drive_problem,
+    "nonnormal_n32": nonnormal_problem,
+    "nonnormal_n24_big": lambda: nonnormal_problem(n=24, N=4, scale=90.0, m=3),
     # global (non-time-varying) variables: all four global term kinds, the reference's test functions
     "global": lambda: pt.global_problem(N=9),
     "global_ref_fixture": lambda: pt.global_problem(N=6, with_goal=False),
@@ -383,6 +397,28 @@ def test_tdbilinear_variants_agree(monkeypatch):
         ev.close()
     for a, b in zip(outs[""], outs["generic"]):
         assert relerr(a, b) <= 1e-12
+
+
+def test_series_plan_matches_norm_based_series(monkeypatch):
+    """The series plan (Taylor length from ||A^2||^(1/2), series_plan.cu) only drops terms below the 2^-53 tail: results
+    agree with the ||A||_1-sized series to round-off, also for non-normal generators where the plan saves the most."""
+    for mk in (nonnormal_problem, lambda: pt.quantum_gate_problem(N=9, levels=16, n_drives=4),
+               lambda: pt.scaled_problem(N=5, state_dim=32, n_controls=3, generator_scale=3.0)):
+        prob = mk()
+        rng = np.random.default_rng(2)
+        Z = prob.trajectory.vec() * (1 + 0.05 * rng.standard_normal(prob.trajectory.vec().size))
+        outs = {}
+        for plan in ("1", "0"):
+            monkeypatch.setenv("DTO_B200_SERIES_PLAN", plan)
+            ev = dto.Evaluator(prob)
+            assert ev.kernel_variant(0) == "persistent"
+            mu = np.random.default_rng(5).random(ev.n_constraints)
+            bufs = [np.full(ev.n_constraints, np.nan), np.full(ev.nnz_jacobian, np.nan), np.full(ev.nnz_hessian, np.nan)]
+            ev.eval_all(Z, 1.0, mu, None, None, *bufs)
+            outs[plan] = bufs
+            ev.close()
+        for a, b in zip(outs["1"], outs["0"]):
+            assert relerr(a, b) <= 1e-13
 
 
 def test_host_pipeline_matches_single_pass(monkeypatch):
