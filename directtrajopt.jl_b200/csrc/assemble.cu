@@ -119,9 +119,13 @@ __device__ __forceinline__ double group_sum(double v, unsigned gmask) {
     return v;
 }
 
+// Narrow knots are register-limited at the compiler's own allocation (68 registers: 3 CTAs of 256 threads per SM, a third
+// of the warp slots, too few loads in flight for a latency-bound stream-out): capped to 5 (GS = 8) / 4 (GS = 16) CTAs per SM
+// (c5: 560 -> 477 us, 0.62 of the measured HBM copy rate).
 template <int GS>
-__global__ void hessian_assemble_kernel(DProb P, const double* __restrict__ Z, double sigma, const double* __restrict__ mu,
-                                        double* __restrict__ hess, int warps_per_cta, long long total) {
+__global__ void __launch_bounds__(256, GS == 8 ? 5 : (GS == 16 ? 4 : 1))
+hessian_assemble_kernel(DProb P, const double* __restrict__ Z, double sigma, const double* __restrict__ mu, double* __restrict__ hess,
+                        int warps_per_cta, long long total) {
     extern __shared__ double sm[];
     constexpr int GPW = 32 / GS;  // groups per warp
     const int z = P.z, lane = threadIdx.x & 31, tid = lane % GS, nt = GS;
