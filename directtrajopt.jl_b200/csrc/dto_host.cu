@@ -868,30 +868,12 @@ extern "C" int dto_create(const dto_problem_desc* d, dto_handle** out) {
                     DInt& I = P.in[i];
                     if (I.kind != DTO_INT_BILINEAR || I.variant != DTO_VAR_PERSISTENT) continue;  // n = 8 / 16 (octet): a plan costs what it saves
                     const dto_integrator_desc& sd = d->integrators[i];
-                    const int n = I.n, nmat = I.m + 1, npairs = nmat * (nmat + 1) / 2;
-                    const size_t nn = (size_t)n * n;
-                    if (sd.G_batch_stride != 0 || series_plan_smem(n, I.m) == 0) continue;  // shared sets that fit shared memory
-                    // symmetrised pair products S_ab = G_a G_b + G_b G_a (S_aa = G_a^2), row-major, from the column-major input
-                    std::vector<double> Sp(npairs * nn);
-                    {
-                        const size_t q = 0;
-                        const double* Gq = sd.G;  // column-major: G_a(r, c) = Gq[a nn + c n + r]
-                        int p = 0;
-                        for (int a = 0; a < nmat; ++a)
-                            for (int bb = a; bb < nmat; ++bb, ++p)
-                                for (int r = 0; r < n; ++r)
-                                    for (int c = 0; c < n; ++c) {
-                                        double v = 0.0;
-                                        for (int k = 0; k < n; ++k) {
-                                            v += Gq[a * nn + (size_t)k * n + r] * Gq[bb * nn + (size_t)c * n + k];
-                                            if (bb != a) v += Gq[bb * nn + (size_t)k * n + r] * Gq[a * nn + (size_t)c * n + k];
-                                        }
-                                        Sp[(q * npairs + p) * nn + (size_t)r * n + c] = v;
-                                    }
-                    }
-                    I.Spair = dev_upload(h, Sp.data(), Sp.size());
+                    if (sd.G_batch_stride != 0 || series_plan_smem(I.n, I.m) == 0) continue;  // shared sets that fit shared memory
+                    std::vector<float> pm;
+                    series_plan_matrices(I.n, I.m, sd.G, pm);
+                    I.planmat = dev_upload(h, pm.data(), pm.size());
                     I.plan = (const double2*)dev_upload<double>(h, nullptr, 2 * B * (size_t)std::max(P.nI, 1));
-                    if (!I.plan || !I.Spair) {
+                    if (!I.plan || !I.planmat) {
                         cudaGetLastError();
                         I.plan = nullptr;
                     }

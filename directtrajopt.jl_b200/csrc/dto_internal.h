@@ -43,7 +43,7 @@ struct DInt {
     // bilinear (persistent / octet variants): per-interval series plan {alpha, theta1} written by series_plan_kernel
     // before the interval kernels of an iterate (series_plan.cu); nullptr: the kernels size the series from ||dt G(u)||_1
     const double2* plan;
-    const double* Spair;  // symmetrised pair products G_a G_b + G_b G_a (a <= b, row-major; shared generator sets only)
+    const float* planmat;  // series_plan.cu: FP32 [G_0..G_m | pair products | norms] (shared generator sets only)
     unsigned long long* wq;  // bilinear, persistent variant: three work-queue counters (FWD, EXP, ADJ)
 };
 
@@ -229,6 +229,7 @@ bool launch_bilinear_product(const DProb& P, int ii, const double* Z, const doub
 void launch_analytic_product(const DProb& P, const double* Z, const double* w, double* y, bool transpose, cudaStream_t st,
                              long long* launches);
 size_t series_plan_smem(int n, int m);
+void series_plan_matrices(int n, int m, const double* Gcm, std::vector<float>& out);
 bool launch_series_plan(const DProb& P, int ii, const double* Z, cudaStream_t st, long long* launches);
 bool tdb_available();
 bool tdb_dmma_supported(const DInt& I);
