@@ -273,7 +273,29 @@ hessian_assemble_kernel(DProb P, const double* __restrict__ Z, double sigma, con
                     }
                 __syncwarp(gmask);
             }
-            // knot objectives are added by knot_objective_hessian_kernel (one thread per hyper-dual pair)
+            if ((O.kind == DTO_OBJ_KNOT || O.kind == DTO_OBJ_GLOBAL_KNOT) && O.nvk > 0 && P.knot_side != nullptr) {
+                // the pairs w Q d2l/dv_a dv_c of a listed knot were evaluated by knot_objective_pairs_kernel (one thread per
+                // hyper-dual pair, beside the interval kernels); lane-private (a, c - a) cursor over the packed upper triangle
+                const int j = O.knot_to_own[kl];
+                if (j >= 0) {
+                    const int nv = O.nvk, npairs = nv * (nv + 1) / 2;
+                    const double* sd = P.knot_side + (long long)b * P.side_stride + O.side_off + (long long)j * npairs;
+                    int a = 0, p = tid;
+                    while (a < nv && p >= nv - a) {
+                        p -= nv - a;
+                        ++a;
+                    }
+                    for (int e = tid; e < npairs; e += nt) {
+                        sym_add(diag, z, O.var_offs[a], O.var_offs[a + p], sigma * sd[e]);
+                        p += nt;
+                        while (a < nv && p >= nv - a) {
+                            p -= nv - a;
+                            ++a;
+                        }
+                    }
+                }
+                __syncwarp(gmask);
+            }
         }
     }
 
@@ -308,11 +330,11 @@ hessian_assemble_kernel(DProb P, const double* __restrict__ Z, double sigma, con
     }
 }
 
-// Knot-objective Hessians: sigma * w * Q * Hess l, one thread per (problem, listed knot, variable pair), added to the
-// already assembled COO values (a terminal cost on a 32- or 64-dimensional state is one knot with ~500-2000 pairs,
-// which would serialise inside the per-knot warp of the assembler).
-__global__ void knot_objective_hessian_kernel(DProb P, int oi, const double* __restrict__ Z, double sigma, double* __restrict__ hess,
-                                              long long total) {
+// Knot-objective Hessians: w * Q * Hess l, one thread per (problem, listed knot, variable pair), into DProb::knot_side (a
+// terminal cost on a 32- or 64-dimensional state is one knot with ~500-2000 hyper-dual evaluations, which would serialise
+// inside the per-knot warp of the assembler).  Depends on Z only: it runs beside the interval kernels on the second stream
+// and the assembler adds sigma times the pairs to the knot's tile.
+__global__ void knot_objective_pairs_kernel(DProb P, int oi, const double* __restrict__ Z, long long total) {
     const DObj& O = P.ob[oi];
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= total) return;
@@ -327,21 +349,12 @@ __global__ void knot_objective_hessian_kernel(DProb P, int oi, const double* __r
     }
     const int c = a + p;
     const int kl = O.own_knot[j];
-    if (kl < P.kc0 || kl >= P.kc1) return;  // assembled (and added to) by another launch of the pipeline
+    if (kl < P.kc0 || kl >= P.kc1) return;  // assembled by another launch of the pipeline
     const double* zk = Z + (long long)b * P.n_vars_local + (long long)kl * z;
     const double* prm = O.params + (long long)O.own_ti[j] * O.np;
     const double* gp = Z + (long long)b * P.n_vars_local + (long long)P.nK * z;
     const HDual res = knot_lfun<HDual>(O.fn, SeededVars{zk, gp, O.var_offs, nv, a, c}, O.nv, prm);
-    const double v = sigma * O.weight * O.Qs[O.own_ti[j]] * res.d12;
-    int i = O.var_offs[a], l = O.var_offs[c];
-    if (i > l) {
-        const int q = i;
-        i = l;
-        l = q;
-    }
-    const int ncross = hess_knot_has_cross(P, kl) ? z : 0;
-    const long long pos = hess_knot_base(P, kl) + (long long)l * ncross + (long long)l * (l + 1) / 2 + ncross + i;
-    atomicAdd(hess + (long long)b * P.nnz_hess_local + pos, v);
+    P.knot_side[(long long)b * P.side_stride + O.side_off + (long long)j * npairs + pair] = O.weight * O.Qs[O.own_ti[j]] * res.d12;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -670,15 +683,22 @@ void launch_hessian_assemble(const DProb& P, const double* Z, double sigma, cons
     else if (GS == 16) hessian_assemble_kernel<16><<<grid, W * 32, smem, st>>>(P, Z, sigma, mu, hess, W, total);
     else hessian_assemble_kernel<32><<<grid, W * 32, smem, st>>>(P, Z, sigma, mu, hess, W, total);
     ++*launches;
-    if (sigma != 0.0)
-        for (int oi = 0; oi < P.n_obj; ++oi) {
-            const DObj& O = P.ob[oi];
-            if ((O.kind != DTO_OBJ_KNOT && O.kind != DTO_OBJ_GLOBAL_KNOT) || O.nt_own == 0 || O.nvk == 0) continue;
-            if (O.own_kmax < P.kc0 || O.own_kmin >= P.kc1) continue;  // no listed knot in the active range
-            const long long tot = (long long)P.batch * O.nt_own * (O.nvk * (O.nvk + 1) / 2);
-            knot_objective_hessian_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(P, oi, Z, sigma, hess, tot);
-            ++*launches;
-        }
+}
+
+// the knot-objective pairs of the active range (nothing to do without knot objectives there)
+bool launch_knot_objective_pairs(const DProb& P, const double* Z, cudaStream_t st, long long* launches) {
+    if (P.knot_side == nullptr) return false;
+    bool any = false;
+    for (int oi = 0; oi < P.n_obj; ++oi) {
+        const DObj& O = P.ob[oi];
+        if ((O.kind != DTO_OBJ_KNOT && O.kind != DTO_OBJ_GLOBAL_KNOT) || O.nt_own == 0 || O.nvk == 0) continue;
+        if (O.own_kmax < P.kc0 || O.own_kmin >= P.kc1) continue;  // no listed knot in the active range
+        const long long tot = (long long)P.batch * O.nt_own * (O.nvk * (O.nvk + 1) / 2);
+        knot_objective_pairs_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(P, oi, Z, tot);
+        ++*launches;
+        any = true;
+    }
+    return any;
 }
 
 void launch_objective(const DProb& P, const double* Z, double* J, double* grad, double* partials, cudaStream_t st,

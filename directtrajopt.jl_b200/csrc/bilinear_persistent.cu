@@ -26,6 +26,7 @@
 
 #include "dto_internal.h"
 #include "series_tables.cuh"
+#include "bulk_copy.cuh"
 
 namespace {
 
@@ -850,11 +851,16 @@ __global__ void __launch_bounds__(max_warps<NT>() * 32, 1)
     constexpr int slot = nn + (1 + kMaxDrives) * n;
 
     double* Gs = sm;
-    for (int e = threadIdx.x; e < (m + 1) * nn; e += blockDim.x) {
-        const int i = e / nn, r = e % nn;
-        Gs[i * nn + sw<NT>(r / n, r % n)] = I.Grm[e];  // coalesced read, rows stay contiguous in shared memory
+    if (I.Gsw != nullptr) {  // the swizzled copy made at construction, moved by the bulk-copy engine
+        __shared__ __align__(8) unsigned long long bar;
+        bulk_stage(Gs, I.Gsw, (unsigned)((m + 1) * nn * sizeof(double)), &bar);
+    } else {
+        for (int e = threadIdx.x; e < (m + 1) * nn; e += blockDim.x) {
+            const int i = e / nn, r = e % nn;
+            Gs[i * nn + sw<NT>(r / n, r % n)] = I.Grm[e];  // coalesced read, rows stay contiguous in shared memory
+        }
+        __syncthreads();
     }
-    __syncthreads();
 
     Ctx<NT> c;
     c.P = &P;
@@ -942,6 +948,15 @@ __global__ void __launch_bounds__(max_warps<NT>() * 32, 1)
 #endif
             __syncwarp();
             }
+        }
+    }
+    // the CTA that leaves last zeroes the queue for the next launch (no memset node between the launches of a stream)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&wq[3], 1ull) == (unsigned long long)gridDim.x - 1) {
+            wq[0] = wq[1] = wq[2] = wq[3] = 0ull;
+            __threadfence();
         }
     }
 }
@@ -1213,8 +1228,8 @@ bool launch_product_nt(const DProb& P, int ii, const double* Z, const double* w,
     const int grid = (int)std::max<long long>(1, std::min<long long>(sms, (items + W - 1) / W));
     const long long per_warp = items / ((long long)grid * W);
     const int fetch = (NT <= 2) ? (int)std::max<long long>(1, std::min<long long>(8, per_warp / 8)) : 1;
-    if (cudaMemsetAsync(I.wq, 0, 3 * sizeof(unsigned long long), st) != cudaSuccess) return false;
     kern<<<grid, W * 32, smem, st>>>(P, ii, Z, w, y, transpose ? 1 : 0, I.wq, fetch);
+    if (cudaMemsetAsync(I.wq, 0, 4 * sizeof(unsigned long long), st) != cudaSuccess) return false;  // zero between launches
     ++*launches;
     return true;
 }
@@ -1259,13 +1274,13 @@ bool launch_variant(const DProb& P, int ii, const double* Z, const double* mu, d
     auto kern = bilinear_persistent_kernel<NT, MT>;
     static PerDeviceOnce configured;
     if (configured.first()) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return false;
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget) != cudaSuccess) return false;
     }
     const long long items = (long long)P.batch * (std::min(P.kc1, P.nI) - P.kc0);
     const long long roles = (f.jets != DTO_JETS_USE ? 1 : 0) + (f.want_jac ? 1 : 0) + (f.want_hess ? 1 : 0);
     const long long want_ctas = (items * roles + W - 1) / W;
     const int grid = (int)std::max<long long>(1, std::min<long long>(std::max(1, sms - P.reserve_sms), want_ctas));
-    if (cudaMemsetAsync(I.wq, 0, 3 * sizeof(unsigned long long), st) != cudaSuccess) return false;
+    // (the queue counters are zero between launches: the kernel's last CTA resets them)
     // small items (n <= 16) are fetched several at a time: the atomic's round trip is as long as the item itself
     const long long per_warp = items / ((long long)grid * W);
     const int fetch = (NT <= 2) ? (int)std::max<long long>(1, std::min<long long>(8, per_warp / 8)) : 1;
@@ -1275,6 +1290,16 @@ bool launch_variant(const DProb& P, int ii, const double* Z, const double* mu, d
 }
 
 }  // namespace
+
+// the swizzled shared-memory image of the (m+1) row-major generators (what the kernel's prologue stages)
+void bilinear_persistent_swizzled(int n, int m, const double* Grm, double* out) {
+    const int NT = n / 8;
+    const size_t nn = (size_t)n * n;
+    for (int i = 0; i <= m; ++i)
+        for (int s = 0; s < n; ++s)
+            for (int k = 0; k < n; ++k) out[i * nn + (size_t)s * n + ((NT % 2 == 0) ? (k ^ ((s & 1) << 3)) : k)] = Grm[i * nn + (size_t)s * n + k];
+}
+
 
 bool bilinear_persistent_supported(int n, int m) {
     if (m < 0 || m > kMaxDrives) return false;

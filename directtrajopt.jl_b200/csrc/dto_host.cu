@@ -179,6 +179,7 @@ struct dto_handle {
     // objective / gradient kernels run beside the interval kernel on a second stream (one SM is left free for them)
     cudaStream_t aux_stream = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_side_fork = nullptr, ev_side = nullptr;  // knot-objective pairs on the second stream
     int overlap_objective = 1;       // DTO_B200_OVERLAP=0 keeps everything on one stream
     int trace = 0;                   // DTO_B200_TRACE=1: device timeline of every host-pointer call on stderr
     bool spec_jac_inflight = false;  // a speculative delivery of the Jacobian into reg_jac is on the copy stream
@@ -231,6 +232,8 @@ extern "C" void dto_destroy(dto_handle* h) {
     if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->ev_side_fork) cudaEventDestroy(h->ev_side_fork);
+    if (h->ev_side) cudaEventDestroy(h->ev_side);
     if (h->hZpin) cudaFreeHost(h->hZpin);
     delete h->zero_fill;
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -328,6 +331,11 @@ extern "C" int dto_create(const dto_problem_desc* d, dto_handle** out) {
                     for (int r = 0; r < s.x_dim; ++r)
                         for (int c = 0; c < s.x_dim; ++c) rm[q * nn + (size_t)r * s.x_dim + c] = s.G[q * nn + (size_t)c * s.x_dim + r];
                 I.Grm = dev_upload(h, rm.data(), cnt);
+                if (s.G_batch_stride == 0 && s.x_dim % 8 == 0) {  // what the persistent kernel's prologue stages
+                    std::vector<double> swz(per);
+                    bilinear_persistent_swizzled(s.x_dim, s.u_dim, rm.data(), swz.data());
+                    I.Gsw = dev_upload(h, swz.data(), per);
+                }
             }
             I.hs_stride = (s.u_dim + 1) * s.x_dim + (s.u_dim + 1) * (s.u_dim + 1);
             I.variant = bilinear_dmma_supported(s.x_dim, s.u_dim) ? DTO_VAR_DMMA : DTO_VAR_GENERIC;
@@ -522,6 +530,21 @@ extern "C" int dto_create(const dto_problem_desc* d, dto_handle** out) {
             if (!s.Qs || (s.n_params > 0 && !s.params)) return fail_create(h, DTO_ERR_INVALID, "knot objective: missing Qs/params");
             O.params = dev_upload(h, s.params, (size_t)std::max(1, s.n_params) * s.n_times);
             O.Qs = dev_upload(h, s.Qs, s.n_times);
+        }
+    }
+
+    {   // knot objectives: room for their Hessian pairs (assemble.cu: knot_objective_pairs_kernel)
+        long long off = 0;
+        for (int i = 0; i < d->n_objectives; ++i) {
+            DObj& O = P.ob[i];
+            O.side_off = off;
+            if ((O.kind == DTO_OBJ_KNOT || O.kind == DTO_OBJ_GLOBAL_KNOT) && O.nvk > 0) off += (long long)O.nt_own * (O.nvk * (O.nvk + 1) / 2);
+        }
+        P.side_stride = off;
+        P.knot_side = nullptr;
+        if (off > 0 && d->eval_hessian) {
+            P.knot_side = dev_upload<double>(h, nullptr, (size_t)off * (size_t)std::max(1, d->batch));
+            if (!P.knot_side) return fail_create(h, DTO_ERR_CUDA, "out of device memory (knot objective pairs)");
         }
     }
 
@@ -1201,11 +1224,42 @@ static void eval_prologue(dto_handle* h, const DProb& P, const double* dZ, doubl
     if (dgrad) launch_global_gradient(P, dZ, dgrad, h->stream, &h->launches);
 }
 
+// the second stream (objective / gradient kernels, knot-objective pairs) and its events; false: keep everything on one stream
+static bool ensure_aux(dto_handle* h) {
+    if (!h->overlap_objective) return false;
+    if (h->aux_stream) return true;
+    if (cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_side_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_side, cudaEventDisableTiming) != cudaSuccess) {
+        cudaGetLastError();
+        if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
+        h->aux_stream = nullptr;
+        h->overlap_objective = 0;
+        return false;
+    }
+    return true;
+}
+
 // Interval kernels, analytic integrators and the Hessian assembler over the active knot range of P.
 static int eval_range(dto_handle* h, const DProb& P, const double* dZ, double sigma, const double* dmu, double* dg, double* djac,
                       double* dhess, EvalFlags f) {
     if (!(f.want_g || f.want_jac || f.want_hess)) return DTO_OK;
     bool fused_missed = false;
+    // knot-objective Hessian pairs: they depend on Z only, so they run beside the interval kernels (second stream) and the
+    // assembler below waits for them
+    bool side_on_aux = false;
+    if (f.want_hess && sigma != 0.0 && P.knot_side != nullptr) {
+        if (P.nI >= 256 && ensure_aux(h)) {
+            CUDA_TRY(h, cudaEventRecord(h->ev_side_fork, h->stream));
+            CUDA_TRY(h, cudaStreamWaitEvent(h->aux_stream, h->ev_side_fork, 0));
+            side_on_aux = launch_knot_objective_pairs(P, dZ, h->aux_stream, &h->launches);
+            if (side_on_aux) CUDA_TRY(h, cudaEventRecord(h->ev_side, h->aux_stream));
+        } else {
+            launch_knot_objective_pairs(P, dZ, h->stream, &h->launches);
+        }
+    }
     for (int i = 0; i < P.n_int; ++i) {
         if (P.in[i].kind == DTO_INT_DERIVATIVE) continue;
         const bool timed = h->timing && h->ev_used < h->ev_pool.size();
@@ -1241,6 +1295,7 @@ static int eval_range(dto_handle* h, const DProb& P, const double* dZ, double si
             launch_analytic(P, dZ, dg, djac, f, h->stream, &h->launches);
         }
     }
+    if (side_on_aux) CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_side, 0));
     if (f.want_hess) launch_hessian_assemble(P, dZ, sigma, dmu, dhess, h->stream, &h->launches);
     if (f.want_hess) launch_global_hessian(P, dZ, sigma, dmu, dhess, nullptr, h->stream, &h->launches);
     return DTO_OK;
@@ -1279,15 +1334,7 @@ static int run_eval(dto_handle* h, const double* dZ, double sigma, const double*
     // ~17 us of serial kernels at c2).
     if (f.want_g || f.want_jac || f.want_hess) launch_plans(h, P, dZ);
     bool overlap = h->overlap_objective && (dJ || dgrad) && (f.want_g || f.want_jac || f.want_hess) && P.nI >= 256;
-    if (overlap && !h->aux_stream) {
-        if (cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking) != cudaSuccess ||
-            cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-            cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) {
-            cudaGetLastError();
-            h->overlap_objective = 0;
-            overlap = false;
-        }
-    }
+    if (overlap && !ensure_aux(h)) overlap = false;
     if (overlap) {
         CUDA_TRY(h, cudaEventRecord(h->ev_fork, h->stream));  // Z (and whatever the caller enqueued before) is ready
         CUDA_TRY(h, cudaStreamWaitEvent(h->aux_stream, h->ev_fork, 0));

@@ -43,6 +43,7 @@ struct DInt {
     // bilinear (persistent / octet variants): per-interval series plan {alpha, theta1} written by series_plan_kernel
     // before the interval kernels of an iterate (series_plan.cu); nullptr: the kernels size the series from ||dt G(u)||_1
     const double2* plan;
+    const double* Gsw;     // persistent variant: the swizzled shared-memory image of Grm (bulk-copied by the prologue)
     const float* planmat;  // series_plan.cu: FP32 [G_0..G_m | pair products | norms] (shared generator sets only)
     unsigned long long* wq;  // bilinear, persistent variant: three work-queue counters (FWD, EXP, ADJ)
 };
@@ -60,6 +61,7 @@ struct DObj {
     int nt_own;
     int own_kmin, own_kmax;   // smallest / largest owned local knot (host-side launch pruning)
     const int* knot_to_own;   // [local knots] -> owned entry index or -1
+    long long side_off;       // knot objectives: offset of this term's [owned knot][variable pair] block in DProb::knot_side
     const double* R;
     const double* baseline;   // nv x N (global knots), may be null
     const double* params;
@@ -115,6 +117,8 @@ struct DProb {
     long long n_cons_local, nnz_jac_local, nnz_hess_local;
     const long long* jac_colptr;  // [nK*z + 1] local
     int jac_closed;               // no knot-constraint entries: column starts follow in closed form (no loads in the kernels)
+    double* knot_side;            // knot-objective Hessian pairs w Q d2l (without sigma), written beside the interval kernels
+    long long side_stride;        //   doubles per problem of the batch
     const double* halo;           // if non-null: knot nK-1 is read from here (peer memory) instead of local Z
     DInt in[DTO_MAX_INT];
     DObj ob[DTO_MAX_OBJ];
@@ -228,6 +232,7 @@ bool launch_bilinear_product(const DProb& P, int ii, const double* Z, const doub
                              long long* launches);
 void launch_analytic_product(const DProb& P, const double* Z, const double* w, double* y, bool transpose, cudaStream_t st,
                              long long* launches);
+void bilinear_persistent_swizzled(int n, int m, const double* Grm, double* out);
 size_t series_plan_smem(int n, int m);
 void series_plan_matrices(int n, int m, const double* Gcm, std::vector<float>& out);
 bool launch_series_plan(const DProb& P, int ii, const double* Z, cudaStream_t st, long long* launches);
@@ -240,6 +245,7 @@ void launch_tdb(const DProb& P, int ii, const double* Z, const double* mu, doubl
                 long long* launches);
 void launch_analytic(const DProb& P, const double* Z, double* g, double* jac, EvalFlags f, cudaStream_t st, long long* launches);
 void launch_constraints(const DProb& P, const double* Z, double* g, double* jac, EvalFlags f, cudaStream_t st, long long* launches);
+bool launch_knot_objective_pairs(const DProb& P, const double* Z, cudaStream_t st, long long* launches);
 void launch_hessian_assemble(const DProb& P, const double* Z, double sigma, const double* mu, double* hess, cudaStream_t st,
                              long long* launches);
 void launch_objective(const DProb& P, const double* Z, double* J, double* grad, double* partials, cudaStream_t st,

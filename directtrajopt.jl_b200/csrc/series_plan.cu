@@ -19,6 +19,7 @@
 // Every variant, pass, range, batch member and shard reads the same plan: their results stay bit-identical to each other.
 #include "dto_internal.h"
 #include "series_tables.cuh"
+#include "bulk_copy.cuh"
 #include <algorithm>
 #include <cmath>
 #include <vector>
@@ -34,34 +35,9 @@ __global__ void __launch_bounds__(512) series_plan_kernel(DProb P, int ii, const
     const DInt& I = P.in[ii];
     const int n = I.n, nn = n * n;
     const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5, wpc = blockDim.x >> 5;
-    {   // stage [G_0..G_m | S_pairs] with the bulk-copy engine (TMA, cp.async.bulk): one thread issues 16 KB pieces that
-        // complete on an mbarrier -- per-thread loads made this copy a chain of L2 latencies (56 % of the kernel's time)
+    {   // stage [G_0..G_m | S_pairs] with the bulk-copy engine: per-thread loads made this copy 56 % of the kernel's time
         __shared__ __align__(8) unsigned long long bar;
-        const unsigned bar_a = (unsigned)__cvta_generic_to_shared(&bar);
-        const unsigned bytes = (unsigned)((NM + NP) * nn * sizeof(float));  // a multiple of 16: n is even
-        if (threadIdx.x == 0) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes) : "memory");
-            const char* src = reinterpret_cast<const char*>(I.planmat);
-            const unsigned dst = (unsigned)__cvta_generic_to_shared(smf);
-            for (unsigned off = 0; off < bytes; off += 16384u) {
-                const unsigned sz = min(16384u, bytes - off);
-                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + off),
-                             "l"(src + off), "r"(sz), "r"(bar_a)
-                             : "memory");
-            }
-        }
-        unsigned done = 0;
-        while (!done) {
-            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
-                         : "=r"(done)
-                         : "r"(bar_a)
-                         : "memory");
-        }
+        bulk_stage(smf, I.planmat, (unsigned)((NM + NP) * nn * sizeof(float)), &bar);  // a multiple of 16 bytes: n is even
     }
     const float *G = smf, *S = smf + NM * nn;
     const float* gnorm = I.planmat + (size_t)(NM + NP) * nn;  // ||G_a||_1, rounded up
