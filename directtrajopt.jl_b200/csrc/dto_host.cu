@@ -161,6 +161,17 @@ struct dto_handle {
     // ---- iterate cache (evaluator.jl:474-482: the reference copies Z once per callback; the solvers call the five
     // callbacks separately on one iterate, ipopt_solver/solver.jl:85).  The handle keeps a page-locked copy of the iterate
     // that is resident on the device; a callback whose Z equals it re-uses the upload and everything already computed.
+    // Early start (DTO_B200_PREFETCH=0 turns it off): the FIRST callback on a new iterate -- the objective or its gradient --
+    // also enqueues the mu-independent pass (residual, Jacobian, jets) and returns as soon as its own small result is on
+    // the host; the interval kernels then run while the solver goes through its next callbacks.
+    int prefetch_mode = 1;
+    int prefetch_score = 0;        // < 0: recent early starts were thrown away (the iterate changed before g / J were read): paused
+    bool async_inflight = false;   // an early-started pass may still be running on `stream`
+    bool prefetch_consumed = false;
+    cudaEvent_t ev_small = nullptr;  // the objective / gradient of this iterate are on the device
+    double* hg_pin = nullptr;        // early start: the residual is staged here ahead of the Jacobian's last block (copy-engine FIFO)
+    cudaEvent_t ev_g = nullptr;
+    bool g_staged = false;
     int cache_mode = 1;        // 0: off; 1: one mu-independent pass (g + Jacobian + second-order jets) per new iterate; 2: compute only what is asked
     double* hZpin = nullptr;   // [batch][n_vars_local]
     bool z_valid = false;      // dZ holds hZpin
@@ -234,6 +245,9 @@ extern "C" void dto_destroy(dto_handle* h) {
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->ev_side_fork) cudaEventDestroy(h->ev_side_fork);
     if (h->ev_side) cudaEventDestroy(h->ev_side);
+    if (h->ev_small) cudaEventDestroy(h->ev_small);
+    if (h->ev_g) cudaEventDestroy(h->ev_g);
+    if (h->hg_pin) cudaFreeHost(h->hg_pin);
     if (h->hZpin) cudaFreeHost(h->hZpin);
     delete h->zero_fill;
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -870,6 +884,10 @@ extern "C" int dto_create(const dto_problem_desc* d, dto_handle** out) {
         if (const char* ov = getenv("DTO_B200_OVERLAP")) h->overlap_objective = atoi(ov);
         const char* env = getenv("DTO_B200_ITERATE_CACHE");
         h->cache_mode = env && strcmp(env, "0") == 0 ? 0 : (env && strcmp(env, "lazy") == 0 ? 2 : 1);
+        {
+            const char* pf = getenv("DTO_B200_PREFETCH");
+            h->prefetch_mode = pf && strcmp(pf, "0") == 0 ? 0 : 1;
+        }
         if (h->cache_mode && cudaHostAlloc((void**)&h->hZpin, sizeof(double) * B * (size_t)P.n_vars_local, cudaHostAllocDefault) != cudaSuccess) {
             cudaGetLastError();
             h->hZpin = nullptr;
@@ -1391,6 +1409,9 @@ static int ensure_iterate(dto_handle* h, const double* Z, bool force = false) {
         return 1;
     }
     ++h->cache_misses;
+    if (h->async_inflight && !h->prefetch_consumed) h->prefetch_score = -4;  // an early start nobody used: pause them
+    h->prefetch_consumed = false;
+    h->g_staged = false;
     h->have_obj = h->have_g = h->have_jac = h->have_jets = false;
     h->z_valid = false;
     h->spec_jac_done = false;
@@ -1430,7 +1451,7 @@ extern "C" int dto_upload_dev(dto_handle* h, const double* dZ) {
     if (!h || !dZ) return DTO_ERR_INVALID;
     const DProb& P = h->P;
     CUDA_TRY(h, cudaSetDevice(h->device));
-    h->have_obj = h->have_g = h->have_jac = h->have_jets = false;
+    h->have_obj = h->have_g = h->have_jac = h->have_jets = h->g_staged = false;
     h->z_valid = false;  // the host copy no longer describes the resident iterate
     if (h->link_rank >= 0 && h->link_world > 1) return publish_iterate(h, dZ);  // copy + publish (+ wait) in one kernel
     if (dZ != h->dZ)
@@ -1480,7 +1501,7 @@ struct Tracer {
 // registered array on the copy stream, and the call returns without waiting for it (dto_eval_jacobian on the same iterate
 // with that array only joins the copy).
 static int eval_core(dto_handle* h, double sigma, const EvalFlags* passes, int n_passes, bool comp_obj, double* J, double* grad,
-                     double* g, double* jac, double* hess, bool spec_jac = false) {
+                     double* g, double* jac, double* hess, bool spec_jac = false, bool prefetch = false) {
     {
         const int rc0 = prepare_halo(h);
         if (rc0 != DTO_OK) return rc0;
@@ -1559,6 +1580,23 @@ static int eval_core(dto_handle* h, double sigma, const EvalFlags* passes, int n
         return DTO_OK;
     };
 
+    // early start: the residual goes to a page-locked staging buffer as soon as it is complete -- issued BEFORE the last
+    // block of the speculative Jacobian delivery, or the constraint callback would queue behind it on the copy engine
+    auto stage_g = [&]() -> int {
+        if (!prefetch || !comp_g || B != 1) return DTO_OK;
+        if (!h->hg_pin && cudaHostAlloc((void**)&h->hg_pin, sizeof(double) * (size_t)std::max<long long>(1, P.n_cons_local), cudaHostAllocDefault) != cudaSuccess) {
+            cudaGetLastError();
+            h->hg_pin = nullptr;
+            return DTO_OK;  // no staging: the constraint callback copies from the device
+        }
+        if (!h->ev_g) CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_g, cudaEventDisableTiming));
+        CUDA_TRY(h, cudaMemcpyAsync(h->hg_pin, h->dg, sizeof(double) * P.n_cons_local, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, cudaEventRecord(h->ev_g, h->stream));
+        d2h += 8LL * P.n_cons_local;
+        h->g_staged = true;
+        return DTO_OK;
+    };
+
     Tracer tr(h->trace != 0);
     tr.mark("start", h->stream);
     // series plans of this iterate (a Hessian pass from stored jets re-uses the plans of the pass that stored them)
@@ -1609,11 +1647,22 @@ static int eval_core(dto_handle* h, double sigma, const EvalFlags* passes, int n
             d2h += 8LL * B * P.nnz_jac_local;
         }
     }
+    if (prefetch) {
+        // early start: the objective and its gradient first, on their way to the host before the interval kernels begin
+        eval_prologue(h, P, h->dZ, dJ, dgrad, nullptr, nullptr, EvalFlags{false, false, false});
+        if (J) CUDA_TRY(h, cudaMemcpyAsync(J, h->dJ, sizeof(double) * B, cudaMemcpyDeviceToHost, h->stream));
+        if (grad) CUDA_TRY(h, cudaMemcpyAsync(grad, h->dgrad, sizeof(double) * B * P.n_grad_local, cudaMemcpyDeviceToHost, h->stream));
+        if (!h->ev_small) CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_small, cudaEventDisableTiming));
+        CUDA_TRY(h, cudaEventRecord(h->ev_small, h->stream));
+        J = grad = nullptr;
+        dJ = dgrad = nullptr;
+    }
     if (!pipelined) {
         for (int i = 0; i < n_passes; ++i)
             if ((rc = eval_range(h, P, h->dZ, sigma, h->dmu, h->dg, h->djac, h->dhess, passes[i])) != DTO_OK) return rc;
         eval_prologue(h, P, h->dZ, dJ, dgrad, h->dg, h->djac, fany);
         CUDA_TRY(h, cudaGetLastError());
+        if ((rc = stage_g()) != DTO_OK) return rc;
         if (B == 1) {
             cudaStream_t jst = h->stream;
             if (spec_jac && comp_jac) {  // the speculative copy must not hold up this call's own outputs
@@ -1660,6 +1709,7 @@ static int eval_core(dto_handle* h, double sigma, const EvalFlags* passes, int n
                 if (grad) CUDA_TRY(h, cudaMemcpyAsync(grad, h->dgrad, sizeof(double) * B * P.n_grad_local, cudaMemcpyDeviceToHost, h->stream));
                 if (g) CUDA_TRY(h, cudaMemcpyAsync(g, h->dg, sizeof(double) * B * P.n_cons_local, cudaMemcpyDeviceToHost, h->stream));
                 J = grad = g = nullptr;
+                if ((rc = stage_g()) != DTO_OK) return rc;
                 cudaEvent_t ev2 = h->chunk_events_at(bounds.size());
                 if (!ev2) {
                     h->err = "cudaEventCreate failed";
@@ -1686,9 +1736,17 @@ static int eval_core(dto_handle* h, double sigma, const EvalFlags* passes, int n
         guard.z->finish();
         guard.z = nullptr;
     }
+    if (prefetch) {  // only this call's own small outputs are waited for; the pass runs on
+        CUDA_TRY(h, cudaEventSynchronize(h->ev_small));
+        if (spec_jac) h->spec_jac_inflight = true;
+        h->async_inflight = true;
+        h->last_d2h_bytes = d2h;
+        return DTO_OK;
+    }
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    h->async_inflight = false;
     if (spec_jac) h->spec_jac_inflight = true;
-    else if (used_copy_stream || h->spec_jac_inflight) {
+    else if (used_copy_stream) {  // (an earlier call's speculative Jacobian copy stays in flight: the Jacobian callback waits for it)
         CUDA_TRY(h, cudaStreamSynchronize(h->copy_stream));
         h->spec_jac_inflight = false;
     }
@@ -1708,7 +1766,7 @@ extern "C" int dto_eval_all(dto_handle* h, const double* Z, double sigma, const 
     if ((rc = ensure_iterate(h, Z)) < 0) return rc;
     // the fused pass recomputes what it is asked for and leaves the callbacks' cache empty (its Hessian pass overwrites
     // the compact second derivatives with this call's mu)
-    h->have_obj = h->have_g = h->have_jac = h->have_jets = false;
+    h->have_obj = h->have_g = h->have_jac = h->have_jets = h->g_staged = false;
     if (hess) CUDA_TRY(h, cudaMemcpyAsync(h->dmu, mu, sizeof(double) * (size_t)P.batch * P.n_cons_local, cudaMemcpyHostToDevice, h->stream));
     EvalFlags f{g != nullptr, jac != nullptr, hess != nullptr};
     rc = eval_core(h, sigma, &f, 1, J || grad, J, grad, g, jac, hess);
@@ -1739,6 +1797,7 @@ static int eval_callback(dto_handle* h, const double* Z, double sigma, const dou
     }
     if (jac && jac == h->reg_jac && h->have_jac && h->spec_jac_done && !J && !grad && !g && !hess) {
         // the Jacobian of this iterate went to the registered array while the constraint callback computed it
+        h->prefetch_consumed = true;
         if (h->spec_jac_inflight) {
             CUDA_TRY(h, cudaStreamSynchronize(h->copy_stream));
             h->spec_jac_inflight = false;
@@ -1746,16 +1805,48 @@ static int eval_callback(dto_handle* h, const double* Z, double sigma, const dou
         h->last_d2h_bytes = 0;
         return DTO_OK;
     }
+    const bool eager = h->cache_mode == 1;
+    const bool only_small = (J || grad) && !g && !jac && !hess;
+    if (only_small && h->have_obj && h->async_inflight) {
+        // resident objective / gradient while an early-started pass still runs on the main stream: a side stream ordered
+        // after the objective kernels only
+        if (ensure_aux(h) && h->ev_small) {
+            CUDA_TRY(h, cudaStreamWaitEvent(h->aux_stream, h->ev_small, 0));
+            if (J) CUDA_TRY(h, cudaMemcpyAsync(J, h->dJ, sizeof(double) * P.batch, cudaMemcpyDeviceToHost, h->aux_stream));
+            if (grad) CUDA_TRY(h, cudaMemcpyAsync(grad, h->dgrad, sizeof(double) * (size_t)P.batch * P.n_grad_local, cudaMemcpyDeviceToHost, h->aux_stream));
+            CUDA_TRY(h, cudaStreamSynchronize(h->aux_stream));
+            h->last_d2h_bytes = 8LL * P.batch * ((J ? 1 : 0) + (grad ? P.n_grad_local : 0));
+            return DTO_OK;
+        }
+    }
+    if (g && !J && !grad && !jac && !hess && h->have_g && h->g_staged) {
+        // the residual of this iterate was staged by the early-started pass
+        h->prefetch_consumed = true;
+        if (h->prefetch_score < 0) h->prefetch_score = 0;
+        CUDA_TRY(h, cudaEventSynchronize(h->ev_g));
+        memcpy(g, h->hg_pin, sizeof(double) * (size_t)P.n_cons_local);
+        h->last_d2h_bytes = 0;  // counted by the call that staged it
+        return DTO_OK;
+    }
+    if ((g || jac || hess) && h->async_inflight && (h->have_g || h->have_jac)) {
+        h->prefetch_consumed = true;
+        if (h->prefetch_score < 0) h->prefetch_score = 0;
+    } else if ((g || jac) && !h->have_g && !h->have_jac && h->have_obj && h->prefetch_score < 0) {
+        ++h->prefetch_score;  // the objective came first on this iterate and the pass was needed after all: an early start would have paid
+    }
     EvalFlags passes[2];
     int np = 0;
     const bool comp_obj = (J || grad) && !h->have_obj;
-    const bool eager = h->cache_mode == 1;
+    // early start: the first callback on a new iterate asks for the objective or its gradient only
+    const bool prefetch = h->prefetch_mode && eager && only_small && comp_obj && !h->have_g && !h->have_jac && P.batch == 1 &&
+                          h->link_rank < 0 && h->prefetch_score >= 0 && P.nI >= 256 && h->jets_ok;
     const bool use_jets = hess && h->jets_ok;
     bool need_g = g && !h->have_g, need_jac = jac && !h->have_jac;
     const bool need_jets = use_jets && !h->have_jets;
-    if (need_g || need_jac || need_jets) {
+    if (need_g || need_jac || need_jets || prefetch) {
         EvalFlags f1{need_g, need_jac, false};
-        if (eager || need_jets) {
+        if (prefetch) need_g = need_jac = true;
+        if (eager || need_jets || prefetch) {
             f1.want_g = f1.want_jac = true;
             f1.jets = h->jets_ok ? DTO_JETS_STORE : DTO_JETS_NONE;
         }
@@ -1769,9 +1860,10 @@ static int eval_callback(dto_handle* h, const double* Z, double sigma, const dou
     }
     // a Jacobian that is computed without being asked for goes to the registered array on the side
     const bool spec = !jac && h->reg_jac != nullptr && np > 0 && passes[0].want_jac && P.batch == 1;
-    rc = eval_core(h, sigma, passes, np, comp_obj, J, grad, g, jac, hess, spec);
+    rc = eval_core(h, sigma, passes, np, comp_obj, J, grad, g, jac, hess, spec, prefetch);
     if (rc != DTO_OK) {
-        h->have_obj = h->have_g = h->have_jac = h->have_jets = false;
+        h->have_obj = h->have_g = h->have_jac = h->have_jets = h->g_staged = false;
+        h->async_inflight = false;
         return rc;
     }
     if (spec) h->spec_jac_done = true;

@@ -164,3 +164,67 @@ def test_eval_all_rejects_bad_buffers():
     with pytest.raises(ValueError):
         ev.eval_constraint_jacobian_product(np.empty(ev.n_constraints), Z, np.ones(ev.n_vars - 1))
     ev.close()
+
+
+def test_early_start_of_the_mu_independent_pass(monkeypatch):
+    """The first callback on a new iterate (objective or gradient) also starts the residual / Jacobian / jets pass and
+    returns without waiting for it (DTO_B200_PREFETCH=0 turns that off).  Whatever order the callbacks then come in --
+    including iterates that are dropped after the objective alone -- the outputs are those of the plain path, bit for bit."""
+    prob = pt.quantum_gate_problem(N=300, levels=16, n_drives=4)
+    monkeypatch.setenv("DTO_B200_PREFETCH", "0")
+    ev_ref = dto.Evaluator(prob)
+    monkeypatch.delenv("DTO_B200_PREFETCH")
+    ev = dto.Evaluator(prob)
+    jac_reg, hess_reg = np.full(ev.nnz_jacobian, np.nan), np.full(ev.nnz_hessian, np.nan)
+    rng = np.random.default_rng(11)
+    Z0 = prob.trajectory.vec()
+    new = lambda: Z0 + 0.01 * rng.standard_normal(Z0.size)
+    buf = lambda n: np.full(n, np.nan)
+    for registered in (False, True):
+        if registered:
+            ev.register_outputs(jac_reg, hess_reg)
+        # A: the solver's order
+        Z, mu = new(), rng.random(ev.n_constraints)
+        ref = _five_calls(ev_ref, Z, 1.2, mu)
+        got = _five_calls(ev, Z, 1.2, mu)
+        for a, b in zip(ref, got):
+            assert np.array_equal(np.asarray(a), np.asarray(b))
+        # B: line-search style -- objective / gradient alone on iterates that are then dropped, then a full sequence
+        for _ in range(3):
+            Zt = new()
+            grad_r, grad_g = buf(ev.n_vars), buf(ev.n_vars)
+            assert ev.eval_objective(Zt) == ev_ref.eval_objective(Zt)
+            ev.eval_objective_gradient(grad_g, Zt)
+            ev_ref.eval_objective_gradient(grad_r, Zt)
+            assert np.array_equal(grad_g, grad_r)
+        for _ in range(6):  # the early start pauses after unused ones and comes back once the pass is asked for again
+            Z, mu = new(), rng.random(ev.n_constraints)
+            for a, b in zip(_five_calls(ev_ref, Z, 0.7, mu), _five_calls(ev, Z, 0.7, mu)):
+                assert np.array_equal(np.asarray(a), np.asarray(b))
+        # C: objective twice, then the Hessian straight away (its jets come from the early-started pass)
+        Z, mu = new(), rng.random(ev.n_constraints)
+        assert ev.eval_objective(Z) == ev.eval_objective(Z) == ev_ref.eval_objective(Z)
+        Hg, Hr = buf(ev.nnz_hessian), buf(ev.nnz_hessian)
+        ev.eval_hessian_lagrangian(Hg, Z, 1.0, mu)
+        ev_ref.eval_hessian_lagrangian(Hr, Z, 1.0, mu)
+        assert np.array_equal(Hg, Hr)
+        # D: objective, then the fused call on the same iterate
+        Z, mu = new(), rng.random(ev.n_constraints)
+        ev.eval_objective(Z)
+        for a, b in zip(_fused(ev_ref, Z, 1.1, mu), _fused(ev, Z, 1.1, mu)):
+            assert np.array_equal(np.asarray(a), np.asarray(b))
+        # E: gradient first, then the Jacobian into an unregistered buffer, then the residual
+        Z = new()
+        gr, gg = buf(ev.n_vars), buf(ev.n_vars)
+        ev.eval_objective_gradient(gg, Z)
+        ev_ref.eval_objective_gradient(gr, Z)
+        jg, jr = buf(ev.nnz_jacobian), buf(ev.nnz_jacobian)
+        ev.eval_constraint_jacobian(jg, Z)
+        ev_ref.eval_constraint_jacobian(jr, Z)
+        cg, cr = buf(ev.n_constraints), buf(ev.n_constraints)
+        ev.eval_constraint(cg, Z)
+        ev_ref.eval_constraint(cr, Z)
+        assert np.array_equal(gg, gr) and np.array_equal(jg, jr) and np.array_equal(cg, cr)
+    ev.unregister_outputs()
+    ev.close()
+    ev_ref.close()
