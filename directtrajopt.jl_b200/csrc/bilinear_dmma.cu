@@ -71,11 +71,13 @@ __device__ __forceinline__ void frag_zero(double (&f)[MT][NT][2]) {
 
 struct Series {
     int stages, terms;
+    double poison;  // 1, or NaN for a generator norm that is not finite or absurd (>= 1e8): the interval's outputs become NaN
 };
 
 __device__ __forceinline__ Series choose_series(double theta) {
-    Series s{1, 2};
+    Series s{1, 2, __longlong_as_double(0x7ff8000000000000LL)};
     if (theta < 1e8) {
+        s.poison = 1.0;
         s.stages = theta > 4.0 ? (int)ceil(theta * 0.25) : 1;  // one stage up to ||dt G||_1 = 4 (e^4 round-off amplification)
         const double ths = theta / s.stages;
         double term = ths;
@@ -208,7 +210,7 @@ __global__ void __launch_bounds__(128) bilinear_dmma_kernel(DProb P, int ii, con
                     term[mt][nt][1] = F[mt][nt][1];
                 }
             for (int t = 1; t <= ser.terms; ++t) {
-                const double c = dt / ((double)t * (double)ser.stages);
+                const double c = ser.poison * dt / ((double)t * (double)ser.stages);
                 double nw[MT][NT][2];
                 frag_zero(nw);
                 mma_apply<MT, NT, MT>(nw, term, Gu, ld, lane);
@@ -367,7 +369,7 @@ __global__ void __launch_bounds__(128) bilinear_dmma_kernel(DProb P, int ii, con
                         term[mt][nt][1] = F[mt][nt][1];
                     }
                 for (int t = 1; t <= ser.terms - 2; ++t) {  // value series only: two terms fewer than the derivative rows
-                    const double c = dt / ((double)t * (double)ser.stages);
+                    const double c = ser.poison * dt / ((double)t * (double)ser.stages);
                     double nw[MT][NT][2];
                     frag_zero(nw);
                     mma_apply<MT, NT, MT>(nw, term, Gu, ld, lane);
@@ -415,7 +417,7 @@ __global__ void __launch_bounds__(128) bilinear_dmma_kernel(DProb P, int ii, con
                 term[0][nt][1] = F[0][nt][1];
             }
             for (int t = 1; t <= ser.terms; ++t) {
-                const double c = dt / ((double)t * (double)ser.stages);
+                const double c = ser.poison * dt / ((double)t * (double)ser.stages);
                 // y_i = G_i' a on the FP64 pipe: lane s reads column s of G_i (row-major, conflict-free)
                 if (row8 == 0) {
 #pragma unroll

@@ -72,7 +72,9 @@ __global__ void __launch_bounds__(32) bilinear_generic_kernel(DProb P, int ii, c
     }
     const double theta = fabs(dt) * warp_max(cmax);
     int s_stages = 1, T = 2;
+    double poison = __longlong_as_double(0x7ff8000000000000LL);  // generator norm not finite or absurd: NaN out
     if (theta < 1e8) {
+        poison = 1.0;
         s_stages = theta > 4.0 ? (int)ceil(theta * 0.25) : 1;
         double ths = theta / s_stages, term = ths;
         T = 1;
@@ -96,7 +98,7 @@ __global__ void __launch_bounds__(32) bilinear_generic_kernel(DProb P, int ii, c
         for (int e = lane; e < ncol * n; e += 32) Ta[e] = V[e];
         __syncwarp();
         for (int q = 1; q <= T; ++q) {
-            const double c = dt / ((double)q * (double)s_stages);
+            const double c = poison * dt / ((double)q * (double)s_stages);
             for (int e = lane; e < ncol * n; e += 32) {
                 const int col = e / n, r = e % n;
                 double acc = 0.0;

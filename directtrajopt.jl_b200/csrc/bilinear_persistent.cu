@@ -534,6 +534,8 @@ __device__ __forceinline__ void role_exp_ps(const Ctx<NT>& c, int b, int kk) {
             ++sq;
         }
         nb = (taylor_terms(fmin(th, alpha)) + 2) / 3;  // polynomial degree from alpha_2(A / 2^sq), squarings from ||A||_1
+    } else {
+        scale = __longlong_as_double(0x7ff8000000000000LL);  // not finite / absurd: NaN out, as choose_series
     }
     double* A = c.Gu;
     for (int p = lane; p < nn; p += 32) A[p] *= scale;

@@ -130,7 +130,10 @@ struct DProb {
 // a macro step of size theta behaves like theta^17 / prod_j (2j)^2 ~ theta^17 1e-14.  The reference controls its error by
 // adaptive Tsit5 steps (time_dependent_bilinear_integrator.jl:117-127); here the step count follows the iterate.
 // Same arithmetic in every kernel (role CTAs of one interval must agree).
-__device__ inline int tdb_item_steps(const DInt& I, const double* zk, const double* zk1, int dt_off) {
+// `poison`: 1, or NaN where the step count would exceed its cap (|dt| (||G|| + omega) > 256 per interval) or the iterate is
+// not finite -- the kernels multiply their initial values by it, so such an interval's outputs are NaN (an evaluation
+// error the solver sees) instead of silently inaccurate numbers.
+__device__ inline int tdb_item_steps(const DInt& I, const double* zk, const double* zk1, int dt_off, double& poison) {
     double g = I.tdb_gnorm;
     for (int i = 0; i < I.m; ++i) {
         const double u0 = fabs(zk[I.u_off + i]), u1 = I.order == 1 ? fabs(zk1[I.u_off + i]) : u0;
@@ -138,7 +141,8 @@ __device__ inline int tdb_item_steps(const DInt& I, const double* zk, const doub
     }
     const double theta = fabs(zk[dt_off]) * (g + I.tdb_wmax);
     int s = I.steps;
-    if (theta > (double)s && theta < 1e8) s = (int)ceil(theta);  // NaN / absurd iterates keep the minimum
+    poison = theta <= 256.0 ? 1.0 : __longlong_as_double(0x7ff8000000000000LL);
+    if (theta > (double)s && theta <= 256.0) s = (int)ceil(theta);
     return s < 256 ? s : 256;
 }
 

@@ -219,7 +219,8 @@ __global__ void __launch_bounds__(kThreads) tdb_kernel(DProb P, int ii, const do
     const double* zk = Z + (long long)b * P.n_vars_local + (long long)kl * z;
     const double* zk1 = zk + z;
     if (P.halo != nullptr && kl + 1 == P.nK - 1) zk1 = P.halo;
-    const int steps = tdb_item_steps(I, zk, zk1, P.dt_off);
+    double poison;
+    const int steps = tdb_item_steps(I, zk, zk1, P.dt_off, poison);
 
     Ctx C;
     C.n = n;
@@ -272,7 +273,7 @@ __global__ void __launch_bounds__(kThreads) tdb_kernel(DProb P, int ii, const do
         if (role == ROLE_FWD) val = v == 0 ? zk[I.x_off + r] : 0.0;
         else if (role == ROLE_EXP) val = v == r ? 1.0 : 0.0;
         else val = v == 0 ? mu[mu_off + r] : 0.0;
-        Y0[e] = val;
+        Y0[e] = val * poison;
     }
     __syncthreads();
 

@@ -577,7 +577,8 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
     const double* zk = Z + (long long)b * P.n_vars_local + (long long)kl * z;
     const double* zk1 = zk + z;
     if (P.halo != nullptr && kl + 1 == P.nK - 1) zk1 = P.halo;
-    const int steps = tdb_item_steps(I, zk, zk1, P.dt_off);  // macro steps of THIS interval
+    double poison;
+    const int steps = tdb_item_steps(I, zk, zk1, P.dt_off, poison);  // macro steps of THIS interval
     __syncthreads();  // the previous item's tables and scalars are dead
     const long long mu_off = (long long)b * P.n_cons_local + I.row_off + (long long)kl * n;
 
@@ -593,7 +594,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
                 if (role == W_FWD) val = v == 0 ? zk[I.x_off + r] : 0.0;
                 else if (role == W_EXP) val = v == r ? 1.0 : 0.0;
                 else if (role == W_ADJ) val = v == 0 ? mu[mu_off + r] : 0.0;
-                if (role != W_IDLE) Y0S[(nt * 2 + j) * 32 + lane] = val;
+                if (role != W_IDLE) Y0S[(nt * 2 + j) * 32 + lane] = val * poison;
             }
     }
     if (warp == scal_warp && lane < 2) make_scal(I, zk, zk1, P.dt_off, lane == 0 ? 0.0 : 1.0, scal[lane], NV + (size_t)lane * NVn);
@@ -1052,13 +1053,14 @@ __global__ void __launch_bounds__(8 * 32, 1)
         const double* zk1 = zk + z;
         if (P.halo != nullptr && kl + 1 == P.nK - 1) zk1 = P.halo;
         const double dts = zk[P.dt_off];
-        const int steps = tdb_item_steps(I, zk, zk1, P.dt_off);  // the same count as the forward/adjoint CTA of this interval
+        double poison;
+        const int steps = tdb_item_steps(I, zk, zk1, P.dt_off, poison);  // the same count as the forward/adjoint CTA of this interval
         __syncthreads();  // previous item done with both generators and the scalars
         if (active) {
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
-                for (int j = 0; j < 2; ++j) Y0S[(nt * 2 + j) * 32 + lane] = (8 * tile + row8 == 8 * nt + 2 * q + j) ? 1.0 : 0.0;
+                for (int j = 0; j < 2; ++j) Y0S[(nt * 2 + j) * 32 + lane] = ((8 * tile + row8 == 8 * nt + 2 * q + j) ? 1.0 : 0.0) * poison;
         }
         // scalars of nodes 0 and 1, G(node 0), drift of node 1
         NodeIter ahead{0, 0, 0, steps, K};

@@ -473,3 +473,39 @@ def test_structural_zero_hessian_delivery(monkeypatch):
             for a, b in zip(outs[mode], outs["0"]):
                 assert np.array_equal(a, b)
 
+
+
+@pytest.mark.parametrize("kind", ["persistent", "octet", "generic", "dmma", "tdb"])
+def test_absurd_steps_poison_their_interval(monkeypatch, kind):
+    """An iterate whose |dt| ||G|| is not finite or absurdly large (>= 1e8 for the Taylor kernels, > 256 for the
+    extrapolation kernels, whose step count is capped there) must not come back as plausible numbers: the interval's
+    residual rows are NaN (an evaluation error for the solver), every other interval is untouched."""
+    if kind == "tdb":
+        prob = pt.carrier_problem(N=6, state_dim=8, n_drives=2)
+        big = 1e4
+    else:
+        if kind in ("generic", "dmma"):
+            monkeypatch.setenv("DTO_B200_KERNEL", kind)
+        n = 16 if kind == "octet" else 32
+        prob = pt.scaled_problem(N=6, state_dim=n, n_controls=2, generator_scale=0.3)
+        big = 1e12
+    ev = dto.Evaluator(prob)
+    spec = prob.to_spec()
+    Z = prob.trajectory.vec().copy()
+    g0 = np.empty(ev.n_constraints)
+    ev.eval_constraint(g0, Z)
+    assert np.isfinite(g0).all()
+    z, dt_off = spec["z"], spec["components"][spec["timestep"]][0]
+    k = 2  # third interval
+    Z[k * z + dt_off] = big
+    g = np.empty(ev.n_constraints)
+    ev.eval_constraint(g, Z)
+    n = prob.integrators[0].x_dim
+    rows = slice(k * n, (k + 1) * n)  # the first integrator's rows of interval k
+    assert np.isnan(g[rows]).all()
+    others = np.ones(ev.n_constraints, bool)
+    others[rows] = False
+    # the derivative integrators of the same interval read the same dt: exclude rows that changed for that reason
+    same = others & (g == g0)
+    assert same.sum() >= (prob.trajectory.N - 2) * n and np.isfinite(g[others]).all()
+    ev.close()
