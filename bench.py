@@ -123,33 +123,64 @@ def workload_config(workload, prob, mode):
 
 
 class ClockSampler(threading.Thread):
-    """Samples nvidia-smi SM clocks and throttle reasons while the timed region runs."""
+    """Samples SM clocks and throttle reasons while the timed region runs: NVML in-process (a query takes ~50 us, so even a
+    few-millisecond region gets several samples; one `nvidia-smi` process start takes longer than the whole region), the
+    `nvidia-smi` query line of the profiling recipe as fallback."""
+
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.stop_flag, self.rows = index, threading.Event(), []
+        self.index, self.stop_flag, self.rows, self.source = index, threading.Event(), [], "nvml"
+        self.nv = self.handle = None
+        try:
+            import pynvml as nv
+            import torch
+
+            nv.nvmlInit()
+            try:  # the CUDA device of this rank, whatever the enumeration order
+                uuid = str(torch.cuda.get_device_properties(index).uuid)
+                self.handle = nv.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            except Exception:
+                self.handle = nv.nvmlDeviceGetHandleByIndex(index)
+            self.nv = nv
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(self.handle, nv.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+            self.source = "nvidia-smi"
+
+    def _nvml_row(self):
+        nv = self.nv
+        mhz = float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
+        get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        r = int(get(self.handle))
+        bits = [getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8), getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20), getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)]
+        return [str(mhz), str(self.max_mhz)] + ["Active" if r & b else "Not Active" for b in bits]
 
     def run(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         while not self.stop_flag.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                if self.nv is not None:
+                    self.rows.append(self._nvml_row())
+                else:
+                    out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                         capture_output=True, text=True, timeout=5).stdout.strip()
+                    if out:
+                        self.rows.append([c.strip() for c in out.split(",")])
             except Exception:
                 pass
-            self.stop_flag.wait(0.02)
+            self.stop_flag.wait(0.002 if self.nv is not None else 0.02)
 
     def summary(self):
         if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
         sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        reasons = [n for i, n in enumerate(self.NAMES) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
-                "samples": len(self.rows)}
+                "samples": len(self.rows), "source": self.source}
 
 
 def cpu_port_rate(prob, sample_intervals, threads, all_dirs=True):

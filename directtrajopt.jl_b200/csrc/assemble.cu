@@ -309,6 +309,14 @@ hessian_assemble_kernel(DProb P, const double* __restrict__ Z, double sigma, con
             const unsigned t = tab[e];
             hp[e] = t == 0xFFFFFFFFu ? 0.0 : diag[t];
         }
+    } else if (has_cross && P.hess_tab != nullptr) {
+        // wide knots: the same table, built once at construction, read from global memory (L2-resident, coalesced) --
+        // the incremental (column, row) decode below costs ~500 cycles per 32 entries
+#pragma unroll 4
+        for (int e = tid; e < region; e += GS) {
+            const unsigned t = __ldg(P.hess_tab + e);
+            hp[e] = t == 0xFFFFFFFFu ? 0.0 : diag[t];
+        }
     } else {
         // wide knots, and the first knot of the trajectory (no cross rows): lane-private (column l, row-in-column i) cursor advanced by GS entries
         int l = 0, i = tid;

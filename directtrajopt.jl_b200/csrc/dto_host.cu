@@ -547,6 +547,17 @@ extern "C" int dto_create(const dto_problem_desc* d, dto_handle** out) {
         }
     }
 
+    P.hess_tab = nullptr;
+    if (d->eval_hessian) {  // stream-out gather table of the Hessian assembler (assemble.cu), knots with cross rows
+        const int zz = P.z;
+        std::vector<unsigned int> tab((size_t)zz * zz + (size_t)zz * (zz + 1) / 2);
+        size_t e = 0;
+        for (int l = 0; l < zz; ++l) {  // column l: [z cross rows | l + 1 diagonal rows]
+            for (int i = 0; i < zz; ++i) tab[e++] = P.any_cross ? (unsigned int)(zz * zz + i * zz + l) : 0xFFFFFFFFu;
+            for (int i = 0; i <= l; ++i) tab[e++] = (unsigned int)(i * zz + l);
+        }
+        P.hess_tab = dev_upload(h, tab.data(), tab.size());
+    }
     {   // knot objectives: room for their Hessian pairs (assemble.cu: knot_objective_pairs_kernel)
         long long off = 0;
         for (int i = 0; i < d->n_objectives; ++i) {
@@ -1350,15 +1361,19 @@ static int run_eval(dto_handle* h, const double* dZ, double sigma, const double*
     // The objective / gradient kernels are independent of the interval kernels and tiny (launch- and latency-bound): they run
     // on a second stream BESIDE the interval kernel, which leaves one SM free for them (0.7 % of its throughput against
     // ~17 us of serial kernels at c2).
-    if (f.want_g || f.want_jac || f.want_hess) launch_plans(h, P, dZ);
     bool overlap = h->overlap_objective && (dJ || dgrad) && (f.want_g || f.want_jac || f.want_hess) && P.nI >= 256;
     if (overlap && !ensure_aux(h)) overlap = false;
     if (overlap) {
+        // forked BEFORE the series plans: the objective kernels then run beside the plan kernel and are gone when the
+        // interval kernel wants its SMs (forked after it, they raced the interval kernel for them: up to 10 us)
         CUDA_TRY(h, cudaEventRecord(h->ev_fork, h->stream));  // Z (and whatever the caller enqueued before) is ready
         CUDA_TRY(h, cudaStreamWaitEvent(h->aux_stream, h->ev_fork, 0));
         launch_objective(P, dZ, dJ, dgrad, h->dpartials, h->aux_stream, &h->launches);
         if (dgrad) launch_global_gradient(P, dZ, dgrad, h->aux_stream, &h->launches);
         CUDA_TRY(h, cudaEventRecord(h->ev_join, h->aux_stream));
+    }
+    if (f.want_g || f.want_jac || f.want_hess) launch_plans(h, P, dZ);
+    if (overlap) {
         DProb Pr = P;
         Pr.reserve_sms = 1;
         rc = eval_range(h, Pr, dZ, sigma, dmu, dg, djac, dhess, f);

@@ -117,6 +117,7 @@ struct DProb {
     long long n_cons_local, nnz_jac_local, nnz_hess_local;
     const long long* jac_colptr;  // [nK*z + 1] local
     int jac_closed;               // no knot-constraint entries: column starts follow in closed form (no loads in the kernels)
+    const unsigned int* hess_tab;  // stream-out gather table of a knot WITH cross rows: region entry -> index into [diag | cross] tiles, 0xFFFFFFFF = structural zero
     double* knot_side;            // knot-objective Hessian pairs w Q d2l (without sigma), written beside the interval kernels
     long long side_stride;        //   doubles per problem of the batch
     const double* halo;           // if non-null: knot nK-1 is read from here (peer memory) instead of local Z
