@@ -140,7 +140,7 @@ __device__ __forceinline__ void mul_t(Mat<NT>& out, const Mat<NT>& V, const Mat<
 template <int NT, int M, bool PP>
 __global__ void __launch_bounds__(NT == 1 ? 256 : 128, (NT == 1 && M <= 2) ? 2 : 1)  // n = 8, m <= 2: 128 registers, two CTAs of 8 warps per SM
     bilinear_octet_kernel(DProb P, int ii, const double* __restrict__ Z, const double* __restrict__ mu, double* __restrict__ g,
-                          double* __restrict__ jac, int want_jac, int want_hess, int jets, int split) {
+                          double* __restrict__ jac, int want_jac, int want_hess, int jets, long long n_whole) {
     constexpr int n = 8 * NT, nn = n * n, J = 1 + M + M * (M + 1) / 2;
     extern __shared__ __align__(16) double sm[];
     const DInt& I = P.in[ii];
@@ -198,16 +198,18 @@ __global__ void __launch_bounds__(NT == 1 ? 256 : 128, (NT == 1 && M <= 2) ? 2 :
 
     // Work units.  Normally one octet = one unit (forward, adjoint and propagator phases back to back in one warp).  When a
     // launch has only a few rounds of octets per warp (a knot-range shard on eight GPUs: 1.3 rounds), the duration of one
-    // unit -- latency-bound, the same with two or eight warps on the SM -- quantises the kernel time; `split` makes every
-    // phase of an octet its own unit (longest first), a third of the granularity.
+    // unit -- latency-bound, the same with two or eight warps on the SM -- quantises the kernel time; the octets from
+    // `n_whole` on are therefore cut into their phases, each its own unit (longest first), a third of the granularity:
+    // whole rounds of whole octets (the faster form), then the remainder in phases.
     int phases[3], nPh = 0;
     if (jets != DTO_JETS_USE) phases[nPh++] = 0;  // forward
     if (want_jac) phases[nPh++] = 1;              // propagator + constant columns (+ derivative integrators)
     if (want_hess) phases[nPh++] = 2;             // adjoint
-    const long long nUnits = split ? nOct * nPh : nOct;
+    const long long nSplit = nOct - n_whole, nUnits = n_whole + nSplit * nPh;
     for (long long unit = warp0; unit < nUnits; unit += nWarps) {
-        const long long oct = split ? unit % nOct : unit;
-        const int ph = split ? phases[unit / nOct] : -1;
+        const bool whole = unit < n_whole;
+        const long long oct = whole ? unit : n_whole + (unit - n_whole) % nSplit;
+        const int ph = whole ? -1 : phases[(unit - n_whole) / nSplit];
         const bool do_fwd = ph < 0 || ph == 0, do_exp = ph < 0 || ph == 1, do_adj = ph < 0 || ph == 2;
         int b, kk;
         const bool valid = locate(oct, row8, b, kk);
@@ -672,15 +674,25 @@ bool launch_octet_pp(const DProb& P, int ii, const double* Z, const double* mu, 
     const long long octs = PP ? (long long)P.batch * ((nIc + 7) / 8) : (items + 7) / 8, wpc = threads / 32;
     const int nPh = (f.jets != DTO_JETS_USE ? 1 : 0) + (f.want_jac ? 1 : 0) + (f.want_hess ? 1 : 0);
     const long long resident = (long long)std::max(1, sms - P.reserve_sms) * per_sm * wpc;  // warps in flight
-    const char* env = getenv("DTO_B200_OCTET_SPLIT");           // A/B switch: 0 = never, 1 = always
-    // split when it recovers more than a tenth of the launch: idle share of the last round of whole octets against that of
-    // the last round of single phases (a third of the granularity; the split form itself is ~8 % slower per octet)
-    auto idle = [&](double rounds) { return (ceil(rounds) - rounds) / ceil(rounds); };
+    const char* env = getenv("DTO_B200_OCTET_SPLIT");           // A/B switch: 0 = whole octets only, 1 = every octet in phases
+    // Three forms: whole octets only; every octet in phases (a third of the granularity, but ~8 % (n = 16) / ~20 % (n = 8)
+    // slower per octet); whole rounds of whole octets and the remainder in phases.  Measured (tools/c4_size_sweep.py,
+    // tools/c5_batch_sweep.py): with two or more complete rounds the third form wins or ties everywhere (c5 on one to
+    // eight GPUs 4-6 %, a c4 shard on two GPUs 4 %); below that the phases of the last round are too unequal for it, and
+    // cutting every octet pays once it recovers more than a tenth of the launch (a c4 shard on eight GPUs: 1.33 rounds,
+    // 256 -> 172 us).
+    auto idle = [&](double r) { return (ceil(r) - r) / ceil(r); };
     const double rounds = (double)octs / (double)resident;
-    const bool split = nPh > 1 && (env ? env[0] == '1' : idle(rounds) - idle(rounds * nPh) > 0.1);
-    const long long units = split ? octs * nPh : octs;
+    const long long full = (long long)floor(rounds) * resident;  // octets of the complete rounds
+    long long n_whole = octs;
+    if (nPh > 1) {
+        if (env) n_whole = env[0] == '1' ? 0 : octs;
+        else if (rounds >= 2.0) n_whole = full < octs ? full : octs;
+        else if (idle(rounds) - idle(rounds * nPh) > 0.1) n_whole = 0;
+    }
+    const long long units = n_whole + (octs - n_whole) * nPh;
     const int grid = (int)std::max<long long>(1, std::min<long long>((long long)std::max(1, sms - P.reserve_sms) * per_sm, (units + wpc - 1) / wpc));
-    kern<<<grid, threads, smem, st>>>(P, ii, Z, mu, f.want_g ? g : nullptr, jac, f.want_jac ? 1 : 0, f.want_hess ? 1 : 0, f.jets, split ? 1 : 0);
+    kern<<<grid, threads, smem, st>>>(P, ii, Z, mu, f.want_g ? g : nullptr, jac, f.want_jac ? 1 : 0, f.want_hess ? 1 : 0, f.jets, n_whole);
     ++*launches;
     return true;
 }
