@@ -191,6 +191,12 @@ struct dto_handle {
     cudaStream_t aux_stream = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev_side_fork = nullptr, ev_side = nullptr;  // knot-objective pairs on the second stream
+    // linked shards: the residual of the last device-pointer evaluation is complete at ev_g_ready (before the Hessian
+    // assembler): dto_shard_scalars_dev then runs beside the assembler on the second stream
+    cudaEvent_t ev_g_ready = nullptr, ev_scal_done = nullptr;
+    const double* g_ready_ptr = nullptr;
+    const double* j_ready_ptr = nullptr;
+    bool g_ready_valid = false, want_g_ready = false;
     int overlap_objective = 1;       // DTO_B200_OVERLAP=0 keeps everything on one stream
     int trace = 0;                   // DTO_B200_TRACE=1: device timeline of every host-pointer call on stderr
     bool spec_jac_inflight = false;  // a speculative delivery of the Jacobian into reg_jac is on the copy stream
@@ -245,6 +251,8 @@ extern "C" void dto_destroy(dto_handle* h) {
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->ev_side_fork) cudaEventDestroy(h->ev_side_fork);
     if (h->ev_side) cudaEventDestroy(h->ev_side);
+    if (h->ev_g_ready) cudaEventDestroy(h->ev_g_ready);
+    if (h->ev_scal_done) cudaEventDestroy(h->ev_scal_done);
     if (h->ev_small) cudaEventDestroy(h->ev_small);
     if (h->ev_g) cudaEventDestroy(h->ev_g);
     if (h->hg_pin) cudaFreeHost(h->hg_pin);
@@ -1261,7 +1269,9 @@ static bool ensure_aux(dto_handle* h) {
         cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_side_fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&h->ev_side, cudaEventDisableTiming) != cudaSuccess) {
+        cudaEventCreateWithFlags(&h->ev_side, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_g_ready, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_scal_done, cudaEventDisableTiming) != cudaSuccess) {
         cudaGetLastError();
         if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
         h->aux_stream = nullptr;
@@ -1325,6 +1335,7 @@ static int eval_range(dto_handle* h, const DProb& P, const double* dZ, double si
         }
     }
     if (side_on_aux) CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_side, 0));
+    if (h->want_g_ready && h->ev_g_ready) CUDA_TRY(h, cudaEventRecord(h->ev_g_ready, h->stream));  // every residual row is written
     if (f.want_hess) launch_hessian_assemble(P, dZ, sigma, dmu, dhess, h->stream, &h->launches);
     if (f.want_hess) launch_global_hessian(P, dZ, sigma, dmu, dhess, nullptr, h->stream, &h->launches);
     return DTO_OK;
@@ -1355,6 +1366,7 @@ static int run_eval(dto_handle* h, const double* dZ, double sigma, const double*
                     double* djac, double* dhess) {
     int rc = check_eval_args(h, dmu, dhess);
     if (rc != DTO_OK) return rc;
+    h->g_ready_valid = false;
     if ((rc = prepare_halo(h)) != DTO_OK) return rc;
     const DProb& P = h->P;
     EvalFlags f{dg != nullptr, djac != nullptr, dhess != nullptr};
@@ -1376,10 +1388,18 @@ static int run_eval(dto_handle* h, const double* dZ, double sigma, const double*
     if (overlap) {
         DProb Pr = P;
         Pr.reserve_sms = 1;
+        eval_prologue(h, P, dZ, nullptr, nullptr, dg, djac, f);  // knot constraints: their own rows and entries, nothing the interval kernels touch
+        h->want_g_ready = h->link_rank >= 0 && dg != nullptr && dJ != nullptr && dhess != nullptr;
         rc = eval_range(h, Pr, dZ, sigma, dmu, dg, djac, dhess, f);
+        const bool recorded = h->want_g_ready;
+        h->want_g_ready = false;
         if (rc != DTO_OK) return rc;
-        eval_prologue(h, P, dZ, nullptr, nullptr, dg, djac, f);  // knot constraints
         CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+        if (recorded) {
+            h->g_ready_valid = true;
+            h->g_ready_ptr = dg;
+            h->j_ready_ptr = dJ;
+        }
     } else {
         rc = eval_range(h, P, dZ, sigma, dmu, dg, djac, dhess, f);
         if (rc != DTO_OK) return rc;
@@ -1517,6 +1537,7 @@ struct Tracer {
 // with that array only joins the copy).
 static int eval_core(dto_handle* h, double sigma, const EvalFlags* passes, int n_passes, bool comp_obj, double* J, double* grad,
                      double* g, double* jac, double* hess, bool spec_jac = false, bool prefetch = false) {
+    h->g_ready_valid = false;
     {
         const int rc0 = prepare_halo(h);
         if (rc0 != DTO_OK) return rc0;
@@ -2245,12 +2266,26 @@ extern "C" int dto_shard_scalars_dev(dto_handle* h, const double* dg, double* dJ
         void* p = nullptr;
         CUDA_TRY(h, cudaMalloc(&p, 2 * sizeof(unsigned long long)));
         h->allocs.push_back(p);
-        CUDA_TRY(h, cudaMemsetAsync(p, 0, 2 * sizeof(unsigned long long), h->stream));
+        CUDA_TRY(h, cudaMemset(p, 0, 2 * sizeof(unsigned long long)));  // synchronous: the kernel may run on either stream
         h->d_scal_scratch = (unsigned long long*)p;
     }
     ++h->scal_seq;
+    // The residual (and, on the second stream, the objective) of the evaluation that was just enqueued are complete before
+    // its Hessian assembler starts: the reduction and the exchange then run BESIDE the assembler, and the wait for the
+    // slowest rank hides behind it.
+    cudaStream_t st = h->stream;
+    const bool beside = h->g_ready_valid && dg == h->g_ready_ptr && dJ == h->j_ready_ptr && h->aux_stream && h->ev_g_ready;
+    if (beside) {
+        CUDA_TRY(h, cudaStreamWaitEvent(h->aux_stream, h->ev_g_ready, 0));
+        st = h->aux_stream;
+    }
+    h->g_ready_valid = false;
     launch_shard_scalars(h->xwin, h->d_peer_win, h->link_rank, h->link_world, h->scal_seq, h->P.n_cons_local, dg, h->d_row_is_eq,
-                         h->d_scal_scratch, dJ, dviol, h->stream, &h->launches);
+                         h->d_scal_scratch, dJ, dviol, st, &h->launches);
+    if (beside) {
+        CUDA_TRY(h, cudaEventRecord(h->ev_scal_done, h->aux_stream));
+        CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_scal_done, 0));
+    }
     CUDA_TRY(h, cudaGetLastError());
     return DTO_OK;
 }
