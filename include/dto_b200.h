@@ -236,6 +236,12 @@ int dto_eval_all(dto_handle* h, const double* Z, double sigma, const double* mu,
  * upload and re-uses what earlier callbacks computed.  The first callback that needs the interval kernels on a NEW
  * iterate runs one mu-independent pass (residual + Jacobian + the second-order vectors of the forward jet); the
  * Hessian callback then runs only the adjoint recurrences, contracts the stored vectors with mu and assembles.
+ * Early start: when the FIRST callback on a new iterate asks for the objective or its gradient only (the order Ipopt and
+ * MadNLP use), it also enqueues that mu-independent pass and returns as soon as its own result is on the host; the
+ * interval kernels run while the solver goes through its next callbacks, which then wait only for what they deliver
+ * (the residual is staged in page-locked memory, the Jacobian goes to a registered array on the side).  Every output is
+ * valid when its own callback returns; iterates that are dropped after the objective alone (line searches) pause the
+ * early start.  DTO_B200_PREFETCH=0 turns it off.
  * Results are bit-identical to dto_eval_all.  DTO_B200_ITERATE_CACHE=0 disables the cache, =lazy computes only what each
  * callback asks for.  dto_upload makes Z the resident iterate without evaluating anything (and returns after the
  * copy has completed: on knot-range shards, the point after which a neighbour may read this rank's knots). */

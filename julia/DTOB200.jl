@@ -344,4 +344,34 @@ function eval_all_dev!(e::B200Evaluator, dZ::DevPtr, σ::Float64, dμ::DevPtr, d
     return nothing
 end
 
+# ---- one long trajectory on several GPUs (INTEGRATION.md section 4b; include/dto_b200.h "knot-range sharding") --------
+# One Julia process per GPU (MPI.jl or Distributed): every rank builds its evaluator with `shard_k0/shard_k1` in the
+# descriptor, exchanges the 64-byte window handles once and links; per iterate every rank uploads its slice exactly once.
+"""64-byte CUDA-IPC handle of this shard's exchange window (`dto_shard_export`); all-gather these in rank order."""
+function shard_export(e::B200Evaluator)
+    buf = Vector{UInt8}(undef, 64)
+    check(ccall((:dto_shard_export, LIB), Cint, (Ptr{Cvoid}, Ptr{UInt8}), e.handle, buf), e.handle)
+    return buf
+end
+"""Map the windows of all `world` shards; `handles` = the gathered 64-byte handles, rank order (`dto_shard_link`)."""
+function shard_link!(e::B200Evaluator, rank::Integer, world::Integer, handles::Vector{Vector{UInt8}})
+    flat = reduce(vcat, handles)
+    check(ccall((:dto_shard_link, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{UInt8}), e.handle, rank, world, flat), e.handle)
+    return nothing
+end
+"""New iterate from host memory: uploads this rank's slice `[z_begin, z_halo_end)` and publishes its first knot (`dto_upload`)."""
+upload!(e::B200Evaluator, Zslice::Vector{Float64}) =
+    (check(ccall((:dto_upload, LIB), Cint, (Ptr{Cvoid}, Ptr{Cdouble}), e.handle, Zslice), e.handle); nothing)
+"""New iterate that already lives on the device (`dto_upload_dev`): copy + publish + wait for the neighbour's knot, one kernel."""
+upload_dev!(e::B200Evaluator, dZ::DevPtr) =
+    (check(ccall((:dto_upload_dev, LIB), Cint, (Ptr{Cvoid}, DevPtr), e.handle, dZ), e.handle); nothing)
+"""Device address of this shard's resident Z (what the `_dev` callbacks are then given) (`dto_local_Z`)."""
+local_Z(e::B200Evaluator) = ccall((:dto_local_Z, LIB), DevPtr, (Ptr{Cvoid},), e.handle)
+"""Violation of this shard's residuals `dg` and the (sum, max) exchange of objective / violation with all shards in one
+kernel, in place on the device, no collective library (`dto_shard_scalars_dev`)."""
+function shard_scalars_dev!(e::B200Evaluator, dg::DevPtr, dJ::DevPtr, dviol::DevPtr)
+    check(ccall((:dto_shard_scalars_dev, LIB), Cint, (Ptr{Cvoid}, DevPtr, DevPtr, DevPtr), e.handle, dg, dJ, dviol), e.handle)
+    return nothing
+end
+
 end # module
