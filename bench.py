@@ -51,7 +51,7 @@ WORKLOADS = {
 }
 FP64_PEAK_TFLOPS = 37.1  # measured on this pool's B200: DMMA m8n8k4 saturation (profiles/r01_fp64_peaks_and_box_probe.log)
 TAYLOR_T = 20            # canonical term count of SURVEY.md section 8d (C1)
-TDB_RHS = 80             # right-hand sides per interval of K7 (Gragg-Bulirsch-Stoer, 8 columns, one macro step): BASELINE.md section 3
+TDB_RHS = 80             # right-hand sides per interval of K7 with eight extrapolation columns and one macro step; the kernels size the columns per interval: tdb_rhs_per_interval
 
 
 def canonical_flops_per_interval(n, m, T=TAYLOR_T, s=0):
@@ -71,6 +71,41 @@ def canonical_flops_per_tdb_interval(n, m, spline_order=1, rhs=TDB_RHS):
     p = (2 * m if spline_order == 1 else m) + 2
     matvecs = n + (1 + 2 * p + 3 * p * (p + 1) / 2) + (1 + 2 * p)
     return rhs * matvecs * 2 * n * n
+
+
+def tdb_rhs_per_interval(prob, Zvec):
+    """Right-hand sides K7 evaluates per interval at this iterate: the host restatement of `tdb_item_steps`
+    (csrc/dto_internal.h): theta = |dt| (||G0||_1 + sum ||D_j||_1 + sum_i max|u_i| (||A_i||_1 + ||B_i||_1) + max omega); ceil(theta)
+    macro steps above 1; the smallest K in 3..8 columns with theta^(2K+1) <= tol (2^K K!)^2 (DTO_B200_TDB_TOL, default 1e-14;
+    0: eight columns); a sweep of K columns costs sum_{k<=K} (2k + 1) = K^2 + 2K right-hand sides."""
+    it = prob.integrators[0]
+    t = prob.trajectory
+    G = it.G
+    n1 = lambda M: float(np.abs(M).sum(axis=0).max()) if M.size else 0.0
+    gnorm = n1(G.G0) + sum(n1(D) for D in G.D)
+    bnorm = np.array([n1(G.A[i]) + n1(G.B[i]) for i in range(G.A.shape[0])])
+    wmax = float(max([0.0] + [abs(w) for w in G.omega] + [abs(w) for w in G.omega_d]))
+    tol = float(os.environ.get("DTO_B200_TDB_TOL", "1e-14"))
+    Zm = np.asarray(Zvec)[: t.N * t.dim].reshape(t.N, t.dim)
+    u = np.abs(Zm[:, t.components[it.u_name]])
+    dt = np.abs(Zm[:, t.components[t.timestep]]).reshape(t.N)
+    total = 0
+    for k in range(t.N - 1):
+        uk = np.maximum(u[k], u[k + 1]) if it.spline_order == 1 else u[k]
+        theta = dt[k] * (gnorm + float(uk @ bnorm) + wmax)
+        steps = max(1, int(it.steps) if it.steps else 1)
+        if theta > steps:
+            steps = min(256, int(np.ceil(theta)))
+        K = 8
+        if tol > 0:
+            ths, den = theta / steps, 2304.0
+            for kk in range(3, 8):
+                if ths ** (2 * kk + 1) <= tol * den:
+                    K = kk
+                    break
+                den *= 4.0 * (kk + 1) ** 2
+        total += steps * (K * K + 2 * K)
+    return total / max(1, t.N - 1)
 
 
 def recorded_traffic(workload, variant):
@@ -477,7 +512,8 @@ def run_workload(args, workload, steps, warmup, *, rank, world, local_rank, full
         intervals_per_launch = {"replicas": t.N - 1, "knot_shards": int(ev.n_dynamics_constraints // max(1, sum(i.x_dim for i in prob.integrators))),
                                 "batch_split": batch_local * (t.N - 1)}[mode]
         tdb = type(prob.integrators[0]).__name__ == "TimeDependentBilinearIntegrator"
-        per_interval = canonical_flops_per_tdb_interval(n, m, prob.integrators[0].spline_order) if tdb else canonical_flops_per_interval(n, m)
+        rhs_avg = tdb_rhs_per_interval(prob, Z) if tdb else None  # what the kernels execute at this iterate (columns sized per interval)
+        per_interval = canonical_flops_per_tdb_interval(n, m, prob.integrators[0].spline_order, rhs=rhs_avg) if tdb else canonical_flops_per_interval(n, m)
         flops_launch = per_interval * intervals_per_launch
         achieved = flops_launch / (k1_avg_ms * 1e-3) * 1e-12
         traffic, traffic_src = recorded_traffic(workload, ev.kernel_variant(0)) if world == 1 or mode == "replicas" else (None, None)
@@ -513,6 +549,10 @@ def run_workload(args, workload, steps, warmup, *, rank, world, local_rank, full
                 "hbm_gbs_step": out_bytes_dev / (dev_ms_max / steps * 1e-3) * 1e-9,
             },
         }
+        if tdb:
+            line["roofline"]["rhs_per_interval"] = rhs_avg
+            line["roofline"]["rhs_note"] = ("right-hand sides executed per interval (extrapolation columns sized per interval from the iterate; 80 with "
+                                            "eight columns everywhere, DTO_B200_TDB_TOL=0): the flop count is per executed right-hand side")
         if e2e_fused_s is not None:
             line["e2e"]["fused"] = {"call": "dto_eval_all", "value": per_step * e2e_steps / e2e_fused_s_max, "ms_per_step": e2e_fused_s_max / e2e_steps * 1e3,
                                     "d2h_bytes_per_step": d2h_fused, "matches_device_path": same}

@@ -415,6 +415,10 @@ extern "C" int dto_create(const dto_problem_desc* d, dto_handle** out) {
                 std::vector<double> bn((size_t)std::max(s.u_dim, 1), 0.0);
                 I.tdb_gnorm = norm1(s.G);
                 I.tdb_wmax = 0.0;
+                {   // DTO_B200_TDB_TOL=0: eight extrapolation columns everywhere (round 1); default: sized per interval
+                    const char* tl = getenv("DTO_B200_TDB_TOL");
+                    I.tdb_tol = tl ? atof(tl) : 1e-14;
+                }
                 for (int i = 0; i < s.u_dim; ++i) {
                     bn[i] = norm1(s.A + (size_t)i * nn) + norm1(s.B + (size_t)i * nn);
                     I.tdb_wmax = std::max(I.tdb_wmax, fabs(s.omega[i]));

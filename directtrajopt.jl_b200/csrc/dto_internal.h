@@ -22,6 +22,7 @@ struct DInt {
     int steps;          // tdbilinear: minimum number of macro steps per interval (the kernels raise it per interval, tdb_item_steps)
     double tdb_gnorm;   // tdbilinear: ||G0||_1 + sum_j ||D_j||_1
     double tdb_wmax;    // tdbilinear: largest carrier frequency |w_i|, |wd_j|
+    double tdb_tol;     // tdbilinear: extrapolation-error target that sizes the columns per interval (0: always the maximum)
     const double* tdb_bnorm;  // tdbilinear: [m] ||A_i||_1 + ||B_i||_1
     int variant;        // kernel variant chosen on the host
     long long row_off;  // local row of this integrator's first residual
@@ -131,10 +132,14 @@ struct DProb {
 // a macro step of size theta behaves like theta^17 / prod_j (2j)^2 ~ theta^17 1e-14.  The reference controls its error by
 // adaptive Tsit5 steps (time_dependent_bilinear_integrator.jl:117-127); here the step count follows the iterate.
 // Same arithmetic in every kernel (role CTAs of one interval must agree).
+// Macro steps AND extrapolation columns of one interval, from the iterate.  With the modified-midpoint sequence
+// n_k = 2, 4, .., 2K the extrapolated value of a linear system with ||dt G|| = theta per macro step has the error
+// theta^(2K+1) / (2^K K!)^2 (the product of the n_k^2: 1e-14 at K = 8, theta = 1): `cols` is the smallest K (>= 3, <= kmax)
+// that keeps it below I.tdb_tol -- an interval with theta = 0.2 needs 5 columns = 35 right-hand sides, not 8 = 80.
 // `poison`: 1, or NaN where the step count would exceed its cap (|dt| (||G|| + omega) > 256 per interval) or the iterate is
 // not finite -- the kernels multiply their initial values by it, so such an interval's outputs are NaN (an evaluation
 // error the solver sees) instead of silently inaccurate numbers.
-__device__ inline int tdb_item_steps(const DInt& I, const double* zk, const double* zk1, int dt_off, double& poison) {
+__device__ inline int tdb_item_steps(const DInt& I, const double* zk, const double* zk1, int dt_off, double& poison, int kmax, int& cols) {
     double g = I.tdb_gnorm;
     for (int i = 0; i < I.m; ++i) {
         const double u0 = fabs(zk[I.u_off + i]), u1 = I.order == 1 ? fabs(zk1[I.u_off + i]) : u0;
@@ -144,7 +149,21 @@ __device__ inline int tdb_item_steps(const DInt& I, const double* zk, const doub
     int s = I.steps;
     poison = theta <= 256.0 ? 1.0 : __longlong_as_double(0x7ff8000000000000LL);
     if (theta > (double)s && theta <= 256.0) s = (int)ceil(theta);
-    return s < 256 ? s : 256;
+    s = s < 256 ? s : 256;
+    cols = kmax;
+    if (I.tdb_tol > 0.0 && theta <= 256.0) {
+        const double ths = theta / (double)s, t2 = ths * ths;
+        double pw = ths * t2 * t2 * t2, den = 2304.0;  // theta^7, (2^3 3!)^2
+        for (int K = 3; K < kmax; ++K) {
+            if (pw <= I.tdb_tol * den) {
+                cols = K;
+                break;
+            }
+            pw *= t2;
+            den *= 4.0 * (K + 1) * (K + 1);
+        }
+    }
+    return s;
 }
 
 // Jacobian position helpers (local numbering) --------------------------------------------------

@@ -209,7 +209,7 @@ __device__ void rhs(int role, const Ctx& C, const Scal& S, const Tables& T, cons
 
 __global__ void __launch_bounds__(kThreads) tdb_kernel(DProb P, int ii, const double* __restrict__ Z, const double* __restrict__ mu,
                                                        double* __restrict__ g, double* __restrict__ jac, int want_jac, int want_hess,
-                                                       int K) {
+                                                       int Kmax) {
     extern __shared__ double sm[];
     const DInt& I = P.in[ii];
     const int n = I.n, m = I.m, z = P.z, tid = threadIdx.x, nt = blockDim.x;
@@ -220,7 +220,9 @@ __global__ void __launch_bounds__(kThreads) tdb_kernel(DProb P, int ii, const do
     const double* zk1 = zk + z;
     if (P.halo != nullptr && kl + 1 == P.nK - 1) zk1 = P.halo;
     double poison;
-    const int steps = tdb_item_steps(I, zk, zk1, P.dt_off, poison);
+    int Ki;
+    const int steps = tdb_item_steps(I, zk, zk1, P.dt_off, poison, Kmax, Ki);
+    const int K = Ki;  // extrapolation columns of THIS interval
 
     Ctx C;
     C.n = n;

@@ -425,7 +425,7 @@ __device__ __forceinline__ void assemble_generators(double* Gf, double* Ga, cons
 template <int NT, int MAXW>
 __global__ void __launch_bounds__(MAXW * 32, 1)
     tdb_dmma_kernel(DProb P, int ii, const double* __restrict__ Z, const double* __restrict__ mu, double* __restrict__ g,
-                    double* __restrict__ jac, int want_jac, int want_hess, int K, int TF, int TE, int TA, int split, int nbs,
+                    double* __restrict__ jac, int want_jac, int want_hess, int Kmax, int TF, int TE, int TA, int split, int nbs,
                     double* __restrict__ scratch) {
     extern __shared__ __align__(16) double sm[];
     constexpr int n = 8 * NT, nn = n * n, FR = NT * 2 * 32;  // FR: doubles of one tile in per-lane fragment order
@@ -526,15 +526,6 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
         ctd[j] = en < ct_hi ? coef_entry(C, KCr, nrowsF, en, tw) : 0;
         ct_twice |= tw ? 1 << j : 0;
     }
-    if (threadIdx.x < kMaxCols) {
-        // w_k = prod_{l != k} n_k^2 / (n_k^2 - n_l^2), n_k = 2(k+1)
-        const int k = threadIdx.x;
-        double w = 1.0;
-        const double nk2 = 4.0 * (k + 1) * (k + 1);
-        for (int l = 0; l < K; ++l)
-            if (l != k) w *= nk2 / (nk2 - 4.0 * (l + 1) * (l + 1));
-        wk[k] = k < K ? w : 0.0;
-    }
     // extrapolation accumulator and macro-step start of this warp: touched only at sweep boundaries, kept in a
     // per-CTA global scratch (L2-resident) so that shared memory can hold the basis matrices instead
     double* AccS = scratch + (((size_t)blockIdx.y * gridDim.x + blockIdx.x) * kMaxWarpsT + warp) * 2 * FR;
@@ -578,8 +569,18 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
     const double* zk1 = zk + z;
     if (P.halo != nullptr && kl + 1 == P.nK - 1) zk1 = P.halo;
     double poison;
-    const int steps = tdb_item_steps(I, zk, zk1, P.dt_off, poison);  // macro steps of THIS interval
+    int K;  // extrapolation columns of THIS interval
+    const int steps = tdb_item_steps(I, zk, zk1, P.dt_off, poison, Kmax, K);  // macro steps of THIS interval
     __syncthreads();  // the previous item's tables and scalars are dead
+    if (threadIdx.x < kMaxCols) {
+        // w_k = prod_{l != k} n_k^2 / (n_k^2 - n_l^2), n_k = 2(k+1)
+        const int k = threadIdx.x;
+        double w = 1.0;
+        const double nk2 = 4.0 * (k + 1) * (k + 1);
+        for (int l = 0; l < K; ++l)
+            if (l != k) w *= nk2 / (nk2 - 4.0 * (l + 1) * (l + 1));
+        wk[k] = k < K ? w : 0.0;
+    }
     const long long mu_off = (long long)b * P.n_cons_local + I.row_off + (long long)kl * n;
 
     // ---- initial values (fragment element (nt, j): vector 8*tile + row8, state 8*nt + 2q + j) ------------
@@ -1004,7 +1005,7 @@ struct NodeIter {
 
 template <int NT>
 __global__ void __launch_bounds__(8 * 32, 1)
-    tdb_exp_kernel(DProb P, int ii, const double* __restrict__ Z, double* __restrict__ jac, int K, int TE, int nbs,
+    tdb_exp_kernel(DProb P, int ii, const double* __restrict__ Z, double* __restrict__ jac, int Kmax, int TE, int nbs,
                    double* __restrict__ scratch) {
     extern __shared__ __align__(16) double sm[];
     constexpr int n = 8 * NT, nn = n * n, FR = NT * 2 * 32;
@@ -1021,14 +1022,6 @@ __global__ void __launch_bounds__(8 * 32, 1)
     double* Bs = wk + kMaxCols + (kMaxCols & 1);               // cached basis matrices
     double* AccS = scratch + ((size_t)(gridDim.x + blockIdx.x) * kMaxWarpsT + warp) * 2 * FR;  // second half of the scratch
     double* Y0S = AccS + FR;
-    if (threadIdx.x < kMaxCols) {
-        const int k = threadIdx.x;
-        double w = 1.0;
-        const double nk2 = 4.0 * (k + 1) * (k + 1);
-        for (int l = 0; l < K; ++l)
-            if (l != k) w *= nk2 / (nk2 - 4.0 * (l + 1) * (l + 1));
-        wk[k] = k < K ? w : 0.0;
-    }
     for (int i = threadIdx.x; i < nbs * nn; i += blockDim.x) Bs[i] = basis_global(I, i / nn, nn)[i % nn];
     auto prefetch_drift = [&](double* Gd) {
         for (int blk = (nn / 64) * warp / nwarps; blk < (nn / 64) * (warp + 1) / nwarps; ++blk) {
@@ -1054,8 +1047,17 @@ __global__ void __launch_bounds__(8 * 32, 1)
         if (P.halo != nullptr && kl + 1 == P.nK - 1) zk1 = P.halo;
         const double dts = zk[P.dt_off];
         double poison;
-        const int steps = tdb_item_steps(I, zk, zk1, P.dt_off, poison);  // the same count as the forward/adjoint CTA of this interval
+        int K;
+        const int steps = tdb_item_steps(I, zk, zk1, P.dt_off, poison, Kmax, K);  // the same counts as the forward/adjoint CTA of this interval
         __syncthreads();  // previous item done with both generators and the scalars
+        if (threadIdx.x < kMaxCols) {
+            const int k = threadIdx.x;
+            double w = 1.0;
+            const double nk2 = 4.0 * (k + 1) * (k + 1);
+            for (int l = 0; l < K; ++l)
+                if (l != k) w *= nk2 / (nk2 - 4.0 * (l + 1) * (l + 1));
+            wk[k] = k < K ? w : 0.0;
+        }
         if (active) {
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt)

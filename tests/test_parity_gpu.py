@@ -509,3 +509,26 @@ def test_absurd_steps_poison_their_interval(monkeypatch, kind):
     same = others & (g == g0)
     assert same.sum() >= (prob.trajectory.N - 2) * n and np.isfinite(g[others]).all()
     ev.close()
+
+
+def test_tdb_extrapolation_columns_sized_per_interval(monkeypatch):
+    """K7 sizes its extrapolation columns per interval from theta = |dt| (||G|| + omega) (error model theta^(2K+1) / (2^K K!)^2
+    <= 1e-14): small steps take 5 of the 8 columns (35 instead of 80 right-hand sides).  The result must agree with the
+    eight-column evaluation to round-off, for small and large steps, and intervals of one trajectory may differ in K."""
+    prob = pt.carrier_problem(N=7, state_dim=16, n_drives=2, spline_order=1)
+    spec = prob.to_spec()
+    rng = np.random.default_rng(4)
+    Z = prob.trajectory.vec() + 0.02 * rng.standard_normal(prob.trajectory.vec().size)
+    dts = slice(spec["components"][spec["timestep"]][0], spec["N"] * spec["z"], spec["z"])
+    Z[dts] = np.abs(Z[dts]) * np.array([1.0, 0.2, 6.0, 1.0, 12.0, 0.05, 1.0])  # a different theta (and K, and step count) per interval
+    outs = {}
+    for tol in ("0", "1e-14"):
+        monkeypatch.setenv("DTO_B200_TDB_TOL", tol)
+        ev = dto.Evaluator(prob)
+        mu = np.random.default_rng(5).random(ev.n_constraints)
+        bufs = [np.full(ev.n_constraints, np.nan), np.full(ev.nnz_jacobian, np.nan), np.full(ev.nnz_hessian, np.nan)]
+        ev.eval_all(Z, 1.0, mu, None, None, *bufs)
+        outs[tol] = bufs
+        ev.close()
+    for a, b in zip(outs["0"], outs["1e-14"]):
+        assert np.isfinite(a).all() and relerr(a, b) <= 1e-11
