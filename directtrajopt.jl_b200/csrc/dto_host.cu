@@ -930,7 +930,8 @@ extern "C" int dto_create(const dto_problem_desc* d, dto_handle** out) {
             if (!(sp && strcmp(sp, "0") == 0))
                 for (int i = 0; i < P.n_int; ++i) {
                     DInt& I = P.in[i];
-                    if (I.kind != DTO_INT_BILINEAR || I.variant != DTO_VAR_PERSISTENT) continue;  // n = 8 / 16 (octet): a plan costs what it saves
+                    if (I.kind != DTO_INT_BILINEAR || I.variant < DTO_VAR_PERSISTENT) continue;
+                    if (I.variant == DTO_VAR_OCTET && !(sp && strcmp(sp, "all") == 0)) continue;  // n = 8 / 16: see DESIGN.md section 3 (DTO_B200_SERIES_PLAN=all)
                     const dto_integrator_desc& sd = d->integrators[i];
                     if (sd.G_batch_stride != 0 || series_plan_smem(I.n, I.m) == 0) continue;  // shared sets that fit shared memory
                     std::vector<float> pm;
