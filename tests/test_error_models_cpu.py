@@ -134,3 +134,19 @@ def test_error_model_against_a_rotation(theta):
         assert err <= 2.0 * model + 3e-14, (K, err, model)  # the alternating extrapolation weights amplify round-off to ~1e-14 at K = 8
         if model > 1e-13:
             assert err >= model / 100.0, (K, err, model)
+
+
+def test_bench_counts_the_executed_right_hand_sides(monkeypatch):
+    """bench.py's host restatement of tdb_item_steps: config c3 (theta ~ 0.2 per interval) runs 5 extrapolation columns = 35
+    right-hand sides per interval; DTO_B200_TDB_TOL=0 restores eight columns = 80 (count C3 of BASELINE.md section 3)."""
+    import os, sys
+
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+
+    prob = bench.build_problem("c3", 42)
+    monkeypatch.delenv("DTO_B200_TDB_TOL", raising=False)
+    assert bench.tdb_rhs_per_interval(prob, prob.trajectory.datavec) == 35.0
+    monkeypatch.setenv("DTO_B200_TDB_TOL", "0")
+    assert bench.tdb_rhs_per_interval(prob, prob.trajectory.datavec) == 80.0
+    assert bench.canonical_flops_per_tdb_interval(64, 2, 1, rhs=80) == pytest.approx(100.3e6, rel=2e-3)
