@@ -122,7 +122,10 @@ __global__ void __launch_bounds__(512) series_plan_kernel(DProb P, int ii, const
                     dtt = dt[t];
                 }
             // FP32 rounding of the sums, added: the plan stays an upper bound
-            const double theta1 = dtt * (n1 + 1e-5 * gs1), d2 = dtt * sqrt(n2 + 1e-5 * gs1 * gs1);
+            double theta1 = dtt * (n1 + 1e-5 * gs1), d2 = dtt * sqrt(n2 + 1e-5 * gs1 * gs1);
+            // an iterate whose crude bound dt sum_a |w_a| ||G_a||_1 is not finite or absurd may have overflowed the FP32 sums
+            // (and fmaxf drops NaN): hand the crude bound on, the interval kernels turn it into NaN outputs (choose_series)
+            if (!(dtt * gs1 < 1e7)) theta1 = d2 = dtt * gs1;
             // alpha: an argument with T(alpha) = min(T(theta1), T(d2) + 1)
             double alpha = theta1;
             if (theta1 < 1e8 && d2 < theta1) {

@@ -532,3 +532,20 @@ def test_tdb_extrapolation_columns_sized_per_interval(monkeypatch):
         ev.close()
     for a, b in zip(outs["0"], outs["1e-14"]):
         assert np.isfinite(a).all() and relerr(a, b) <= 1e-11
+
+
+def test_absurd_drive_poisons_a_planned_interval():
+    """The series plan sums in FP32: a drive amplitude that overflows it (or is NaN) must still end as NaN outputs of that
+    interval, not as a short series over a huge generator."""
+    prob = pt.quantum_gate_problem(N=6, levels=16, n_drives=4)
+    ev = dto.Evaluator(prob)
+    spec = prob.to_spec()
+    z, u_off = spec["z"], spec["components"]["u"][0]
+    for bad in (1e200, np.nan):
+        Z = prob.trajectory.vec().copy()
+        Z[3 * z + u_off] = bad
+        g = np.empty(ev.n_constraints)
+        ev.eval_constraint(g, Z)
+        n = prob.integrators[0].x_dim
+        assert np.isnan(g[3 * n:4 * n]).all() and np.isfinite(g[:3 * n]).all() and np.isfinite(g[4 * n:5 * n]).all()
+    ev.close()
