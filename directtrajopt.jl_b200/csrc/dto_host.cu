@@ -965,7 +965,15 @@ extern "C" int dto_create(const dto_problem_desc* d, dto_handle** out) {
             // ~100 us): two ranges; the octet kernel's items are small: four
             bool persistent = false;
             for (int i = 0; i < P.n_int; ++i) persistent |= P.in[i].kind == DTO_INT_BILINEAR && P.in[i].variant == DTO_VAR_PERSISTENT;
-            if (persistent) h->pipeline_fracs = {0.5};
+            bool tdbi = false;
+            for (int i = 0; i < P.n_int; ++i) tdbi |= P.in[i].kind == DTO_INT_TDBILINEAR;
+            if (tdbi) {
+                // one CTA per SM works through the intervals of a range in rounds (~1 ms each at n = 64): boundaries at
+                // multiples of two full rounds, so that cutting costs no partial round (c3: 296 / 592 / 888 of 999)
+                int sms = 148;
+                cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+                for (int k = 2 * sms; k + sms / 2 < P.nI; k += 2 * sms) h->pipeline_fracs.push_back((k + 0.5) / (double)std::max(P.nI, 1));
+            } else if (persistent) h->pipeline_fracs = {0.5};
             else h->pipeline_fracs = {0.1, 0.4, 0.7};
         }
         else if (strcmp(env, "0") != 0) {
@@ -1414,12 +1422,17 @@ static int run_eval(dto_handle* h, const double* dZ, double sigma, const double*
     return DTO_OK;
 }
 
-// Every interval kernel of the problem honours DProb::kc0/kc1 (the persistent and octet bilinear variants do)
+// Every interval kernel of the problem honours DProb::kc0/kc1 (the persistent and octet bilinear variants and the
+// time-dependent kernels do).  Cross-knot Hessian blocks (time-dependent integrator, linear spline) are fine: the assembler
+// of a range reads the compact second derivatives of interval kc0 - 1, which the range before it wrote.
 static bool range_capable(const dto_handle* h) {
     const DProb& P = h->P;
-    if (P.batch != 1 || P.any_cross || P.gl.G > 0) return false;
-    for (int i = 0; i < P.n_int; ++i)
-        if (P.in[i].kind != DTO_INT_DERIVATIVE && !(P.in[i].kind == DTO_INT_BILINEAR && P.in[i].variant >= DTO_VAR_PERSISTENT)) return false;
+    if (P.batch != 1 || P.gl.G > 0) return false;
+    for (int i = 0; i < P.n_int; ++i) {
+        const DInt& I = P.in[i];
+        if (I.kind == DTO_INT_DERIVATIVE || I.kind == DTO_INT_TDBILINEAR) continue;
+        if (!(I.kind == DTO_INT_BILINEAR && I.variant >= DTO_VAR_PERSISTENT)) return false;
+    }
     return true;
 }
 

@@ -20,6 +20,7 @@
 // This is the correctness-first CUDA-core variant (LDS-bound dot products); DESIGN.md lists the DMMA port as
 // the next step for BASELINE config c3.
 #include "dto_internal.h"
+#include <algorithm>
 
 namespace {
 
@@ -213,7 +214,8 @@ __global__ void __launch_bounds__(kThreads) tdb_kernel(DProb P, int ii, const do
     extern __shared__ double sm[];
     const DInt& I = P.in[ii];
     const int n = I.n, m = I.m, z = P.z, tid = threadIdx.x, nt = blockDim.x;
-    const int b = blockIdx.x / P.nI, kl = blockIdx.x % P.nI;
+    const int nIc = min(P.kc1, P.nI) - P.kc0;  // intervals of the active range
+    const int b = blockIdx.x / nIc, kl = P.kc0 + blockIdx.x % nIc;
     int role = blockIdx.y;
     if (role == 1 && !want_jac) role = ROLE_ADJ;
     const double* zk = Z + (long long)b * P.n_vars_local + (long long)kl * z;
@@ -407,14 +409,15 @@ bool tdb_available() { return true; }
 void launch_tdb(const DProb& P, int ii, const double* Z, const double* mu, double* g, double* jac, EvalFlags f, cudaStream_t st,
                 long long* launches) {
     const DInt& I = P.in[ii];
-    if (P.nI <= 0) return;
+    const int nIc = std::min(P.kc1, P.nI) - P.kc0;
+    if (nIc <= 0) return;
     const size_t smem = tdb_smem_bytes(I, f.want_jac, f.want_hess);
     static PerDeviceOnce configured;
     if (configured.first()) {
         cudaFuncSetAttribute(tdb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     }
     const int K = 8;
-    dim3 grid((unsigned)(P.nI * P.batch), 1 + (f.want_jac ? 1 : 0) + (f.want_hess ? 1 : 0));
+    dim3 grid((unsigned)(nIc * P.batch), 1 + (f.want_jac ? 1 : 0) + (f.want_hess ? 1 : 0));
     tdb_kernel<<<grid, kThreads, smem, st>>>(P, ii, Z, mu, f.want_g ? g : nullptr, jac, f.want_jac ? 1 : 0, f.want_hess ? 1 : 0, K);
     ++*launches;
 }

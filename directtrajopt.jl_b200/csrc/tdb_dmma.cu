@@ -562,9 +562,10 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
 
     // PG/Pb and PGa/PT are laid out back to back: table t of the forward set is PG + t*8n, of the adjoint set PGa + t*n
 
-    const int n_items = P.nI * P.batch;
+    const int nIc = min(P.kc1, P.nI) - P.kc0;  // intervals of the active range
+    const int n_items = nIc * P.batch;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-    const int b = item / P.nI, kl = item % P.nI;
+    const int b = item / nIc, kl = P.kc0 + item % nIc;
     const double* zk = Z + (long long)b * P.n_vars_local + (long long)kl * z;
     const double* zk1 = zk + z;
     if (P.halo != nullptr && kl + 1 == P.nK - 1) zk1 = P.halo;
@@ -1039,9 +1040,10 @@ __global__ void __launch_bounds__(8 * 32, 1)
         else assemble_generators<NT, false, kMaxM, kMaxC>(Gd, nullptr, Bs, I, S, S, m, nc, false, eb0, eb1, lane);
     };
 
-    const int n_items = P.nI * P.batch;
+    const int nIc = min(P.kc1, P.nI) - P.kc0;
+    const int n_items = nIc * P.batch;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int b = item / P.nI, kl = item % P.nI;
+        const int b = item / nIc, kl = P.kc0 + item % nIc;
         const double* zk = Z + (long long)b * P.n_vars_local + (long long)kl * z;
         const double* zk1 = zk + z;
         if (P.halo != nullptr && kl + 1 == P.nK - 1) zk1 = P.halo;
@@ -1219,7 +1221,7 @@ void launch_nt_w(const DProb& P, int ii, const double* Z, const double* mu, doub
         cudaFuncSetAttribute(tdb_exp_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     }
     const DInt& I = P.in[ii];
-    const int ctas = std::min(P.nI * P.batch, I.tdb_scratch_ctas / 2);  // persistent: one CTA per SM
+    const int ctas = std::min((std::min(P.kc1, P.nI) - P.kc0) * P.batch, I.tdb_scratch_ctas / 2);  // persistent: one CTA per SM
     if (!pl.split) {
         kern<<<ctas, pl.warps * 32, pl.smem, st>>>(P, ii, Z, mu, f.want_g ? g : nullptr, jac, f.want_jac ? 1 : 0, f.want_hess ? 1 : 0, 8,
                                                    pl.TF, pl.TE, pl.TA, 0, pl.nbs, I.tdb_scratch);
@@ -1252,7 +1254,7 @@ bool tdb_dmma_supported(const DInt& I) {
 bool launch_tdb_dmma(const DProb& P, int ii, const double* Z, const double* mu, double* g, double* jac, EvalFlags f, cudaStream_t st,
                      long long* launches) {
     const DInt& I = P.in[ii];
-    if (P.nI <= 0) return true;
+    if (std::min(P.kc1, P.nI) - P.kc0 <= 0) return true;
     Plan pl;
     if (!make_plan(I, f.want_jac, f.want_hess, pl)) return false;
     switch (I.n / 8) {
